@@ -1,0 +1,167 @@
+// fft.cuh -- warp-cooperative real FFTs in shared memory.
+//
+// One warp transforms one frame.  A real frame of N samples is viewed as
+// H = N/2 complex points z[n] = x[2n] + i x[2n+1] (which is simply the frame as
+// it lies in memory), transformed by an in-place Stockham autosort FFT whose
+// radix-8/4/2 butterflies live in registers, and then split into the N/2+1
+// bins of the real transform.  Between passes the lanes exchange data through a
+// padded shared-memory buffer (FPAD) so that both the strided and the
+// contiguous side of every pass stay (almost) bank-conflict free.
+//
+// Twiddles come from exactly rounded tables (computed on the host in long
+// double): tw_h[i] = exp(-2 pi i/H), tw_n[k] = exp(-2 pi k/N).
+#pragma once
+#include "common.cuh"
+
+namespace ds {
+
+// element index -> padded element index (one pad element every 8)
+__host__ __device__ __forceinline__ constexpr int FPAD(int i) { return i + (i >> 3); }
+// number of V2 elements a frame buffer needs (H+1 bins, padded)
+__host__ __device__ constexpr int fft_buf_elems(int n_fft) { return FPAD(n_fft / 2 + 1) + 1; }
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+// multiply by -i : (x + iy)(-i) = y - ix
+template <typename C> __device__ __forceinline__ C cmul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
+
+template <typename C> __device__ __forceinline__ void dft2(C *v) {
+  C a = v[0], b = v[1];
+  v[0] = cadd(a, b); v[1] = csub(a, b);
+}
+template <typename C> __device__ __forceinline__ void dft4(C &x0, C &x1, C &x2, C &x3) {
+  C t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = cmul_mi(csub(x1, x3));
+  x0 = cadd(t0, t2); x2 = csub(t0, t2); x1 = cadd(t1, t3); x3 = csub(t1, t3);
+}
+template <typename T, typename C> __device__ __forceinline__ void dft8(C *v) {
+  // even / odd 4-point DFTs, then combine with W8^k
+  C e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  C o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4(e0, e1, e2, e3);
+  dft4(o0, o1, o2, o3);
+  const T h = (T)0.70710678118654752440;
+  C w1; w1.x = (o1.x + o1.y) * h; w1.y = (o1.y - o1.x) * h;   // o1 * (1-i)/sqrt2
+  C w2 = cmul_mi(o2);                                          // o2 * (-i)
+  C w3; w3.x = (o3.y - o3.x) * h; w3.y = -(o3.x + o3.y) * h;  // o3 * (-1-i)/sqrt2
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, w1); v[5] = csub(e1, w1);
+  v[2] = cadd(e2, w2); v[6] = csub(e2, w2);
+  v[3] = cadd(e3, w3); v[7] = csub(e3, w3);
+}
+
+template <int H, int NS, typename T> struct FftPass {
+  typedef typename V2<T>::type C;
+  static constexpr int REM = H / NS;
+  static constexpr int R = (REM % 8 == 0) ? 8 : ((REM % 4 == 0) ? 4 : 2);
+  static constexpr int NB = H / R;                  // butterflies in this pass
+  static constexpr int PER = (NB + 31) / 32;        // per lane
+
+  __device__ __forceinline__ static void run(C *buf, const C *__restrict__ tw, int lane) {
+    C v[PER][R];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = lane + 32 * i;
+      if (NB % 32 == 0 || j < NB) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[i][r] = buf[FPAD(j + r * NB)];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = lane + 32 * i;
+      if (NB % 32 == 0 || j < NB) {
+        const int k = j & (NS - 1);
+        if (NS > 1) {
+          constexpr int TSTEP = H / (NS * R);
+#pragma unroll
+          for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], tw[r * k * TSTEP]);
+        }
+        if (R == 8) dft8<T>(v[i]);
+        else if (R == 4) dft4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        else dft2(v[i]);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[FPAD(j0 + r * NS)] = v[i][r];
+      }
+    }
+    __syncwarp();
+    if constexpr (NS * R < H) FftPass<H, NS * R, T>::run(buf, tw, lane);
+  }
+};
+
+// in-place forward complex FFT of H points held in buf[FPAD(i)], one warp
+template <int H, typename T>
+__device__ __forceinline__ void warp_cfft(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h, int lane) {
+  FftPass<H, 1, T>::run(buf, tw_h, lane);
+}
+
+// Forward real FFT of N = 2H samples.  On entry buf[FPAD(n)] = (x[2n], x[2n+1]);
+// on exit buf[FPAD(k)] = X[k], k = 0..H.   (numpy.fft.rfft)
+template <int N, typename T>
+__device__ __forceinline__ void warp_rfft(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h,
+                                          const typename V2<T>::type *__restrict__ tw_n, int lane) {
+  typedef typename V2<T>::type C;
+  constexpr int H = N / 2;
+  warp_cfft<H, T>(buf, tw_h, lane);
+  // split: pair (k, H-k).  s = a + conj(b), d = a - conj(b), e = (i/2) W^k d
+  // X[k] = s/2 - e ; X[H-k] = conj(s/2 + e)
+  for (int k = lane; k <= H / 2; k += 32) {
+    if (k == 0) {
+      C a = buf[FPAD(0)];
+      buf[FPAD(0)] = mk2<T>(a.x + a.y, (T)0);
+      buf[FPAD(H)] = mk2<T>(a.x - a.y, (T)0);
+    } else {
+      C a = buf[FPAD(k)], b = buf[FPAD(H - k)];
+      C w = tw_n[k];
+      T sx = (T)0.5 * (a.x + b.x), sy = (T)0.5 * (a.y - b.y);
+      T dx = (T)0.5 * (a.x - b.x), dy = (T)0.5 * (a.y + b.y);
+      // e = i * (w * d)
+      T px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;
+      T ex = -py, ey = px;
+      buf[FPAD(k)] = mk2<T>(sx - ex, sy - ey);
+      buf[FPAD(H - k)] = mk2<T>(sx + ex, -(sy + ey));
+    }
+  }
+  __syncwarp();
+}
+
+// Inverse real FFT.  On entry buf[FPAD(k)] = Y[k], k = 0..H (imaginary parts of
+// Y[0], Y[H] are ignored like numpy.fft.irfft); on exit buf[FPAD(n)] =
+// (x[2n], x[2n+1]) * N, i.e. UNSCALED -- the caller folds 1/N into its window.
+template <int N, typename T>
+__device__ __forceinline__ void warp_irfft_unscaled(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h,
+                                                    const typename V2<T>::type *__restrict__ tw_n, int lane) {
+  typedef typename V2<T>::type C;
+  constexpr int H = N / 2;
+  // merge: Z[k] = s + f, Z[H-k] = conj(s - f), s = a + conj(b), d = a - conj(b),
+  // f = i conj(W^k) d   (everything x2 relative to numpy; total scale N)
+  // we store conj(Z) so that a forward FFT followed by a conjugate is the inverse.
+  for (int k = lane; k <= H / 2; k += 32) {
+    if (k == 0) {
+      T a = buf[FPAD(0)].x, b = buf[FPAD(H)].x;
+      buf[FPAD(0)] = mk2<T>(a + b, -(a - b));
+    } else {
+      C a = buf[FPAD(k)], b = buf[FPAD(H - k)];
+      C w = tw_n[k];
+      T sx = a.x + b.x, sy = a.y - b.y;
+      T dx = a.x - b.x, dy = a.y + b.y;
+      // conj(w) * d
+      T px = w.x * dx + w.y * dy, py = w.x * dy - w.y * dx;
+      T fx = -py, fy = px;
+      buf[FPAD(k)] = mk2<T>(sx + fx, -(sy + fy));          // conj(Z[k])
+      buf[FPAD(H - k)] = mk2<T>(sx - fx, (sy - fy));       // conj(Z[H-k]) = s - f
+    }
+  }
+  __syncwarp();
+  warp_cfft<H, T>(buf, tw_h, lane);
+  // result r[n] = conj(z[n]) * (2H): x[2n] = r.x, x[2n+1] = -r.y
+  for (int n = lane; n < H; n += 32) {
+    C r = buf[FPAD(n)];
+    r.y = -r.y;
+    buf[FPAD(n)] = r;
+  }
+  __syncwarp();
+}
+
+}  // namespace ds

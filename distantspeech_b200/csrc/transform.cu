@@ -1,0 +1,518 @@
+// transform.cu -- batched STFT / ISTFT kernels and the fused fixed beamformer.
+//
+// Reference behaviour restated (file:line relative to the reference tree):
+//   stft            DistantSpeech/transform/transform.py:10-221   (complex64 result, :212)
+//   istft           transform.py:237-404 + __overlap_add :224-234 (float32 OLA, no window-sum norm)
+//   Transform       transform.py:407-496 (streaming history/tail, hop/W0 scaling :479)
+//   FixedBeamformer beamformer/fixedbeamformer.py:147-207 (Y = sum_m conj(W) X, :163)
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace ds {
+
+// ===========================================================================
+// STFT
+// ===========================================================================
+struct StftArgs {
+  const float *x; float *history; void *X; const double *window;
+  int S, C, Ns, T, hop, mode, out_c128;
+};
+
+constexpr int STFT_WARPS = 4;
+
+template <int N, typename T>
+__global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const typename V2<T>::type *__restrict__ tw_h,
+                                                              const typename V2<T>::type *__restrict__ tw_n) {
+  typedef typename V2<T>::type C2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = N / 2, K = H + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  C2 *buf = reinterpret_cast<C2 *>(smem_raw) + warp * fft_buf_elems(N);
+  T *fbuf = reinterpret_cast<T *>(buf);
+  const long long total = (long long)a.S * a.C * a.T;
+  const int ov = N - a.hop;
+  for (long long f = (long long)blockIdx.x * STFT_WARPS + warp; f < total; f += (long long)gridDim.x * STFT_WARPS) {
+    const int t = (int)(f % a.T);
+    const int c = (int)((f / a.T) % a.C);
+    const int s = (int)(f / ((long long)a.T * a.C));
+    const float *xs = a.x + ((long long)s * a.C + c) * a.Ns;
+    const float *hs = a.history ? a.history + ((long long)s * a.C + c) * ov : nullptr;
+    for (int n = lane; n < N; n += 32) {
+      int g;
+      float v;
+      if (a.mode == DS_STFT_STREAMING) {
+        g = t * a.hop + n - ov;
+        v = (g < 0) ? hs[ov + g] : xs[g];
+      } else if (a.mode == DS_STFT_CENTER) {
+        g = t * a.hop + n - N / 2;
+        if (g < 0) g = -g;
+        if (g >= a.Ns) g = 2 * (a.Ns - 1) - g;
+        v = xs[g];
+      } else {
+        g = t * a.hop + n;
+        v = xs[g];
+      }
+      // complex element n/2, component n&1, padded per complex element
+      fbuf[2 * FPAD(n >> 1) + (n & 1)] = (T)v * (T)a.window[n];
+    }
+    __syncwarp();
+    warp_rfft<N, T>(buf, tw_h, tw_n, lane);
+    const long long obase = (((long long)s * a.T + t) * a.C + c) * K;
+    if (a.out_c128) {
+      double2 *out = reinterpret_cast<double2 *>(a.X) + obase;
+      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD(k)]; out[k] = make_double2((double)v.x, (double)v.y); }
+    } else {
+      float2 *out = reinterpret_cast<float2 *>(a.X) + obase;
+      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD(k)]; out[k] = make_float2((float)v.x, (float)v.y); }
+    }
+    __syncwarp();
+  }
+}
+
+// history <- last `ov` samples of concat(history, x)        (transform.py:451)
+__global__ void stft_history_kernel(const float *x, float *history, int Ns, int ov) {
+  const long long sc = blockIdx.x;
+  const float *xs = x + sc * Ns;
+  float *hs = history + sc * ov;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = threadIdx.x + i * blockDim.x;
+    if (idx < ov) {
+      int g = Ns + idx;  // index into concat(history[ov], x[Ns])
+      v[i] = (g < ov) ? hs[g] : xs[g - ov];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = threadIdx.x + i * blockDim.x;
+    if (idx < ov) hs[idx] = v[i];
+  }
+}
+
+template <int N, typename T>
+static int launch_stft(const StftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+  const size_t smem = (size_t)STFT_WARPS * fft_buf_elems(N) * sizeof(typename V2<T>::type);
+  auto kern = stft_kernel<N, T>;
+  if (smem > 48 * 1024) DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long total = (long long)a.S * a.C * a.T;
+  long long blocks = (total + STFT_WARPS - 1) / STFT_WARPS;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, STFT_WARPS * 32, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw));
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
+template <typename T>
+static int dispatch_stft(int n_fft, const StftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+  switch (n_fft) {
+    case 128: return launch_stft<128, T>(a, tw, st);
+    case 256: return launch_stft<256, T>(a, tw, st);
+    case 512: return launch_stft<512, T>(a, tw, st);
+    case 1024: return launch_stft<1024, T>(a, tw, st);
+    case 2048: return launch_stft<2048, T>(a, tw, st);
+  }
+  set_error("unsupported n_fft %d", n_fft);
+  return DS_EUNSUPPORTED;
+}
+
+// ===========================================================================
+// ISTFT
+// ===========================================================================
+struct IstftArgs {
+  const void *Y; float *y; float *tail; const double *window;
+  int S, C, T, hop, mode, n_out, in_c128;  // n_out = samples written per (s,c)
+  double scale;
+};
+
+constexpr int ISTFT_WARPS = 4;
+constexpr int ISTFT_TILE = 8;   // output hop-blocks per CTA
+constexpr int ISTFT_MAXR = 8;   // max overlapping frames per sample
+
+// Windowed inverse transform of frame t of (s,c) into dst[0..N) (float).
+template <int N, typename T>
+__device__ __forceinline__ void istft_frame(const IstftArgs &a, int s, int c, int t, typename V2<T>::type *buf,
+                                            const typename V2<T>::type *tw_h, const typename V2<T>::type *tw_n,
+                                            float *dst, int lane) {
+  typedef typename V2<T>::type C2;
+  constexpr int H = N / 2, K = H + 1;
+  const long long ibase = (((long long)s * a.T + t) * a.C + c) * K;
+  if (a.in_c128) {
+    const double2 *in = reinterpret_cast<const double2 *>(a.Y) + ibase;
+    for (int k = lane; k < K; k += 32) { double2 v = in[k]; buf[FPAD(k)] = mk2<T>((T)v.x, (T)v.y); }
+  } else {
+    const float2 *in = reinterpret_cast<const float2 *>(a.Y) + ibase;
+    for (int k = lane; k < K; k += 32) { float2 v = in[k]; buf[FPAD(k)] = mk2<T>((T)v.x, (T)v.y); }
+  }
+  __syncwarp();
+  warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
+  const T *fb = reinterpret_cast<const T *>(buf);
+  const T inv_n = (T)1 / (T)N;
+  for (int n = lane; n < N; n += 32) {
+    T v = fb[2 * FPAD(n >> 1) + (n & 1)] * inv_n;      // numpy irfft value
+    dst[n] = (float)((double)v * a.window[n]);         // ifft_window * irfft   (:368)
+  }
+  __syncwarp();
+}
+
+// One CTA = (s, c, tile of ISTFT_TILE hop-blocks).  Frames that touch the tile
+// are inverse-transformed into shared memory (halo frames recomputed), then each
+// output sample adds its frames in increasing frame order in float32, exactly
+// like the reference's float32 += accumulation.
+template <int N, typename T>
+__global__ void __launch_bounds__(ISTFT_WARPS * 32) istft_kernel(IstftArgs a, const typename V2<T>::type *__restrict__ tw_h,
+                                                                const typename V2<T>::type *__restrict__ tw_n,
+                                                                int R, int tail_pass) {
+  typedef typename V2<T>::type C2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  C2 *fftbuf = reinterpret_cast<C2 *>(smem_raw) + warp * fft_buf_elems(N);
+  float *frames = reinterpret_cast<float *>(reinterpret_cast<C2 *>(smem_raw) + ISTFT_WARPS * fft_buf_elems(N));
+  const int ov = N - a.hop;
+  const int sc = blockIdx.y;
+  const int s = sc / a.C, c = sc % a.C;
+  const int total_len = a.T * a.hop + ov;                     // OLA buffer length
+  // tile of hop-blocks [b0, b1)
+  int b0, b1;
+  if (!tail_pass) {
+    b0 = blockIdx.x * ISTFT_TILE;
+    b1 = min(b0 + ISTFT_TILE, (a.n_out + a.hop - 1) / a.hop);
+  } else {  // blocks covering [T*hop, T*hop+ov)
+    b0 = a.T;
+    b1 = (total_len + a.hop - 1) / a.hop;
+  }
+  const int tf0 = max(0, b0 - R + 1), tf1 = min(a.T - 1, b1 - 1);   // frames needed (inclusive)
+  for (int t = tf0 + warp; t <= tf1; t += ISTFT_WARPS)
+    istft_frame<N, T>(a, s, c, t, fftbuf, tw_h, tw_n, frames + (size_t)(t - tf0) * N, lane);
+  __syncthreads();
+  const int g0 = b0 * a.hop;
+  const int g1 = tail_pass ? total_len : min(b1 * a.hop, a.n_out);
+  float *ys = a.y + (long long)sc * a.n_out;
+  float *tl = a.tail ? a.tail + (long long)sc * ov : nullptr;
+  // tail pass: every thread first computes its values (reads old tail), then all write
+  float keep[(ISTFT_MAXR * 2048 / 8) / (ISTFT_WARPS * 32) + 1];
+  int nkeep = 0;
+  for (int g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+    int t_hi = min(a.T - 1, g / a.hop);
+    int t_lo = (g - N + 1 + a.hop - 1);
+    t_lo = (t_lo <= 0) ? 0 : t_lo / a.hop;
+    float acc = 0.0f;
+    for (int t = t_lo; t <= t_hi; ++t) acc = acc + frames[(size_t)(t - tf0) * N + (g - t * a.hop)];
+    if (a.mode == DS_STFT_STREAMING) {
+      if (g < ov) acc = acc + tl[g];                          // x[:overlap] += previous_output (:476)
+      if (!tail_pass) ys[g] = (float)((double)acc * a.scale);  // :479
+      else keep[nkeep++] = acc;
+    } else {
+      ys[g] = acc;
+    }
+  }
+  if (tail_pass) {
+    __syncthreads();
+    nkeep = 0;
+    for (int g = g0 + threadIdx.x; g < g1; g += blockDim.x) tl[g - a.T * a.hop] = keep[nkeep++];
+  }
+}
+
+template <int N, typename T>
+static int launch_istft(const IstftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+  const int R = (N + a.hop - 1) / a.hop;
+  if (R > ISTFT_MAXR) { set_error("istft: hop %d < n_fft/8 unsupported", a.hop); return DS_EUNSUPPORTED; }
+  const int max_frames = ISTFT_TILE + R - 1 + R;   // tail pass may need up to 2R-2 frames
+  const size_t smem = (size_t)ISTFT_WARPS * fft_buf_elems(N) * sizeof(typename V2<T>::type) + (size_t)max_frames * N * sizeof(float);
+  auto kern = istft_kernel<N, T>;
+  DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblk = (a.n_out + a.hop - 1) / a.hop;
+  dim3 grid((nblk + ISTFT_TILE - 1) / ISTFT_TILE, a.S * a.C);
+  if (grid.x > 0 && grid.y > 0) {
+    kern<<<grid, ISTFT_WARPS * 32, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw), R, 0);
+    DS_LAUNCH_CHECK();
+  }
+  if (a.mode == DS_STFT_STREAMING && a.tail && N > a.hop) {
+    dim3 g2(1, a.S * a.C);
+    kern<<<g2, ISTFT_WARPS * 32, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw), R, 1);
+    DS_LAUNCH_CHECK();
+  }
+  return DS_OK;
+}
+
+template <typename T>
+static int dispatch_istft(int n_fft, const IstftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+  switch (n_fft) {
+    case 128: return launch_istft<128, T>(a, tw, st);
+    case 256: return launch_istft<256, T>(a, tw, st);
+    case 512: return launch_istft<512, T>(a, tw, st);
+    case 1024: return launch_istft<1024, T>(a, tw, st);
+    case 2048: return launch_istft<2048, T>(a, tw, st);
+  }
+  set_error("unsupported n_fft %d", n_fft);
+  return DS_EUNSUPPORTED;
+}
+
+// ===========================================================================
+// fused fixed beamformer:  STFT -> sum_m conj(W) X -> ISTFT/OLA, one kernel
+// ===========================================================================
+// State blob: int parity (+pad to 16 B), then two halves, each
+//   history [S][M][ov] float32 ; tail [S][B][ov] float32.
+// The kernel reads half `parity`, writes half `1-parity`; a trailing 1-thread
+// kernel flips the parity, so segments of one stream never race on the state.
+struct FixedBfArgs {
+  const float *x; float *y; const float2 *W; const double *window;
+  unsigned char *state;
+  int S, M, B, Ns, T, hop, segs, frames_per_seg;
+  double scale;
+};
+
+constexpr int FBF_WARPS = 8;
+
+__host__ __device__ inline size_t fbf_half_bytes(int S, int M, int B, int ov) {
+  return ((size_t)S * M * ov + (size_t)S * B * ov) * sizeof(float);
+}
+
+template <int N>
+__global__ void __launch_bounds__(FBF_WARPS * 32) fixedbf_kernel(FixedBfArgs a, const float2 *__restrict__ tw_h,
+                                                                const float2 *__restrict__ tw_n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = N / 2, K = H + 1;
+  constexpr int BE = fft_buf_elems(N);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int ov = N - a.hop;
+  const int R = N / a.hop;                       // hop divides N (checked on host)
+  // smem carve-up
+  float2 *micbuf = reinterpret_cast<float2 *>(smem_raw);           // [M][BE]
+  float2 *beambuf = micbuf + (size_t)a.M * BE;                     // [B][BE]
+  float *ola = reinterpret_cast<float *>(beambuf + (size_t)a.B * BE);   // [B][N] ring accumulator
+  float *win = ola + (size_t)a.B * N;                              // [N]
+  for (int n = tid; n < N; n += blockDim.x) win[n] = (float)a.window[n];
+  for (int i = tid; i < a.B * N; i += blockDim.x) ola[i] = 0.0f;
+
+  const int s = blockIdx.x / a.segs, seg = blockIdx.x % a.segs;
+  const int t0 = seg * a.frames_per_seg;
+  const int t1 = min(a.T, t0 + a.frames_per_seg);
+  const int parity = *reinterpret_cast<const int *>(a.state);
+  const size_t half = fbf_half_bytes(a.S, a.M, a.B, ov);
+  const float *hist_in = reinterpret_cast<const float *>(a.state + 16 + (size_t)parity * half);
+  const float *tail_in = hist_in + (size_t)a.S * a.M * ov;
+  float *hist_out = reinterpret_cast<float *>(a.state + 16 + (size_t)(1 - parity) * half);
+  float *tail_out = hist_out + (size_t)a.S * a.M * ov;
+  __syncthreads();
+
+  const float inv_n = 1.0f / (float)N;
+  // frames before t0 that still overlap the segment's first output block are
+  // recomputed (halo) so that each segment is self-contained.
+  const int th0 = max(0, t0 - (R - 1));
+  for (int t = th0; t < t1; ++t) {
+    // ---- analysis: one warp per mic ------------------------------------
+    for (int m = warp; m < a.M; m += FBF_WARPS) {
+      const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
+      const float *hs = hist_in + ((long long)s * a.M + m) * ov;
+      float2 *buf = micbuf + (size_t)m * BE;
+      float *fb = reinterpret_cast<float *>(buf);
+      for (int n = lane; n < N; n += 32) {
+        int g = t * a.hop + n - ov;
+        float v = (g < 0) ? hs[ov + g] : xs[g];
+        fb[2 * FPAD(n >> 1) + (n & 1)] = v * win[n];
+      }
+      __syncwarp();
+      warp_rfft<N, float>(buf, tw_h, tw_n, lane);
+    }
+    __syncthreads();
+    // ---- weights: Y_b[k] = sum_m conj(W[b,k,m]) X_m[k] --------------------
+    for (int i = tid; i < a.B * K; i += blockDim.x) {
+      const int b = i / K, k = i - b * K;
+      const float2 *w = a.W + ((size_t)b * K + k) * a.M;
+      float yr = 0.f, yi = 0.f;
+      for (int m = 0; m < a.M; ++m) {
+        float2 xv = micbuf[(size_t)m * BE + FPAD(k)];
+        float2 wv = __ldg(w + m);
+        yr += wv.x * xv.x + wv.y * xv.y;
+        yi += wv.x * xv.y - wv.y * xv.x;
+      }
+      beambuf[(size_t)b * BE + FPAD(k)] = make_float2(yr, yi);
+    }
+    __syncthreads();
+    // ---- synthesis + overlap-add: one warp per beam -------------------------
+    for (int b = warp; b < a.B; b += FBF_WARPS) {
+      float2 *buf = beambuf + (size_t)b * BE;
+      warp_irfft_unscaled<N, float>(buf, tw_h, tw_n, lane);
+      const float *fb = reinterpret_cast<const float *>(buf);
+      float *acc = ola + (size_t)b * N;
+      // ring: sample g lives at acc[g % N]
+      for (int n = lane; n < N; n += 32) {
+        float v = fb[2 * FPAD(n >> 1) + (n & 1)] * inv_n * win[n];
+        int pos = (t * a.hop + n) & (N - 1);
+        acc[pos] = acc[pos] + v;
+      }
+      __syncwarp();
+      // samples [t*hop, (t+1)*hop) are complete now
+      if (t >= t0) {
+        float *ys = a.y + ((long long)s * a.B + b) * a.Ns;
+        const float *tl = tail_in + ((long long)s * a.B + b) * ov;
+        for (int j = lane; j < a.hop; j += 32) {
+          int g = t * a.hop + j;
+          int pos = g & (N - 1);
+          float v = acc[pos];
+          if (g < ov) v = v + tl[g];
+          ys[g] = (float)((double)v * a.scale);
+          acc[pos] = 0.0f;
+        }
+      } else {
+        for (int j = lane; j < a.hop; j += 32) acc[(t * a.hop + j) & (N - 1)] = 0.0f;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  // ---- new state (last segment of each stream) ----------------------------
+  if (t1 == a.T && seg == a.segs - 1) {
+    for (int i = tid; i < a.B * ov; i += blockDim.x) {
+      int b = i / ov, j = i - b * ov;
+      int g = a.T * a.hop + j;
+      float v = ola[(size_t)b * N + (g & (N - 1))];
+      if (g < ov) v = v + tail_in[((long long)s * a.B + b) * ov + g];
+      tail_out[((long long)s * a.B + b) * ov + j] = v;
+    }
+    for (int i = tid; i < a.M * ov; i += blockDim.x) {
+      int m = i / ov, j = i - m * ov;
+      int g = a.Ns + j;  // index into concat(history, x)
+      const float *hs = hist_in + ((long long)s * a.M + m) * ov;
+      const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
+      hist_out[((long long)s * a.M + m) * ov + j] = (g < ov) ? hs[g] : xs[g - ov];
+    }
+  }
+}
+
+__global__ void flip_parity_kernel(unsigned char *state) {
+  int *p = reinterpret_cast<int *>(state);
+  *p = 1 - *p;
+}
+
+template <int N>
+static int launch_fixedbf(const FixedBfArgs &a0, const TwiddleSet &tw, cudaStream_t st) {
+  FixedBfArgs a = a0;
+  constexpr int BE = fft_buf_elems(N);
+  const size_t smem = ((size_t)a.M + a.B) * BE * sizeof(float2) + (size_t)a.B * N * sizeof(float) + (size_t)N * sizeof(float);
+  if (smem > 227 * 1024) { set_error("fixedbf: M=%d B=%d n_fft=%d does not fit shared memory", a.M, a.B, N); return DS_EUNSUPPORTED; }
+  auto kern = fixedbf_kernel<N>;
+  DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // split the frame axis into segments when there are too few streams to fill the GPU
+  int segs = 1;
+  const int target_ctas = 148 * 2;
+  if (a.S < target_ctas) {
+    segs = (target_ctas + a.S - 1) / a.S;
+    int max_segs = a.T / 16;                     // keep the halo overhead small
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+  }
+  a.frames_per_seg = (a.T + segs - 1) / segs;
+  a.segs = (a.T + a.frames_per_seg - 1) / a.frames_per_seg;
+  if (a.segs < 1) a.segs = 1;
+  kern<<<a.S * a.segs, FBF_WARPS * 32, smem, st>>>(a, tw.h32, tw.n32);
+  DS_LAUNCH_CHECK();
+  flip_parity_kernel<<<1, 1, 0, st>>>(a.state);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+int ds_stft_num_frames(const ds_stft_params *p) {
+  if (!p || p->n_fft <= 0 || p->hop <= 0 || p->n_samples < 0) return DS_EINVAL;
+  const int ov = p->n_fft - p->hop;
+  switch (p->mode) {
+    case DS_STFT_STREAMING:
+      if (ov + p->n_samples < p->n_fft) return 0;
+      return 1 + (ov + p->n_samples - p->n_fft) / p->hop;
+    case DS_STFT_CENTER:
+      return 1 + p->n_samples / p->hop;
+    case DS_STFT_PLAIN:
+      if (p->n_samples < p->n_fft) return 0;
+      return 1 + (p->n_samples - p->n_fft) / p->hop;
+  }
+  return DS_EINVAL;
+}
+
+int ds_stft_run(const ds_stft_params *p, const double *window, float *history, const float *x, void *X, void *stream) {
+  DS_CHECK_ARG(p && window && x && X, "ds_stft_run: null argument");
+  DS_CHECK_ARG(p->hop >= 1 && p->hop <= p->n_fft, "ds_stft_run: hop %d out of range", p->hop);
+  DS_CHECK_ARG(p->n_streams >= 1 && p->n_ch >= 1 && p->n_samples >= 1, "ds_stft_run: bad shape");
+  DS_CHECK_ARG(p->mode != DS_STFT_STREAMING || history || p->hop == p->n_fft, "ds_stft_run: streaming mode needs a history buffer");
+  DS_CHECK_ARG(p->mode != DS_STFT_CENTER || p->n_samples > p->n_fft / 2, "ds_stft_run: reflect padding needs n_samples > n_fft/2");
+  TwiddleSet tw;
+  int rc = get_twiddles(p->n_fft, &tw);
+  if (rc != DS_OK) return rc;
+  const int T = ds_stft_num_frames(p);
+  if (T < 0) { set_error("ds_stft_run: bad mode"); return DS_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  StftArgs a;
+  a.x = x; a.history = (p->mode == DS_STFT_STREAMING) ? history : nullptr; a.X = X; a.window = window; a.out_c128 = p->out_c128;
+  a.S = p->n_streams; a.C = p->n_ch; a.Ns = p->n_samples; a.T = T; a.hop = p->hop; a.mode = p->mode;
+  if (T > 0) {
+    rc = p->fft_fp64 ? dispatch_stft<double>(p->n_fft, a, tw, st) : dispatch_stft<float>(p->n_fft, a, tw, st);
+    if (rc != DS_OK) return rc;
+  }
+  const int ov = p->n_fft - p->hop;
+  if (p->mode == DS_STFT_STREAMING && ov > 0) {
+    int threads = (ov + 7) / 8;
+    threads = ((threads + 31) / 32) * 32;
+    stft_history_kernel<<<p->n_streams * p->n_ch, threads, 0, st>>>(x, history, p->n_samples, ov);
+    DS_LAUNCH_CHECK();
+  }
+  return DS_OK;
+}
+
+int ds_istft_run(const ds_istft_params *p, const double *window, float *tail, const void *Y, float *y, void *stream) {
+  DS_CHECK_ARG(p && window && Y && y, "ds_istft_run: null argument");
+  DS_CHECK_ARG(p->hop >= 1 && p->hop <= p->n_fft, "ds_istft_run: hop %d out of range", p->hop);
+  DS_CHECK_ARG(p->n_streams >= 1 && p->n_ch >= 1 && p->n_frames >= 1, "ds_istft_run: bad shape");
+  DS_CHECK_ARG(p->mode == DS_STFT_STREAMING || p->mode == DS_STFT_PLAIN, "ds_istft_run: mode must be STREAMING or PLAIN");
+  DS_CHECK_ARG(p->mode != DS_STFT_STREAMING || tail || p->hop == p->n_fft, "ds_istft_run: streaming mode needs a tail buffer");
+  TwiddleSet tw;
+  int rc = get_twiddles(p->n_fft, &tw);
+  if (rc != DS_OK) return rc;
+  IstftArgs a;
+  a.Y = Y; a.in_c128 = p->in_c128; a.y = y; a.tail = (p->mode == DS_STFT_STREAMING) ? tail : nullptr; a.window = window;
+  a.S = p->n_streams; a.C = p->n_ch; a.T = p->n_frames; a.hop = p->hop; a.mode = p->mode;
+  a.n_out = (p->mode == DS_STFT_STREAMING) ? p->n_frames * p->hop : p->n_fft + p->hop * (p->n_frames - 1);
+  a.scale = p->scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->fft_fp64 ? dispatch_istft<double>(p->n_fft, a, tw, st) : dispatch_istft<float>(p->n_fft, a, tw, st);
+}
+
+size_t ds_fixedbf_state_bytes(const ds_fixedbf_params *p) {
+  if (!p) return 0;
+  const int ov = p->n_fft - p->hop;
+  return 16 + 2 * fbf_half_bytes(p->n_streams, p->n_mics, p->n_beams, ov);
+}
+
+int ds_fixedbf_run(const ds_fixedbf_params *p, const double *window, const void *W, void *state, const float *x,
+                   float *y, void *stream) {
+  DS_CHECK_ARG(p && window && W && state && x && y, "ds_fixedbf_run: null argument");
+  DS_CHECK_ARG(p->hop * 2 == p->n_fft || p->hop * 4 == p->n_fft, "ds_fixedbf_run: hop must be n_fft/2 or n_fft/4");
+  DS_CHECK_ARG(p->n_streams >= 1 && p->n_mics >= 1 && p->n_beams >= 1, "ds_fixedbf_run: bad shape");
+  DS_CHECK_ARG(p->n_samples >= p->hop && p->n_samples % p->hop == 0, "ds_fixedbf_run: n_samples must be a positive multiple of hop");
+  TwiddleSet tw;
+  int rc = get_twiddles(p->n_fft, &tw);
+  if (rc != DS_OK) return rc;
+  FixedBfArgs a;
+  a.x = x; a.y = y; a.W = (const float2 *)W; a.window = window; a.state = (unsigned char *)state;
+  a.S = p->n_streams; a.M = p->n_mics; a.B = p->n_beams; a.Ns = p->n_samples; a.T = p->n_samples / p->hop;
+  a.hop = p->hop; a.segs = 1; a.frames_per_seg = a.T; a.scale = p->scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p->n_fft) {
+    case 128: return launch_fixedbf<128>(a, tw, st);
+    case 256: return launch_fixedbf<256>(a, tw, st);
+    case 512: return launch_fixedbf<512>(a, tw, st);
+    case 1024: return launch_fixedbf<1024>(a, tw, st);
+    case 2048: return launch_fixedbf<2048>(a, tw, st);
+  }
+  set_error("ds_fixedbf_run: unsupported n_fft %d", p->n_fft);
+  return DS_EUNSUPPORTED;
+}
+
+}  // extern "C"

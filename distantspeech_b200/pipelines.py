@@ -1,0 +1,175 @@
+"""Batched pipelines over many independent microphone-array streams.
+
+``MvdrMcsppChain`` is the config-4 composition pinned in SURVEY.md 8c -- the
+reference has no single function for it; the closest call sites are
+example/mcsppbase.ipynb cell 3, example/mvdr.ipynb cell 4 and GSC.py:225,286:
+
+    D = Transform(n_fft, hop, channel=M).stft(x)
+    est = McSppBase(nfft, channels=M); a0 = beamformer(...).compute_steering_vector_from_doa(look)
+    for n: est.estimation(D[:, n, :]); w = compute_mvdr_weight(a0, est.Phi_vv_inv)
+           est.compute_omlsa_weight(est.xi, est.p); Y[:, n] = (w^H D[:, n, :]) * est.G
+    y = Transform(n_fft, hop, channel=1).istft(Y)
+
+All three stages run in CUDA (ds_chain_run).  Streams are independent, so a job
+shards over GPUs by splitting the stream axis; there is no collective.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .beamformer.beamformer import beamformer
+from .transform.transform import _sqrt_hann
+
+
+class MvdrMcsppChain(object):
+    def __init__(self, mic_array, look_angle=(0, 0), n_fft=512, hop=256, apply_gain=True, full_state=False,
+                 fft_precision="fp32"):
+        self.mic_array = mic_array
+        self.M = mic_array.M
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        self.K = self.n_fft // 2 + 1
+        self.apply_gain = bool(apply_gain)
+        self.full_state = bool(full_state)
+        self.fft_fp64 = fft_precision == "fp64"
+        self.window = _sqrt_hann(self.n_fft)
+        self.W0 = float(np.sum(self.window ** 2))
+        bf = beamformer(mic_array, frame_len=self.n_fft, hop=self.hop, nfft=self.n_fft)
+        self.a0 = bf.compute_steering_vector_from_doa(look_angle)          # [K, M]
+        self.frm_cnt, self.ell, self.mcra_L = 0, 1, 15
+        self._state = None
+        self._ws = None
+        self._key = None
+        self._a0_dev = None
+
+    # ------------------------------------------------------------------
+    def _params(self, S, N):
+        p = L.ChainParams()
+        L.lib().ds_mcspp_default_params(C.byref(p.est), self.n_fft, S, self.M, N // self.hop)
+        p.est.frm_cnt, p.est.ell, p.est.mcra_L = self.frm_cnt, self.ell, self.mcra_L
+        p.est.full_state = int(self.full_state)
+        p.hop, p.n_samples, p.fft_fp64, p.apply_gain = self.hop, N, int(self.fft_fp64), int(self.apply_gain)
+        p.scale = self.hop / self.W0
+        return p
+
+    def reset(self):
+        self._state = None
+        self.frm_cnt, self.ell = 0, 1
+
+    def _prepare(self, S, N):
+        t = L.require_cuda()
+        L.ensure_init()
+        p = self._params(S, N)
+        if self._state is None or self._key is None or self._key[0] != S:
+            self._state = t.zeros(L.lib().ds_chain_state_bytes(C.byref(p)), dtype=t.uint8, device="cuda")
+            self.frm_cnt, self.ell = 0, 1
+            p = self._params(S, N)
+        if self._ws is None or self._key != (S, N):
+            self._ws = None
+            self._ws = t.empty(L.lib().ds_chain_workspace_bytes(C.byref(p)), dtype=t.uint8, device="cuda")
+        self._key = (S, N)
+        if self._a0_dev is None or self._a0_dev.device.index != t.cuda.current_device():
+            self._a0_dev = t.as_tensor(np.ascontiguousarray(self.a0.T)).to("cuda")     # [M, K] complex128
+        return p
+
+    def process_device(self, x_dev, out=None):
+        """x_dev [S, M, N] float32 CUDA (mic-major) -> y [S, N] float32 CUDA.  No copies, no sync."""
+        t = L.require_cuda()
+        S, M, N = x_dev.shape
+        if M != self.M or N % self.hop != 0 or N < self.hop:
+            raise ValueError("expected [S, %d, N] with N a positive multiple of hop=%d" % (self.M, self.hop))
+        if x_dev.dtype != t.float32 or not x_dev.is_contiguous():
+            raise ValueError("x_dev must be a contiguous float32 CUDA tensor")
+        p = self._prepare(S, N)
+        y = out if out is not None else t.empty((S, N), dtype=t.float32, device="cuda")
+        L.check(L.lib().ds_chain_run(C.byref(p), L.ptr(L.device_window(self.window, self.n_fft)), L.ptr(self._a0_dev),
+                                     L.ptr(self._state), L.ptr(self._ws), L.ptr(x_dev), L.ptr(y), L.stream_ptr()),
+                "ds_chain_run")
+        f, e = C.c_int32(self.frm_cnt), C.c_int32(self.ell)
+        L.lib().ds_mcra_advance(self.mcra_L, N // self.hop, C.byref(f), C.byref(e))
+        self.frm_cnt, self.ell = f.value, e.value
+        return y
+
+    def process_device_profiled(self, x_dev, out=None):
+        """Like process_device but synchronises and returns (y, [ms_analysis, ms_perbin, ms_synthesis])
+        measured with CUDA events on the launching stream (bench/roofline use only)."""
+        t = L.require_cuda()
+        S, M, N = x_dev.shape
+        p = self._prepare(S, N)
+        y = out if out is not None else t.empty((S, N), dtype=t.float32, device="cuda")
+        ms = (C.c_float * 3)()
+        L.check(L.lib().ds_chain_run_profiled(C.byref(p), L.ptr(L.device_window(self.window, self.n_fft)),
+                                              L.ptr(self._a0_dev), L.ptr(self._state), L.ptr(self._ws), L.ptr(x_dev),
+                                              L.ptr(y), L.stream_ptr(), ms), "ds_chain_run_profiled")
+        f, e = C.c_int32(self.frm_cnt), C.c_int32(self.ell)
+        L.lib().ds_mcra_advance(self.mcra_L, N // self.hop, C.byref(f), C.byref(e))
+        self.frm_cnt, self.ell = f.value, e.value
+        return y, [float(v) for v in ms]
+
+    def process(self, x):
+        """Reference-shaped call: x [N, M] (or [S, N, M]) NumPy / torch -> y [N] (or [S, N]).
+        NumPy in -> NumPy (float64 holding float32 values, like Transform.istft) out."""
+        t = L.require_cuda()
+        as_torch = isinstance(x, t.Tensor)
+        xd = L.to_device(x, t.float32)
+        batched = xd.dim() == 3
+        if not batched:
+            xd = xd[None]
+        y = self.process_device(xd.permute(0, 2, 1).contiguous())
+        if not batched:
+            y = y[0]
+        return y if as_torch else y.double().cpu().numpy()
+
+    def process_host(self, x_host, y_host=None, chunk_streams=128):
+        """End-to-end call with HOST buffers: x_host [S, M, N] float32 (pinned for speed) ->
+        y_host [S, N] float32.  Streams are independent, so the batch is cut into groups of
+        ``chunk_streams`` and H2D copy / kernels / D2H copy of consecutive groups overlap on
+        three CUDA streams.  Each group is a fresh utterance (state reset)."""
+        t = L.require_cuda()
+        S, M, N = x_host.shape
+        if y_host is None:
+            y_host = t.empty((S, N), dtype=t.float32, pin_memory=True)
+        cs = min(chunk_streams, S)
+        n_chunks = (S + cs - 1) // cs
+        cur = t.cuda.current_stream()
+        s_in, s_out = t.cuda.Stream(), t.cuda.Stream()
+        xbuf = [t.empty((cs, M, N), dtype=t.float32, device="cuda") for _ in range(2)]
+        ybuf = [t.empty((cs, N), dtype=t.float32, device="cuda") for _ in range(2)]
+        ev_in = [t.cuda.Event() for _ in range(2)]
+        ev_done = [t.cuda.Event() for _ in range(2)]
+        ev_out = [t.cuda.Event() for _ in range(2)]
+        sub = MvdrMcsppChain.__new__(MvdrMcsppChain)
+        sub.__dict__.update(self.__dict__)
+        sub._state = None
+        sub._ws = None
+        sub._key = None
+        for c in range(n_chunks):
+            b = c & 1
+            lo, hi = c * cs, min(S, (c + 1) * cs)
+            n = hi - lo
+            with t.cuda.stream(s_in):
+                if c >= 2:
+                    s_in.wait_event(ev_done[b])          # kernels of chunk c-2 finished reading xbuf[b]
+                xbuf[b][:n].copy_(x_host[lo:hi], non_blocking=True)
+                ev_in[b].record(s_in)
+            cur.wait_event(ev_in[b])
+            if c >= 2:
+                cur.wait_event(ev_out[b])                # D2H of chunk c-2 finished reading ybuf[b]
+            if n != cs:
+                sub._state = None
+                sub._key = None
+            sub.reset_counters()
+            if sub._state is not None:
+                sub._state.zero_()
+            sub.process_device(xbuf[b][:n], out=ybuf[b][:n])
+            ev_done[b].record(cur)
+            with t.cuda.stream(s_out):
+                s_out.wait_event(ev_done[b])
+                y_host[lo:hi].copy_(ybuf[b][:n], non_blocking=True)
+                ev_out[b].record(s_out)
+        s_out.synchronize()
+        cur.synchronize()
+        return y_host
+
+    def reset_counters(self):
+        self.frm_cnt, self.ell = 0, 1

@@ -1,0 +1,257 @@
+/*
+ * ds_b200.h -- C ABI of libds_b200.so: B200 (sm_100a) kernels for the
+ * DistantSpeech multichannel enhancement hot path.
+ *
+ * The reference (wangwei2009/DistantSpeech) is pure Python/NumPy and has no
+ * FFI layer; the boundary a maintainer binds is its Python call surface
+ * (SURVEY.md 8b).  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  INTEGRATION.md shows
+ * the ctypes stub that goes on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _h;
+ *   - no allocation, no synchronisation and no host<->device copies inside a
+ *     *_run call; kernels are enqueued on the cudaStream_t passed as `stream`
+ *     (a `void*`, so this header needs no CUDA include);
+ *   - state lives in caller-allocated blobs whose size is returned by the
+ *     matching *_state_bytes(); a zero-filled blob is the reset state;
+ *   - return value: DS_OK (0) or a negative DS_E* code; ds_last_error() gives
+ *     a thread-local human-readable message for the last failure;
+ *   - a state blob is not thread-safe; distinct blobs are independent;
+ *   - complex arrays are interleaved (re, im); "c64" = 2 x float, "c128" =
+ *     2 x double;
+ *   - K = n_fft/2 + 1 bins, T frames, M mics/channels, S independent streams.
+ *
+ * Device layouts (chosen for coalescing: the bin index is innermost because
+ * kernels map threads to bins; the sample index is innermost for audio):
+ *   audio      x [S][M][N]   float32     (stream, mic, sample)
+ *   spectrum   X [S][T][M][K] c64        (stream, frame, mic, bin)
+ *   per-bin    p [S][T][K]   float64
+ */
+#ifndef DS_B200_H
+#define DS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_VERSION 100
+
+enum {
+  DS_OK = 0,
+  DS_EINVAL = -1,       /* bad shape / null pointer / inconsistent params        */
+  DS_EUNSUPPORTED = -2, /* n_fft, M ... outside the compiled template set         */
+  DS_ECUDA = -3,        /* CUDA runtime error (launch failure, wrong device ...)  */
+  DS_ESTATE = -4        /* state blob too small                                   */
+};
+
+/* ---- library ---------------------------------------------------------- */
+int ds_version(void);
+const char *ds_last_error(void);
+/* Builds the twiddle tables for every supported n_fft on the current device.
+ * Idempotent. Call once before the first *_run (the *_run calls also do it
+ * lazily, but that allocates on first use). */
+int ds_init(void);
+/* SM count and compute capability of the current device. */
+int ds_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- STFT / ISTFT  (transform/transform.py) --------------------------- */
+enum {
+  DS_STFT_STREAMING = 0, /* Transform.stft  :430-453: `history` (n_fft-hop samples per
+                            channel) is prepended, T = N/hop, history is updated   */
+  DS_STFT_CENTER = 1,    /* stft(center=True, pad_mode="reflect") :205-206, T=1+N/hop */
+  DS_STFT_PLAIN = 2      /* stft(center=False)  :209, T = 1+(N-n_fft)/hop           */
+};
+
+typedef struct ds_stft_params {
+  int32_t n_fft;     /* power of two, 128..2048                                   */
+  int32_t hop;       /* 1..n_fft                                                  */
+  int32_t n_streams; /* S                                                         */
+  int32_t n_ch;      /* M (channels per stream)                                   */
+  int32_t n_samples; /* N samples per channel in this call                        */
+  int32_t mode;      /* DS_STFT_*                                                 */
+  int32_t fft_fp64;  /* 0: fp32 FFT (default), 1: fp64 FFT                        */
+  int32_t out_c128;  /* 0: X is complex64 (reference default dtype), 1: complex128 */
+} ds_stft_params;
+
+/* Number of frames a call produces (negative DS_E* on bad params). */
+int ds_stft_num_frames(const ds_stft_params *p);
+
+/* replaces transform.stft (transform.py:10-221) and Transform.stft (:430-453).
+ *   window  [n_fft] float64 (already centre-padded to n_fft)
+ *   history [S][M][n_fft-hop] float32, in/out, DS_STFT_STREAMING only (else NULL)
+ *   x       [S][M][N] float32
+ *   X       [S][T][M][K] c64 out (rounded to complex64 like :212) or c128        */
+int ds_stft_run(const ds_stft_params *p, const double *window, float *history,
+                const float *x, void *X, void *stream);
+
+typedef struct ds_istft_params {
+  int32_t n_fft;
+  int32_t hop;
+  int32_t n_streams;
+  int32_t n_ch;
+  int32_t n_frames; /* T                                                          */
+  int32_t mode;     /* DS_STFT_STREAMING: Transform.istft (:455-481): out has hop*T
+                       samples, `tail` carries previous_output, scaled by `scale`;
+                       DS_STFT_PLAIN: istft(center=False): out has n_fft+hop*(T-1)
+                       samples, no tail, no scaling                               */
+  int32_t fft_fp64;
+  int32_t in_c128; /* 0: Y is complex64, 1: complex128                            */
+  double scale; /* Transform.istft: hop / sum(window^2) (:479)                    */
+} ds_istft_params;
+
+/* replaces transform.istft (transform.py:237-404, float32 overlap-add :224-234,
+ * no window-sum normalisation) and Transform.istft (:455-481).
+ *   Y    [S][T][C][K] c64/c128 tail [S][C][n_fft-hop] float32 in/out (streaming)
+ *   y    [S][C][n_out] float32                                                   */
+int ds_istft_run(const ds_istft_params *p, const double *window, float *tail,
+                 const void *Y, float *y, void *stream);
+
+/* ---- fixed beamformer (beamformer/fixedbeamformer.py) ----------------- */
+typedef struct ds_fixedbf_params {
+  int32_t n_fft;
+  int32_t hop; /* must be n_fft/2 or n_fft/4                                      */
+  int32_t n_streams;
+  int32_t n_mics;
+  int32_t n_samples; /* multiple of hop                                           */
+  int32_t n_beams;   /* B >= 1 look directions evaluated at once                  */
+  int32_t reserved0;
+  int32_t reserved1;
+  double scale; /* hop / sum(window^2)                                            */
+} ds_fixedbf_params;
+
+size_t ds_fixedbf_state_bytes(const ds_fixedbf_params *p);
+/* replaces FixedBeamformer.process (fixedbeamformer.py:167-207): Transform.stft
+ * -> Y[k,t] = sum_m conj(W[k,m]) X[k,t,m] (:163) -> Transform.istft, fused in
+ * one kernel (the spectrum never goes to HBM).
+ *   W     [B][K][M] c64 weights (as returned by compute_weights, NOT conjugated)
+ *   state ds_fixedbf_state_bytes() blob: input history + output tail (zero = reset)
+ *   x     [S][M][N] float32        y [S][B][N] float32                           */
+int ds_fixedbf_run(const ds_fixedbf_params *p, const double *window, const void *W,
+                   void *state, const float *x, float *y, void *stream);
+
+/* ---- per-bin weight helpers (beamformer/beamformer.py module functions) -- */
+/* replaces compute_mvdr_weight (beamformer.py:133-155): w = R^-1 a / (a^H R^-1 a).
+ *   steer [bins][M] c128   Rvv_inv [bins][M][M] c128   w_out [bins][M] c128, M <= 16 */
+int ds_mvdr_weight_run(int n_bins, int n_mics, const void *steer, const void *Rvv_inv,
+                       void *w_out, void *stream);
+/* replaces compute_pmwf_weight (beamformer.py:100-130, mcspp_base.py:220-240):
+ * w = (Rvv_inv Rxx) u_1 / (beta + xi).  xi [bins] float64, Rxx/Rvv_inv [bins][M][M] c128 */
+int ds_pmwf_weight_run(int n_bins, int n_mics, const double *xi, const void *Rxx,
+                       const void *Rvv_inv, double beta, void *w_out, void *stream);
+/* replaces process_freframe (fixedbeamformer.py:147-165): Y[s,t,k] = sum_m conj(W[k,m]) X[s,t,m,k].
+ *   X [S][T][M][K] c64 or c128   W [K][M] c128   Y [S][T][K] c128                 */
+int ds_apply_weights_run(int n_streams, int n_frames, int n_mics, int n_bins, const void *X,
+                         int x_is_c128, const void *W, void *Y, void *stream);
+
+/* replaces McSppBase.compute_omlsa_weight (mcspp_base.py:140-155):
+ * G = clip((xi/(1+xi))^p Gmin^(1-p), Gmin, 1), G[:2] = 0 per row of n_bins.       */
+int ds_omlsa_gain_run(int n_rows, int n_bins, const double *xi, const double *p, double Gmin,
+                      double *G, double *G_H1, void *stream);
+
+/* ---- MCRA noise estimator (noise_estimation/mcra.py) ------------------ */
+typedef struct ds_mcra_params {
+  int32_t n_bins;    /* K                                                         */
+  int32_t n_streams; /* S                                                         */
+  int32_t n_frames;  /* T                                                         */
+  int32_t L;         /* minimum-search window (15)                      mcra.py:25 */
+  int32_t frm_cnt;   /* frames already processed (host-tracked)          :72       */
+  int32_t ell;       /* window counter at entry (1 at reset)             Base :18  */
+  int32_t reserved0;
+  int32_t reserved1;
+  double alpha_d, alpha_s, delta_s, alpha_p, p_min, p_max; /* .95 .8 5 .2 1e-3 .999 */
+} ds_mcra_params;
+
+size_t ds_mcra_state_bytes(const ds_mcra_params *p); /* [S][5][K] float64: S,Smin,Stmp,p,lambda_d */
+/* replaces NoiseEstimationMCRA.estimation (mcra.py:27-77) applied to T frames.
+ *   Ypow [S][T][K] float64 power spectrum    lambda_out/p_out [S][T][K] or NULL
+ * The caller advances frm_cnt/ell with ds_mcra_advance().                        */
+int ds_mcra_run(const ds_mcra_params *p, void *state, const double *Ypow,
+                double *lambda_out, double *p_out, void *stream);
+/* Host-side helper: frm_cnt/ell after n_frames more frames (mcra.py:52-56,72-74). */
+void ds_mcra_advance(int32_t L, int32_t n_frames, int32_t *frm_cnt, int32_t *ell);
+
+/* ---- McSppBase estimator + MVDR/OMLSA chain --------------------------- */
+typedef struct ds_mcspp_params {
+  int32_t n_fft;
+  int32_t n_streams;
+  int32_t n_mics;   /* 2..8                                                       */
+  int32_t n_frames; /* T                                                          */
+  int32_t frm_cnt;  /* frames already processed (host-tracked)                    */
+  int32_t ell;      /* inner MCRA window counter at entry                         */
+  int32_t mcra_L;   /* 15                                         mcspp_base.py:77 */
+  int32_t full_state; /* 1: track complex Phi_yy/Phi_vv, all K bins and the PMWF
+                         weights (every public attribute of McSppBase);
+                         0: output-only -- real parts and bins 2..K-1 only, which is
+                         everything the chain output depends on (:278-284 use .real,
+                         compute_omlsa_weight zeroes G[:2])                       */
+  double alpha, alpha_d;              /* .92 .92                          :38-40  */
+  double diag_eps;                    /* 1e-6                             :74     */
+  double q_min, q_max, p_min, p_max;  /* .01 .99 .01 .99                  :120,290 */
+  double snr_min, snr_max;            /* 1e-6 1e6  (xi, gamma clip)       :286-287 */
+  double Gmin;                        /* 0.0631                           :140    */
+  double mcra_alpha_d, mcra_alpha_s, mcra_delta_s, mcra_alpha_p, mcra_p_min, mcra_p_max;
+} ds_mcspp_params;
+
+/* Fills every constant of *p with the reference defaults. */
+void ds_mcspp_default_params(ds_mcspp_params *p, int n_fft, int n_streams, int n_mics, int n_frames);
+size_t ds_mcspp_state_bytes(const ds_mcspp_params *p);
+
+typedef struct ds_mcspp_taps { /* optional per-frame outputs, any may be NULL     */
+  double *p;      /* [S][T][K]    posterior SPP                                   */
+  double *xi;     /* [S][T][K]                                                    */
+  double *gamma;  /* [S][T][K]                                                    */
+  double *q;      /* [S][T][K]                                                    */
+  double *G;      /* [S][T][K]    OMLSA gain (compute_omlsa_weight)               */
+  void *w_mvdr;   /* [S][T][M][K] c128 MVDR weights                               */
+  void *w_pmwf;   /* [S][T][M][K] c128 PMWF weights (full_state only)             */
+  double *Phi_vv_inv_last; /* [S][K][M][M] float64, inverse used by the LAST frame */
+} ds_mcspp_taps;
+
+/* replaces, per frame: McSppBase.estimation (mcspp_base.py:262-297),
+ * compute_mvdr_weight(a0, Phi_vv_inv) (beamformer.py:133-155),
+ * McSppBase.compute_omlsa_weight (:140-155) and the weight/gain apply
+ * Y = (w^H y) G  (example/mvdr.ipynb, GSC.py:286).
+ *   a0   [M][K] c128 steering vectors (or NULL: estimator only, Yout unused)
+ *   X    [S][T][M][K] c64 (x_is_c128 = 0) or c128 (x_is_c128 = 1)
+ *   Yout [S][T][K] c64 beamformed+postfiltered spectrum (or NULL)
+ *   apply_gain: multiply by the OMLSA gain G (1) or output the plain MVDR (0)    */
+int ds_mcspp_run(const ds_mcspp_params *p, void *state, const void *a0, const void *X,
+                 int x_is_c128, void *Yout, int apply_gain, const ds_mcspp_taps *taps,
+                 void *stream);
+/* state export for the Python attribute views: copies one named field of every
+ * stream into `out`. field: 0 Phi_yy, 1 Phi_vv (c128 [S][K][M][M]),
+ * 2 mcra block ([S][5][K] float64).                                              */
+int ds_mcspp_export(const ds_mcspp_params *p, const void *state, int field, void *out, void *stream);
+
+/* ---- config-4 chain: STFT -> McSppBase -> MVDR -> OMLSA -> ISTFT ------- */
+typedef struct ds_chain_params {
+  ds_mcspp_params est; /* n_frames is derived: n_samples / hop                    */
+  int32_t hop;
+  int32_t n_samples; /* multiple of hop                                           */
+  int32_t fft_fp64;
+  int32_t apply_gain;
+  double scale; /* hop / sum(window^2)                                            */
+} ds_chain_params;
+
+size_t ds_chain_state_bytes(const ds_chain_params *p);
+size_t ds_chain_workspace_bytes(const ds_chain_params *p);
+/* replaces the composition pinned in SURVEY.md 8c (mcsppbase.ipynb cell 3,
+ * mvdr.ipynb cell 4): x [S][M][N] float32 -> y [S][N] float32.                   */
+int ds_chain_run(const ds_chain_params *p, const double *window, const void *a0,
+                 void *state, void *workspace, const float *x, float *y, void *stream);
+
+/* Profiling variant (bench only): same work, but records CUDA events between the
+ * three kernels, SYNCHRONISES, and returns their durations in milliseconds in
+ * phase_ms_h[3] = {analysis, per-bin estimator/beamformer, synthesis} (host). */
+int ds_chain_run_profiled(const ds_chain_params *p, const double *window, const void *a0,
+                          void *state, void *workspace, const float *x, float *y, void *stream,
+                          float *phase_ms_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DS_B200_H */

@@ -1,0 +1,158 @@
+"""TEST INFRASTRUCTURE ONLY -- import harness for the *unmodified* reference.
+
+This file lets the reference package under ``/root/reference`` be imported in
+the build container so that (a) the numpy restatement in ``oracle/np_oracle.py``
+can be validated against the real thing and (b) golden vectors can be dumped to
+``tests/golden`` (see ``tests/golden/make_golden.py``).  It cannot travel to the
+GPU box (``/root/reference`` does not exist there); everything that runs on the
+GPU box uses the committed fixtures and the numpy oracle instead.
+
+Nothing under ``distantspeech_b200/`` may import this module.
+
+What it does:
+  1. stubs third-party modules that are absent here and carry no arithmetic
+     (matplotlib, sounddevice, soundfile, pyroomacoustics, pesq, pystoi,
+     pyaudio, turtle, tkinter.tix, imp, tqdm is present);
+  2. installs a tiny ``librosa`` stand-in that provides only the pure-indexing
+     helpers ``transform.py`` needs (pad_center, frame, valid_audio, fix_length,
+     MAX_MEM_BLOCK, filters.get_window);
+  3. applies three mechanical compatibility patches from the outside:
+       (i)   ``np.mat = np.asmatrix``  (NumPy >= 2 dropped ``np.mat``;
+             used at beamformer/adaptivebeamformer.py:84);
+       (ii)  ``beamformer.__init__`` accepts-and-drops ``c= fs= r=``
+             (fixedbeamformer.py:99, adaptivebeamformer.py:13, postfilter.py:11
+             pass them; beamformer.py:223 no longer takes them);
+       (iii) ``adaptivebeamfomer.transformer.istft`` gets its 2-D ``[K,T]``
+             argument lifted to ``[K,T,1]`` (adaptivebeamformer.py:122 vs
+             transform.py:463-464).
+The reference source files themselves are never modified or copied.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from unittest import mock
+
+REFERENCE_ROOT = os.environ.get("DS_REFERENCE_ROOT", "/root/reference")
+
+_installed = False
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "DistantSpeech"))
+
+
+def _make_librosa_stub():
+    import numpy as np
+    import scipy.signal
+
+    librosa = types.ModuleType("librosa")
+    util = types.ModuleType("librosa.util")
+    filters = types.ModuleType("librosa.filters")
+
+    def pad_center(data, size, axis=-1, **kwargs):
+        n = data.shape[axis]
+        lpad = int((size - n) // 2)
+        lengths = [(0, 0)] * data.ndim
+        lengths[axis] = (lpad, int(size - n - lpad))
+        if lpad < 0:
+            raise ValueError("target size smaller than input")
+        return np.pad(data, lengths, **kwargs)
+
+    def frame(x, frame_length, hop_length, axis=-1):
+        n_frames = 1 + (x.shape[-1] - frame_length) // hop_length
+        idx = np.arange(frame_length)[:, None] + hop_length * np.arange(n_frames)[None, :]
+        return x[idx]
+
+    def valid_audio(y, mono=True):
+        return True
+
+    def fix_length(data, size, axis=-1, **kwargs):
+        n = data.shape[axis]
+        if n > size:
+            sl = [slice(None)] * data.ndim
+            sl[axis] = slice(0, size)
+            return data[tuple(sl)]
+        if n < size:
+            lengths = [(0, 0)] * data.ndim
+            lengths[axis] = (0, size - n)
+            return np.pad(data, lengths, **kwargs)
+        return data
+
+    def get_window(window, Nx, fftbins=True):
+        return scipy.signal.get_window(window, Nx, fftbins=fftbins)
+
+    util.pad_center = pad_center
+    util.frame = frame
+    util.valid_audio = valid_audio
+    util.fix_length = fix_length
+    util.MAX_MEM_BLOCK = 2 ** 18
+    filters.get_window = get_window
+    librosa.__path__ = []  # behave like a package so ``import librosa.display`` resolves
+    librosa.util = util
+    librosa.filters = filters
+    librosa.load = mock.MagicMock()
+    librosa.display = mock.MagicMock(name="librosa.display")
+    librosa.power_to_db = mock.MagicMock()
+    return librosa, util, filters
+
+
+def install():
+    """Make ``import DistantSpeech...`` work in this container. Idempotent."""
+    global _installed
+    if _installed:
+        return
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/ds_numba_cache")
+    sys.dont_write_bytecode = True
+
+    import numpy as np
+
+    if not hasattr(np, "mat"):
+        np.mat = np.asmatrix  # patch (i)
+
+    for name in [
+        "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors",
+        "mpl_toolkits", "mpl_toolkits.mplot3d", "sounddevice", "soundfile",
+        "pyroomacoustics", "pesq", "pystoi", "pystoi.stoi", "pyaudio", "turtle",
+        "tkinter.tix", "imp", "gpuRIR", "webrtcvad",
+    ]:
+        if name not in sys.modules:
+            sys.modules[name] = mock.MagicMock(name=name)
+
+    if "librosa" not in sys.modules:
+        librosa, util, filters = _make_librosa_stub()
+        sys.modules["librosa"] = librosa
+        sys.modules["librosa.util"] = util
+        sys.modules["librosa.filters"] = filters
+        sys.modules["librosa.display"] = librosa.display
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+    # patch (ii)
+    from DistantSpeech.beamformer import beamformer as _bf_mod
+
+    _orig_init = _bf_mod.beamformer.__init__
+
+    def _init(self, mic, frame_len=256, hop=None, nfft=None, c=None, fs=None, r=None):
+        _orig_init(self, mic, frame_len=frame_len, hop=hop, nfft=nfft)
+
+    if not getattr(_bf_mod.beamformer, "_ds_patched", False):
+        _bf_mod.beamformer.__init__ = _init
+        _bf_mod.beamformer._ds_patched = True
+
+    _installed = True
+
+
+def make_adaptive_mvdr(mic, frameLen, hop, nfft):
+    """Construct the reference ``adaptivebeamfomer`` with patch (iii) applied."""
+    install()
+    from DistantSpeech.beamformer.adaptivebeamformer import adaptivebeamfomer
+
+    obj = adaptivebeamfomer(mic, frameLen=frameLen, hop=hop, nfft=nfft)
+    orig = obj.transformer.istft
+    obj.transformer.istft = lambda Y: orig(Y[..., None] if Y.ndim == 2 else Y)
+    return obj

@@ -1,0 +1,120 @@
+"""Generate the golden fixtures in tests/golden by running the UNMODIFIED
+reference (imported from /root/reference through oracle/ref_harness.py).
+
+    python tests/golden/make_golden.py
+
+Only runs in the build container (the reference tree is not on the GPU box);
+the resulting .npz files are committed.  Inputs are stored with the outputs so
+the fixtures are self-contained.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as H  # noqa: E402
+from oracle import np_oracle as O    # noqa: E402  (only for the synthetic input generator)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def save(name, **kw):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **kw)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def main():
+    H.install()
+    from DistantSpeech.transform.transform import Transform, stft, istft
+    from DistantSpeech.beamformer.MicArray import MicArray
+    from DistantSpeech.beamformer.beamformer import beamformer, compute_mvdr_weight
+    from DistantSpeech.beamformer.fixedbeamformer import FixedBeamformer
+    from DistantSpeech.noise_estimation.mcspp_base import McSppBase
+    from DistantSpeech.noise_estimation.mcra import NoiseEstimationMCRA
+
+    rng = np.random.default_rng(1234)
+
+    # ---- a1/a2: module-level stft / istft ------------------------------------
+    x = (rng.standard_normal(6000) * 0.1).astype(np.float32)
+    win = O.sqrt_hann(512)
+    D = stft(x.astype(np.float64), n_fft=512, hop_length=128, window=win, center=True)
+    y = istft(D, hop_length=128, window=win, center=True, length=6000)
+    D2 = stft(x.astype(np.float64), n_fft=256, hop_length=128, window=O.sqrt_hann(256), center=False)
+    y2 = istft(D2, hop_length=128, window=O.sqrt_hann(256), center=False)
+    save("stft_istft.npz", x=x, D_512_128_center=D, y_512_128_center=y, D_256_128_plain=D2, y_256_128_plain=y2)
+
+    # ---- a3: streaming Transform, 3 chunks -----------------------------------
+    xs = (rng.standard_normal((256 * 12, 3)) * 0.1).astype(np.float32)
+    tf = Transform(n_fft=512, hop_length=256, channel=3)
+    chunks = [xs[:256 * 5], xs[256 * 5:256 * 6], xs[256 * 6:]]
+    Ys = [tf.stft(c.astype(np.float64)) for c in chunks]
+    tf2 = Transform(n_fft=512, hop_length=256, channel=3)
+    ys = [np.atleast_2d(tf2.istft(Y)) for Y in Ys]
+    save("transform_stream.npz", x=xs, Y0=Ys[0], Y1=Ys[1], Y2=Ys[2], y0=ys[0], y1=ys[1], y2=ys[2],
+         prev_in=tf.previous_input, prev_out=tf2.previous_output)
+
+    # ---- a9: fixed beamformer -------------------------------------------------
+    geo8 = O.MicGeometry("circular", r=0.05, M=8, n_fft=256)
+    x8 = O.synth_streams(1, geo8, 8192, seed0=77)[0].T.copy()            # [N, 8] float32
+    mic8 = MicArray(arrayType="circular", r=0.05, M=8, n_fft=256)
+    fb = FixedBeamformer(mic8, 256, 128, 256)
+    y_sd = fb.process(x8.astype(np.float64), (30, 0))                     # reference always uses SD here
+    W_sd = fb.W.copy()
+    fb2 = FixedBeamformer(mic8, 256, 128, 256)
+    W_ds = beamformer.compute_weights(fb2, (30, 0), "DS")
+    D8 = fb2.transform.stft(x8.astype(np.float64))
+    Yf = np.einsum("km,ktm->kt", W_ds.conj(), D8)[:, :, None]
+    y_ds = fb2.transform.istft(Yf)
+    save("fixedbf.npz", x=x8, angle=np.array([30, 0]), W_sd=W_sd, y_sd=y_sd, W_ds=W_ds, y_ds=y_ds)
+
+    # ---- a12: MCRA -------------------------------------------------------------
+    P = np.abs(D8[:, :, 0]) ** 2                                           # [129, T]
+    m = NoiseEstimationMCRA(nfft=256)
+    lam = np.zeros_like(P)
+    pp = np.zeros_like(P)
+    for n in range(P.shape[1]):
+        lam[:, n] = m.estimation(P[:, n])
+        pp[:, n] = m.p
+    save("mcra.npz", P=P, lambda_d=lam, p=pp, S=m.S, Smin=m.Smin, Stmp=m.Stmp, ell=m.ell, frm_cnt=m.frm_cnt)
+
+    # ---- a13 + config-4 composition ---------------------------------------------
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    xc = O.synth_streams(1, geo, 16384, seed0=99)[0].T.copy()             # [N, 8]
+    mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=512)
+    T = Transform(n_fft=512, hop_length=256, channel=8)
+    Dc = T.stft(xc.astype(np.float64))
+    est = McSppBase(nfft=512, channels=8)
+    a0 = beamformer(mic, frame_len=512, hop=256, nfft=512).compute_steering_vector_from_doa((30, 0))
+    nT = Dc.shape[1]
+    Y = np.zeros((257, nT, 1), dtype=complex)
+    tr = {k: np.zeros((257, nT)) for k in ("p", "xi", "gamma", "q", "G")}
+    for n in range(nT):
+        yv = Dc[:, n, :]
+        est.estimation(yv)
+        w = compute_mvdr_weight(a0, est.Phi_vv_inv)
+        est.compute_omlsa_weight(est.xi, est.p)
+        Y[:, n, 0] = np.einsum("ij,ij->i", w.conj(), yv) * est.G
+        for k in tr:
+            tr[k][:, n] = getattr(est, k)
+    yc = Transform(n_fft=512, hop_length=256, channel=1).istft(Y)
+    save("chain_mcspp_mvdr.npz", x=xc, look=np.array([30, 0]), a0=a0, y=yc, Yspec=Y[:, :, 0].astype(np.complex64),
+         p=tr["p"].astype(np.float32), xi=tr["xi"], gamma=tr["gamma"], q=tr["q"].astype(np.float32),
+         G=tr["G"].astype(np.float32), Phi_vv_last=est.Phi_vv, Phi_yy_last=est.Phi_yy, w_pmwf_last=est.w,
+         Phi_vv_inv_last=est.Phi_vv_inv)
+
+    # ---- a11: online MVDR (run_MVDRbeamformer.py path) ----------------------------
+    geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    x4 = O.synth_streams(1, geo4, 12800, seed0=55)[0].copy()               # [4, N]
+    mic4 = MicArray(arrayType="circular", r=0.032, M=4, n_fft=256)
+    ab = H.make_adaptive_mvdr(mic4, 256, 128, 256)
+    ang = np.array([30, 0]) / 180 * np.pi
+    with np.errstate(all="ignore"):
+        ya = ab.process(x4.astype(np.float64), ang, method=2)["data"]
+    save("adaptive_mvdr.npz", x=x4, angle_rad=ang, y=ya, H_last=ab.H, Rvv_last=ab.Rvv, p_last=ab.mcra.p)
+
+
+if __name__ == "__main__":
+    main()

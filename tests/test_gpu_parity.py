@@ -1,0 +1,249 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the numpy oracle and the
+golden vectors dumped from the reference.  Tolerances: spectra are compared
+relative to the frame peak (fp32 FFT), waveforms by the north_star contract
+(max-abs <= 1e-4 and SNR >= 60 dB)."""
+import numpy as np
+import pytest
+
+from conftest import golden, snr_db, assert_wave_parity
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- a1 / a2
+@pytest.mark.parametrize("n_fft,hop,center", [(512, 128, True), (256, 128, False), (1024, 512, True), (128, 64, True),
+                                              (2048, 512, False), (512, 200, True)])
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_stft_vs_oracle(cuda, n_fft, hop, center, precision):
+    from distantspeech_b200.transform.transform import stft
+    rng = np.random.default_rng(n_fft + hop)
+    x = (rng.standard_normal(9000) * 0.2).astype(np.float32)
+    win = O.sqrt_hann(n_fft)
+    ref = O.stft(x.astype(np.float64), n_fft=n_fft, hop_length=hop, window=win, center=center)
+    out = stft(x, n_fft=n_fft, hop_length=hop, window=win, center=center, precision=precision)
+    assert out.shape == ref.shape and out.dtype == np.complex64
+    scale = np.max(np.abs(ref))
+    tol = 3e-6 if precision == "fp32" else 2.5e-7          # fp64 path: complex64 rounding only
+    assert np.max(np.abs(out - ref)) <= tol * scale
+
+
+def test_stft_golden_and_errors(cuda):
+    from distantspeech_b200.transform.transform import stft, istft
+    g = golden("stft_istft.npz")
+    D = stft(g["x"], n_fft=512, hop_length=128, window=O.sqrt_hann(512), center=True, precision="fp64")
+    ref = g["D_512_128_center"]
+    assert np.max(np.abs(D - ref)) <= 2.5e-7 * np.max(np.abs(ref))
+    y = istft(ref, hop_length=128, window=O.sqrt_hann(512), center=True, length=6000)
+    assert y.dtype == np.float32 and np.max(np.abs(y - g["y_512_128_center"])) < 2e-6
+    y2 = istft(g["D_256_128_plain"], hop_length=128, window=O.sqrt_hann(256), center=False)
+    assert np.max(np.abs(y2 - g["y_256_128_plain"])) < 2e-6
+    with pytest.raises(AttributeError):
+        stft(g["x"], n_fft=512)                            # default window="hann" is dead in the reference
+    with pytest.raises(ValueError):
+        stft(g["x"], n_fft=512, window=None)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(512, 256), (512, 128), (256, 128), (1024, 256)])
+def test_istft_gain_quirk(cuda, n_fft, hop):
+    # module-level istft applies no window-sum normalisation: gain 1 at hop=n/2, 2 at hop=n/4 (quirk 2)
+    from distantspeech_b200.transform.transform import stft, istft
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(8192) * 0.2).astype(np.float32)
+    win = O.sqrt_hann(n_fft)
+    y = istft(stft(x, n_fft=n_fft, hop_length=hop, window=win), hop_length=hop, window=win, length=8192)
+    gain = (n_fft // hop) / 2.0
+    assert np.max(np.abs(y[n_fft:-n_fft] - gain * x[n_fft:-n_fft])) < 5e-6
+    ref = O.istft(O.stft(x.astype(np.float64), n_fft=n_fft, hop_length=hop, window=win), hop_length=hop, window=win, length=8192)
+    assert np.max(np.abs(y - ref)) < 5e-6
+
+
+# ---------------------------------------------------------------- a3
+def test_transform_streaming_golden(cuda):
+    from distantspeech_b200.transform.transform import Transform
+    g = golden("transform_stream.npz")
+    x = g["x"]
+    tf = Transform(n_fft=512, hop_length=256, channel=3)
+    tf2 = Transform(n_fft=512, hop_length=256, channel=3)
+    cuts = [(0, 256 * 5), (256 * 5, 256 * 6), (256 * 6, 256 * 12)]
+    for i, (a, b) in enumerate(cuts):
+        Y = tf.stft(x[a:b])
+        ref = g["Y%d" % i]
+        assert Y.shape == ref.shape and Y.dtype == np.complex128
+        assert np.max(np.abs(Y - ref)) <= 3e-6 * np.max(np.abs(ref))
+        y = np.atleast_2d(tf2.istft(ref))
+        assert y.shape == g["y%d" % i].shape
+        assert np.max(np.abs(y - g["y%d" % i])) < 2e-6
+    assert np.array_equal(tf.previous_input, g["prev_in"])
+    assert np.max(np.abs(tf2.previous_output - g["prev_out"])) < 2e-6
+
+
+def test_transform_rank_semantics_and_reconstruction(cuda):
+    from distantspeech_b200.transform.transform import Transform
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((256 * 16, 2)) * 0.2).astype(np.float32)
+    tf = Transform(n_fft=512, hop_length=256, channel=2)
+    Y = tf.stft(x)
+    assert Y.shape == (257, 16, 2)
+    y = tf.istft(Y)
+    assert y.shape == (256 * 16, 2)
+    assert np.max(np.abs(y[256:] - x[:-256])) < 3e-6          # delay = n_fft - hop
+    # 2-D input to istft means ONE frame x channels (quirk 5), 1-D means one frame / one channel
+    tf3 = Transform(n_fft=512, hop_length=256, channel=2)
+    assert tf3.istft(Y[:, 0, :]).shape == (256, 2)
+    assert tf3.istft(Y[:, 1, 0]).shape == (256,)
+    # hop-by-hop streaming equals batch
+    tfs = Transform(n_fft=512, hop_length=256, channel=2)
+    tfo = Transform(n_fft=512, hop_length=256, channel=2)
+    ys = np.concatenate([tfo.istft(tfs.stft(x[i:i + 256])) for i in range(0, x.shape[0], 256)])
+    assert np.max(np.abs(ys - y)) < 1e-6
+
+
+# ---------------------------------------------------------------- a9
+@pytest.mark.parametrize("wt", ["SD", "DS"])
+def test_fixed_beamformer_golden(cuda, wt):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.fixedbeamformer import FixedBeamformer
+    g = golden("fixedbf.npz")
+    mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=256)
+    fb = FixedBeamformer(mic, 256, 128, 256)
+    y = fb.process(g["x"], tuple(g["angle"]), weightType=None if wt == "SD" else "DS")
+    assert np.allclose(fb.W, g["W_sd" if wt == "SD" else "W_ds"], rtol=0, atol=1e-12)
+    assert_wave_parity(g["y_sd" if wt == "SD" else "y_ds"], y, "fixed %s" % wt)
+
+
+def test_fixed_beamformer_batch_stream_multibeam(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.fixedbeamformer import FixedBeamformer
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    xs = O.synth_streams(5, geo, 256 * 40, seed0=11)                       # [S, M, N]
+    x_nm = np.ascontiguousarray(xs.transpose(0, 2, 1))                     # [S, N, M]
+    mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=512)
+    fb = FixedBeamformer(mic, 512, 256, 512)
+    y = fb.process(x_nm, (30, 0))
+    W = O.fixed_weights(geo, 512, (30, 0), "SD")
+    for s in range(5):
+        assert_wave_parity(O.fixed_beamform(x_nm[s].astype(np.float64), W, 512, 256), y[s], "stream %d" % s)
+    # two chunks == one call (streaming state), segment split == no split (S small -> segmented launch)
+    fb2 = FixedBeamformer(mic, 512, 256, 512)
+    ya = fb2.process(x_nm[:, :256 * 15], (30, 0))
+    yb = fb2.process(x_nm[:, 256 * 15:], (30, 0))
+    assert np.max(np.abs(np.concatenate([ya, yb], axis=1) - y)) < 1e-6
+    # multibeam
+    fb3 = FixedBeamformer(mic, 512, 256, 512)
+    ym = fb3.process_multibeam(x_nm, [(30, 0), (200, 0), (90, 10)], weightType="DS")
+    for b, ang in enumerate([(30, 0), (200, 0), (90, 10)]):
+        Wb = O.fixed_weights(geo, 512, ang, "DS")
+        assert_wave_parity(O.fixed_beamform(x_nm[1].astype(np.float64), Wb, 512, 256), ym[1, b], "beam %d" % b)
+
+
+def test_fixed_beamformer_quarter_hop(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.fixedbeamformer import FixedBeamformer
+    geo = O.MicGeometry("linear", r=0.04, M=4, n_fft=256)
+    x = np.ascontiguousarray(O.synth_streams(1, geo, 64 * 100, seed0=5)[0].T)
+    mic = MicArray(arrayType="linear", r=0.04, M=4, n_fft=256)
+    fb = FixedBeamformer(mic, 256, 64, 256)
+    y = fb.process(x, (60, 0), weightType="DS")
+    ref = O.fixed_beamform(x.astype(np.float64), O.fixed_weights(geo, 256, (60, 0), "DS"), 256, 64)
+    assert_wave_parity(ref, y, "hop n/4")
+
+
+# ---------------------------------------------------------------- a12
+def test_mcra_golden_bit_exact(cuda):
+    from distantspeech_b200.noise_estimation.mcra import NoiseEstimationMCRA
+    g = golden("mcra.npz")
+    P = g["P"]
+    m = NoiseEstimationMCRA(nfft=256)
+    for n in range(20):                                       # per-frame API like the reference loop
+        lam = m.estimation(P[:, n])
+        assert np.array_equal(lam, g["lambda_d"][:, n]), n
+        assert np.array_equal(m.p, g["p"][:, n]), n
+    lam, p = m.estimation_frames(P[:, 20:].T.copy(), return_p=True)   # rest in one launch
+    assert np.array_equal(lam.T, g["lambda_d"][:, 20:])
+    assert np.array_equal(p.T, g["p"][:, 20:])
+    assert np.array_equal(m.S, g["S"]) and np.array_equal(m.Smin, g["Smin"]) and np.array_equal(m.Stmp, g["Stmp"])
+    assert m.ell == int(g["ell"]) and m.frm_cnt == int(g["frm_cnt"])
+
+
+# ---------------------------------------------------------------- a13 + a6 + config 4
+def test_mcspp_estimator_golden(cuda):
+    from distantspeech_b200.noise_estimation.mcspp_base import McSppBase
+    from distantspeech_b200.beamformer.beamformer import compute_mvdr_weight
+    g = golden("chain_mcspp_mvdr.npz")
+    D = O.Transform(n_fft=512, hop_length=256, channel=8).stft(g["x"].astype(np.float64))     # oracle spectrum
+    est = McSppBase(nfft=512, channels=8)
+    nT = D.shape[1]
+    worst = {}
+    for n in range(12):                                       # per-frame API
+        p = est.estimation(D[:, n, :])
+        est.compute_omlsa_weight(est.xi, est.p)
+        for k, v in (("p", p), ("xi", est.xi), ("gamma", est.gamma), ("q", est.q), ("G", est.G)):
+            ref = g[k][:, n].astype(np.float64)
+            rel = np.max(np.abs(v - ref) / (np.abs(ref) + 1e-12))
+            worst[k] = max(worst.get(k, 0), rel)
+    assert worst["q"] < 1e-6 and worst["p"] < 1e-5 and worst["G"] < 1e-5, worst
+    assert worst["xi"] < 1e-6 and worst["gamma"] < 1e-6, worst
+    res = est.estimation_frames(D[:, 12:, :], a0=g["a0"])     # remaining frames in one launch
+    assert np.allclose(res["xi"], g["xi"][:, 12:], rtol=1e-5)
+    assert np.allclose(res["p"], g["p"][:, 12:], atol=1e-5)
+    assert np.allclose(est.Phi_vv, g["Phi_vv_last"], rtol=1e-7, atol=1e-12)
+    assert np.allclose(est.Phi_yy, g["Phi_yy_last"], rtol=1e-7, atol=1e-12)
+    assert np.allclose(est.w, g["w_pmwf_last"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(est.Phi_vv_inv, g["Phi_vv_inv_last"], rtol=1e-6, atol=1e-9)
+    Yref = g["Yspec"][:, 12:]
+    assert np.max(np.abs(res["Y"] - Yref)) <= 1e-5 * np.max(np.abs(Yref))
+    w = compute_mvdr_weight(g["a0"], est.Phi_vv_inv)
+    wr = O.mvdr_weight(g["a0"], g["Phi_vv_inv_last"])
+    assert np.allclose(w, wr, rtol=1e-5, atol=1e-9)
+    assert np.allclose(np.sum(np.conj(w) * g["a0"], axis=1), 1.0, atol=1e-9)      # distortionless
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp64"])
+@pytest.mark.parametrize("full", [False, True])
+def test_chain_golden(cuda, prec, full):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.pipelines import MvdrMcsppChain
+    g = golden("chain_mcspp_mvdr.npz")
+    mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=512)
+    ch = MvdrMcsppChain(mic, look_angle=tuple(g["look"]), n_fft=512, hop=256, fft_precision=prec, full_state=full)
+    y = ch.process(g["x"])
+    err, s = assert_wave_parity(g["y"], y, "chain %s full=%s" % (prec, full))
+    print("chain %s full=%s: max-abs %.2e SNR %.1f dB" % (prec, full, err, s))
+
+
+def test_chain_batch_and_streaming(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.pipelines import MvdrMcsppChain
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    xs = O.synth_streams(4, geo, 256 * 125, seed0=0x5EED)                  # 2 s
+    mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=512)
+    x_nm = np.ascontiguousarray(xs.transpose(0, 2, 1))
+    ch = MvdrMcsppChain(mic, look_angle=(30, 0))
+    y = ch.process(x_nm)
+    worst = 1e9
+    for s in range(4):
+        ref = O.mvdr_mcspp_chain(x_nm[s].astype(np.float64), geo, (30, 0), 512, 256)
+        err, snr = assert_wave_parity(ref, y[s], "chain stream %d" % s)
+        worst = min(worst, snr)
+    print("chain batch worst SNR %.1f dB" % worst)
+    ch2 = MvdrMcsppChain(mic, look_angle=(30, 0))
+    ya = ch2.process(x_nm[:, :256 * 50])
+    yb = ch2.process(x_nm[:, 256 * 50:])
+    assert np.max(np.abs(np.concatenate([ya, yb], axis=1) - y)) < 1e-6      # chunked == whole
+    # host-buffer pipeline == device path
+    import torch
+    yh = ch.process_host(torch.from_numpy(xs).pin_memory(), chunk_streams=3)
+    assert np.max(np.abs(yh.numpy() - y)) < 1e-6
+
+
+@pytest.mark.parametrize("M", [2, 4, 6])
+def test_chain_other_mic_counts(cuda, M):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.pipelines import MvdrMcsppChain
+    geo = O.MicGeometry("circular" if M != 6 else "linear", r=0.04, M=M, n_fft=256)
+    x = np.ascontiguousarray(O.synth_streams(1, geo, 128 * 120, seed0=M)[0].T)
+    mic = MicArray(arrayType="circular" if M != 6 else "linear", r=0.04, M=M, n_fft=256)
+    ch = MvdrMcsppChain(mic, look_angle=(30, 0), n_fft=256, hop=128)
+    ref = O.mvdr_mcspp_chain(x.astype(np.float64), geo, (30, 0), 256, 128)
+    assert_wave_parity(ref, ch.process(x), "chain M=%d" % M)
