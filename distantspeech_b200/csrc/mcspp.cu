@@ -15,6 +15,7 @@
 // HBM is only touched at the start and the end of the launch.
 #include "common.cuh"
 #include "perbin.cuh"
+#include "mcspp_args.cuh"
 
 namespace ds {
 
@@ -53,20 +54,8 @@ __global__ void mcra_kernel(McraArgs a) {
 // ===========================================================================
 // McSppBase + MVDR + OMLSA
 // ===========================================================================
-struct McsppArgs {
-  double *state;            // [S][NE][K]
-  const double2 *a0;        // [M][K] or null
-  const void *X;            // [S][T][M][K] float2 or double2
-  float2 *Yout;             // [S][T][K] or null
-  double *tp, *txi, *tgamma, *tq, *tG;   // taps [S][T][K]
-  double2 *tw_mvdr, *tw_pmwf;            // taps [S][T][M][K]
-  double *tAinv;                         // [S][K][M][M] last frame only
-  int S, K, T, frm_cnt, ell, k_first, apply_gain;
-  double alpha, alpha_d, eps, q_min, q_max, p_min, p_max, snr_min, snr_max, Gmin, logGmin;
-  McraConst mc;
-};
+// McsppArgs: see mcspp_args.cuh
 
-template <int M> __host__ __device__ constexpr int mcspp_state_elems() { return 2 * M * M + 5; }
 
 template <typename XT> struct XLoad;
 template <> struct XLoad<float2> {
@@ -381,6 +370,7 @@ int mcspp_run_impl(const ds_mcspp_params *p, void *state, const void *a0, const 
   const bool any_tap = a.tp || a.txi || a.tgamma || a.tq || a.tG || a.tw_mvdr || a.tw_pmwf || a.tAinv;
   // output-only mode may skip bins 0 and 1 (their gain is identically 0)
   a.k_first = (!p->full_state && apply_gain && a0 && Yout && !any_tap) ? 2 : 0;
+  if (!p->full_state && a0 && Yout && !any_tap && !x_is_c128) return launch_mcspp_fast(p->n_mics, a, st);
   return launch_mcspp(p->n_mics, a, p->full_state != 0, x_is_c128 != 0, st);
 }
 
