@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libds_b200.so")
+LIB_PATH = os.environ.get("DS_B200_LIB", os.path.join(_HERE, "libds_b200.so"))   # override: A/B testing of builds
 
 DS_OK = 0
 DS_STFT_STREAMING, DS_STFT_CENTER, DS_STFT_PLAIN = 0, 1, 2

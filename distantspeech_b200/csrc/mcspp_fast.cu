@@ -24,42 +24,32 @@ template <int B, int E, typename F> __device__ __forceinline__ void sfor(F &&f) 
 }
 #define SIDX(ic) (decltype(ic)::value)
 
-// In-place inverse of an SPD matrix in packed upper storage (Cholesky R = U^T U,
-// V = U^-1, A = V V^T), all indices compile-time.
+template <int M> __host__ __device__ constexpr int psym(int i, int j) { return i <= j ? pidx<M>(i, j) : pidx<M>(j, i); }
+
+// In-place inverse of an SPD matrix in packed upper storage by symmetric Gauss-Jordan
+// sweeps (sweep operator): after sweeping every pivot the array holds -A^-1, which is
+// negated on the way out.  Compared with Cholesky (U, U^-1, U^-1 U^-T) the dependent
+// chain per pivot is one reciprocal + two FMA levels, and the 28 rank-1 updates of a
+// pivot are independent -- this is what the fp64 pipe needs at 2-3 warps per scheduler.
 template <int M> __device__ __forceinline__ void spd_inverse_packed(double (&a)[M * (M + 1) / 2]) {
-  double invd[M];
-  sfor<0, M>([&](auto ic) {
-    constexpr int i = SIDX(ic);
-    double d = a[pidx<M>(i, i)];
-    sfor<0, i>([&](auto kc) { constexpr int k = SIDX(kc); d = fma(-a[pidx<M>(k, i)], a[pidx<M>(k, i)], d); });
-    const double r = rsqrt(d);
-    invd[i] = r;
-    sfor<i + 1, M>([&](auto jc) {
-      constexpr int j = SIDX(jc);
-      double v = a[pidx<M>(i, j)];
-      sfor<0, i>([&](auto kc) { constexpr int k = SIDX(kc); v = fma(-a[pidx<M>(k, i)], a[pidx<M>(k, j)], v); });
-      a[pidx<M>(i, j)] = v * r;
-    });
-  });
-  sfor<0, M>([&](auto jc) {
-    constexpr int j = SIDX(jc);
-    sfor<0, j>([&](auto ic) {
+  sfor<0, M>([&](auto kc) {
+    constexpr int k = SIDX(kc);
+    const double r = rcp_pos(a[pidx<M>(k, k)]);
+    double t[M];
+    sfor<0, M>([&](auto ic) { constexpr int i = SIDX(ic); if constexpr (i != k) t[i] = a[psym<M>(i, k)] * r; });
+    sfor<0, M>([&](auto ic) {
       constexpr int i = SIDX(ic);
-      double acc = invd[i] * a[pidx<M>(i, j)];
-      sfor<i + 1, j>([&](auto kc) { constexpr int k = SIDX(kc); acc = fma(a[pidx<M>(i, k)], a[pidx<M>(k, j)], acc); });
-      a[pidx<M>(i, j)] = -acc * invd[j];
+      if constexpr (i != k) {
+        sfor<i, M>([&](auto jc) {
+          constexpr int j = SIDX(jc);
+          if constexpr (j != k) a[pidx<M>(i, j)] = fma(-t[i], a[psym<M>(j, k)], a[pidx<M>(i, j)]);
+        });
+      }
     });
+    sfor<0, M>([&](auto ic) { constexpr int i = SIDX(ic); if constexpr (i != k) a[psym<M>(i, k)] = t[i]; });
+    a[pidx<M>(k, k)] = -r;
   });
-  sfor<0, M>([&](auto ic) { constexpr int i = SIDX(ic); a[pidx<M>(i, i)] = invd[i]; });
-  sfor<0, M>([&](auto ic) {
-    constexpr int i = SIDX(ic);
-    sfor<i, M>([&](auto jc) {
-      constexpr int j = SIDX(jc);
-      double acc = 0.0;
-      sfor<j, M>([&](auto kc) { constexpr int k = SIDX(kc); acc = fma(a[pidx<M>(i, k)], a[pidx<M>(j, k)], acc); });
-      a[pidx<M>(i, j)] = acc;
-    });
-  });
+  sfor<0, M * (M + 1) / 2>([&](auto ec) { constexpr int e = SIDX(ec); a[e] = -a[e]; });
 }
 
 // non-CSE-able read-only loads: the kernel re-reads small per-bin constants instead of
@@ -117,7 +107,7 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
       mcra_step(mS, mSmin, mStmp, mp, mlam, Ym1, Y0, Yp1, k, K, frm, reset, a.mc);
       if (reset) ell = 0;
       ++ell; ++frm;
-      q = fmin(fmax(sqrt(1.0 - mp), a.q_min), a.q_max);
+      q = fmin(fmax(sqrt_pos(1.0 - mp), a.q_min), a.q_max);
     }
     Xp += M * K;
 
@@ -218,7 +208,8 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
 
     // ---- P6: posterior SPP                                                   :124-138
     const double xi1 = 1.0 + xi;
-    double p = 1.0 / (1.0 + q / (1.0 - q) * xi1 * exp(-1.0 * (gam / xi1)));
+    const double rxi1 = rcp_pos(xi1);
+    double p = rcp_pos(1.0 + q * rcp_pos(1.0 - q) * xi1 * exp(-1.0 * (gam * rxi1)));
     p = fmin(fmax(p, a.p_min), a.p_max);
 
     // ---- noise PSD update                                                    :299-319
@@ -235,9 +226,9 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
     }
 
     // ---- OMLSA gain and output  Y = (w^H y) G,  w = A a / den                :140-155
-    double scale = 1.0 / den;
+    double scale = rcp_pos(den);
     if (a.apply_gain) {
-      double G = exp(p * log(xi / xi1) + (1.0 - p) * a.logGmin);
+      double G = exp(p * log(xi * rxi1) + (1.0 - p) * a.logGmin);
       G = fmax(fmin(G, 1.0), a.Gmin);
       if (k < 2) G = 0.0;
       scale *= G;
@@ -255,9 +246,9 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
 
 template <int M>
 static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
-  constexpr int NT = 128;
+  constexpr int NT = 64;
   constexpr int NP = M * (M + 1) / 2;
-  constexpr int MINB = (M >= 7) ? 3 : 4;
+  constexpr int MINB = 4;            // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
   const size_t smem = (size_t)2 * NP * NT * sizeof(double);
   auto kern = mcspp_fast_kernel<M, NT, MINB>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

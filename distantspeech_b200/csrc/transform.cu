@@ -18,51 +18,78 @@ struct StftArgs {
   int S, C, Ns, T, hop, mode, out_c128;
 };
 
-constexpr int STFT_WARPS = 4;
+constexpr int STFT_WARPS = 8;
 
+// One warp per frame.  Twiddles and the window are staged once per CTA in shared
+// memory; interior frames of 16-byte aligned rows are read with float4 loads
+// ([stream, mic, sample] rows are contiguous), everything else (history, reflect
+// padding, odd alignment) takes the scalar path.
 template <int N, typename T>
-__global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const typename V2<T>::type *__restrict__ tw_h,
-                                                              const typename V2<T>::type *__restrict__ tw_n) {
+__global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const typename V2<T>::type *__restrict__ tw_h_g,
+                                                              const typename V2<T>::type *__restrict__ tw_n_g) {
   typedef typename V2<T>::type C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int H = N / 2, K = H + 1;
+  constexpr int H = N / 2, K = H + 1, BE = fft_buf_elems(N);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  C2 *buf = reinterpret_cast<C2 *>(smem_raw) + warp * fft_buf_elems(N);
+  C2 *tw_h = reinterpret_cast<C2 *>(smem_raw);          // [H]
+  C2 *tw_n = tw_h + H;                                  // [H/2 + 1] (+1 pad)
+  T *win = reinterpret_cast<T *>(tw_n + H / 2 + 2);     // [N]
+  C2 *buf = reinterpret_cast<C2 *>(win + N) + warp * BE;
   T *fbuf = reinterpret_cast<T *>(buf);
-  const long long total = (long long)a.S * a.C * a.T;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) tw_h[i] = tw_h_g[i];
+  for (int i = threadIdx.x; i <= H / 2; i += blockDim.x) tw_n[i] = tw_n_g[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) win[i] = (T)a.window[i];
+  __syncthreads();
+  const unsigned total = (unsigned)a.S * a.C * a.T;      // host guarantees < 2^31
   const int ov = N - a.hop;
-  for (long long f = (long long)blockIdx.x * STFT_WARPS + warp; f < total; f += (long long)gridDim.x * STFT_WARPS) {
-    const int t = (int)(f % a.T);
-    const int c = (int)((f / a.T) % a.C);
-    const int s = (int)(f / ((long long)a.T * a.C));
-    const float *xs = a.x + ((long long)s * a.C + c) * a.Ns;
-    const float *hs = a.history ? a.history + ((long long)s * a.C + c) * ov : nullptr;
-    for (int n = lane; n < N; n += 32) {
-      int g;
-      float v;
-      if (a.mode == DS_STFT_STREAMING) {
-        g = t * a.hop + n - ov;
-        v = (g < 0) ? hs[ov + g] : xs[g];
-      } else if (a.mode == DS_STFT_CENTER) {
-        g = t * a.hop + n - N / 2;
-        if (g < 0) g = -g;
-        if (g >= a.Ns) g = 2 * (a.Ns - 1) - g;
-        v = xs[g];
-      } else {
-        g = t * a.hop + n;
-        v = xs[g];
+  for (unsigned f = blockIdx.x * STFT_WARPS + warp; f < total; f += gridDim.x * STFT_WARPS) {
+    const unsigned sc = f / (unsigned)a.T;
+    const int t = (int)(f - sc * (unsigned)a.T);
+    const float *xs = a.x + (size_t)sc * a.Ns;
+    int g0;
+    if (a.mode == DS_STFT_STREAMING) g0 = t * a.hop - ov;
+    else if (a.mode == DS_STFT_CENTER) g0 = t * a.hop - N / 2;
+    else g0 = t * a.hop;
+    const bool interior = (g0 >= 0) && (g0 + N <= a.Ns) && ((reinterpret_cast<size_t>(xs + g0) & 15) == 0);
+    if (interior) {
+      const float4 *src = reinterpret_cast<const float4 *>(xs + g0);
+      float4 v[N / 128];
+#pragma unroll
+      for (int i = 0; i < N / 128; ++i) v[i] = __ldg(src + lane + 32 * i);
+#pragma unroll
+      for (int i = 0; i < N / 128; ++i) {
+        const int q = lane + 32 * i;                     // samples 4q .. 4q+3 = complex 2q, 2q+1
+        const T w0 = win[4 * q], w1 = win[4 * q + 1], w2 = win[4 * q + 2], w3 = win[4 * q + 3];
+        buf[FPAD(2 * q)] = mk2<T>((T)v[i].x * w0, (T)v[i].y * w1);
+        buf[FPAD(2 * q + 1)] = mk2<T>((T)v[i].z * w2, (T)v[i].w * w3);
       }
-      // complex element n/2, component n&1, padded per complex element
-      fbuf[2 * FPAD(n >> 1) + (n & 1)] = (T)v * (T)a.window[n];
+    } else {
+      const float *hs = a.history ? a.history + (size_t)sc * ov : nullptr;
+      for (int n = lane; n < N; n += 32) {
+        int g = g0 + n;
+        float v;
+        if (a.mode == DS_STFT_STREAMING) {
+          v = (g < 0) ? hs[ov + g] : xs[g];
+        } else {
+          if (g < 0) g = -g;                              // np.pad(mode="reflect")
+          if (g >= a.Ns) g = 2 * (a.Ns - 1) - g;
+          v = xs[g];
+        }
+        fbuf[2 * FPAD(n >> 1) + (n & 1)] = (T)v * win[n];
+      }
     }
     __syncwarp();
     warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-    const long long obase = (((long long)s * a.T + t) * a.C + c) * K;
+    const size_t obase = (size_t)f * K;                  // [S][T][C][K] with f = (s*C + c)*T + t  -> reorder below
+    (void)obase;
+    const unsigned s = sc / (unsigned)a.C;
+    const unsigned c = sc - s * (unsigned)a.C;
+    const size_t o = (((size_t)s * a.T + t) * a.C + c) * K;
     if (a.out_c128) {
-      double2 *out = reinterpret_cast<double2 *>(a.X) + obase;
+      double2 *out = reinterpret_cast<double2 *>(a.X) + o;
       for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD(k)]; out[k] = make_double2((double)v.x, (double)v.y); }
     } else {
-      float2 *out = reinterpret_cast<float2 *>(a.X) + obase;
+      float2 *out = reinterpret_cast<float2 *>(a.X) + o;
       for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD(k)]; out[k] = make_float2((float)v.x, (float)v.y); }
     }
     __syncwarp();
@@ -93,12 +120,15 @@ __global__ void stft_history_kernel(const float *x, float *history, int Ns, int 
 
 template <int N, typename T>
 static int launch_stft(const StftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
-  const size_t smem = (size_t)STFT_WARPS * fft_buf_elems(N) * sizeof(typename V2<T>::type);
+  typedef typename V2<T>::type C2;
+  constexpr int H = N / 2;
+  const size_t smem = (size_t)(H + H / 2 + 2) * sizeof(C2) + (size_t)N * sizeof(T) + (size_t)STFT_WARPS * fft_buf_elems(N) * sizeof(C2);
   auto kern = stft_kernel<N, T>;
   if (smem > 48 * 1024) DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)a.S * a.C * a.T;
+  if (total >= (1LL << 31)) { set_error("stft: more than 2^31 frames in one call"); return DS_EUNSUPPORTED; }
   long long blocks = (total + STFT_WARPS - 1) / STFT_WARPS;
-  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, STFT_WARPS * 32, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw));
   DS_LAUNCH_CHECK();
