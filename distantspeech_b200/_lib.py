@@ -62,6 +62,14 @@ class McsppTaps(C.Structure):
                 ("w_mvdr", C.c_void_p), ("w_pmwf", C.c_void_p), ("Phi_vv_inv_last", C.c_void_p)]
 
 
+class AmvdrParams(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_frames", C.c_int32),
+                ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32), ("method", C.c_int32),
+                ("alpha_y", C.c_double), ("alpha_v", C.c_double), ("diag", C.c_double), ("vad_thr", C.c_double),
+                ("mcra_alpha_d", C.c_double), ("mcra_alpha_s", C.c_double), ("mcra_delta_s", C.c_double),
+                ("mcra_alpha_p", C.c_double), ("mcra_p_min", C.c_double), ("mcra_p_max", C.c_double)]
+
+
 class ChainParams(C.Structure):
     _fields_ = [("est", McsppParams), ("hop", C.c_int32), ("n_samples", C.c_int32), ("fft_fp64", C.c_int32),
                 ("apply_gain", C.c_int32), ("scale", C.c_double)]
@@ -97,6 +105,12 @@ def _declare(lib):
     lib.ds_mcspp_state_bytes.restype = C.c_size_t
     lib.ds_mcspp_run.argtypes = [C.POINTER(McsppParams), vp, vp, vp, i32, vp, i32, C.POINTER(McsppTaps), vp]
     lib.ds_mcspp_export.argtypes = [C.POINTER(McsppParams), vp, i32, vp, vp]
+    lib.ds_amvdr_default_params.argtypes = [C.POINTER(AmvdrParams), i32, i32, i32, i32]
+    lib.ds_amvdr_default_params.restype = None
+    lib.ds_amvdr_state_bytes.argtypes = [C.POINTER(AmvdrParams)]
+    lib.ds_amvdr_state_bytes.restype = C.c_size_t
+    lib.ds_amvdr_run.argtypes = [C.POINTER(AmvdrParams), vp, vp, vp, vp, vp, vp, vp]
+    lib.ds_amvdr_export.argtypes = [C.POINTER(AmvdrParams), vp, i32, vp, vp]
     lib.ds_chain_state_bytes.argtypes = [C.POINTER(ChainParams)]
     lib.ds_chain_state_bytes.restype = C.c_size_t
     lib.ds_chain_workspace_bytes.argtypes = [C.POINTER(ChainParams)]

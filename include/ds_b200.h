@@ -227,6 +227,37 @@ int ds_mcspp_run(const ds_mcspp_params *p, void *state, const void *a0, const vo
  * 2 mcra block ([S][5][K] float64).                                              */
 int ds_mcspp_export(const ds_mcspp_params *p, const void *state, int field, void *out, void *stream);
 
+/* ---- online MVDR with MCRA-VAD gate (beamformer/adaptivebeamformer.py) ---- */
+typedef struct ds_amvdr_params {
+  int32_t n_fft;
+  int32_t n_streams;
+  int32_t n_mics;   /* 2..8                                                       */
+  int32_t n_frames; /* T                                                          */
+  int32_t frm_cnt;  /* MCRA frames already processed (host-tracked)               */
+  int32_t ell;      /* MCRA window counter at entry                               */
+  int32_t mcra_L;   /* 15                                               mcra.py:25 */
+  int32_t method;   /* AlgorithmList index: 0 src, 1 DS, 2 MVDR, 3 TFGSC      :37 */
+  double alpha_y, alpha_v; /* 0.8, 0.9998                                  :65-66 */
+  double diag;             /* 1e-6 diagonal loading                        :89    */
+  double vad_thr;          /* 0.4: update Rvv where mcra.p < vad_thr       :94    */
+  double mcra_alpha_d, mcra_alpha_s, mcra_delta_s, mcra_alpha_p, mcra_p_min, mcra_p_max;
+} ds_amvdr_params;
+
+void ds_amvdr_default_params(ds_amvdr_params *p, int n_fft, int n_streams, int n_mics, int n_frames);
+size_t ds_amvdr_state_bytes(const ds_amvdr_params *p);
+/* replaces the frame/bin loops of adaptivebeamfomer.process
+ * (adaptivebeamformer.py:69-120): MCRA on channel 0, Ryy / gated Rvv recursions,
+ * Hermitian inverse with diagonal loading, getweights (beamformer.py:306-336) and
+ * the weight apply.
+ *   a      [M][K] c128 propagation vectors exp(-j w_k tao_m)          (:84)
+ *   X      [S][T][M][K] c64        Yout [S][T][K] c64
+ *   H_last [S][K][M] c128 weights of the last frame or NULL
+ *   p_out  [S][T][K] float64 MCRA speech presence or NULL                        */
+int ds_amvdr_run(const ds_amvdr_params *p, void *state, const void *a, const void *X,
+                 void *Yout, void *H_last, double *p_out, void *stream);
+/* dense view of one state field: 0 Rvv, 1 Rvv_inv, 2 Ryy -> [S][K][M][M] c128    */
+int ds_amvdr_export(const ds_amvdr_params *p, const void *state, int field, void *out, void *stream);
+
 /* ---- config-4 chain: STFT -> McSppBase -> MVDR -> OMLSA -> ISTFT ------- */
 typedef struct ds_chain_params {
   ds_mcspp_params est; /* n_frames is derived: n_samples / hop                    */

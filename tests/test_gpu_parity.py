@@ -247,3 +247,63 @@ def test_chain_other_mic_counts(cuda, M):
     ch = MvdrMcsppChain(mic, look_angle=(30, 0), n_fft=256, hop=128)
     ref = O.mvdr_mcspp_chain(x.astype(np.float64), geo, (30, 0), 256, 128)
     assert_wave_parity(ref, ch.process(x), "chain M=%d" % M)
+
+
+# ---------------------------------------------------------------- a11 (config 1)
+def test_adaptive_mvdr_golden(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.adaptivebeamformer import adaptivebeamfomer
+    g = golden("adaptive_mvdr.npz")
+    mic = MicArray(arrayType="circular", r=0.032, M=4, n_fft=256)
+    ab = adaptivebeamfomer(mic, 256, 128, 256)
+    out = ab.process(g["x"], g["angle_rad"], method=2)
+    assert set(out.keys()) == {"data", "WNG", "DI", "beampattern"}
+    err, s = assert_wave_parity(g["y"], out["data"], "adaptive MVDR")
+    print("adaptive MVDR: max-abs %.2e SNR %.1f dB" % (err, s))
+    assert np.array_equal(ab.mcra.p, g["p_last"])                      # MCRA decisions identical
+    assert np.allclose(ab.Rvv, g["Rvv_last"], rtol=1e-6, atol=1e-12)
+    assert np.allclose(ab.H, g["H_last"], rtol=1e-4, atol=1e-7)
+    with pytest.raises(AttributeError):
+        ab.process(g["x"], g["angle_rad"], method=2, retWNG=True)
+
+
+def test_adaptive_mvdr_512_streaming_batch(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.adaptivebeamformer import adaptivebeamfomer
+    geo = O.MicGeometry("circular", r=0.032, M=4, n_fft=512)
+    xs = O.synth_streams(3, geo, 256 * 100, seed0=21)                  # [S, M, N]
+    mic = MicArray(arrayType="circular", r=0.032, M=4, n_fft=512)
+    ang = np.array([30, 0]) / 180 * np.pi
+    ab = adaptivebeamfomer(mic, 512, 256, 512)
+    y = ab.process(xs, ang, method=2)["data"]
+    for s in range(3):
+        ref = O.adaptive_mvdr(xs[s].astype(np.float64), geo, ang, 512, 256)
+        assert_wave_parity(ref, y[s], "adaptive MVDR stream %d" % s)
+    ab2 = adaptivebeamfomer(mic, 512, 256, 512)
+    ya = ab2.process(xs[:, :, :256 * 40], ang, method=2)["data"]
+    yb = ab2.process(xs[:, :, 256 * 40:], ang, method=2)["data"]
+    assert np.max(np.abs(np.concatenate([ya, yb], axis=1) - y)) < 1e-6
+
+
+def test_adaptive_other_methods(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.adaptivebeamformer import adaptivebeamfomer
+    geo = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    x = O.synth_streams(1, geo, 128 * 60, seed0=8)[0]
+    mic = MicArray(arrayType="circular", r=0.032, M=4, n_fft=256)
+    ang = np.array([50, 0]) / 180 * np.pi
+    tao = -1 * geo.r * np.cos(ang[1]) * np.cos(ang[0] - geo.gamma) / geo.c
+    a = np.exp(-1j * (2 * np.pi * np.arange(129) * 16000 / 256)[:, None] * tao[None, :])        # [K, M]
+    y_ds = adaptivebeamfomer(mic, 256, 128, 256).process(x, ang, method=1)["data"]
+    assert_wave_parity(O.fixed_beamform(x.T.astype(np.float64), a / 4, 256, 128), y_ds, "method DS")
+    W0 = np.zeros_like(a)
+    W0[:, 0] = a[:, 0]
+    y_src = adaptivebeamfomer(mic, 256, 128, 256).process(x, ang, method=0)["data"]
+    assert_wave_parity(O.fixed_beamform(x.T.astype(np.float64), W0, 256, 128), y_src, "method src")
+    # TFGSC (beamformer.py:327-333): w = ((Rvv_inv Ryy) - I) u / (trace(Rvv_inv Ryy) - M), checked on the final state
+    ab = adaptivebeamfomer(mic, 256, 128, 256)
+    ab.process(x, ang, method=3)
+    temp = ab.Rvv_inv @ ab.Ryy
+    u = np.zeros((4, 1)); u[0] = 1
+    w = ((temp - np.eye(4)) @ u)[:, :, 0] / (np.trace(temp, axis1=-2, axis2=-1) - 4)[:, None]
+    assert np.allclose(ab.H.T, w, rtol=1e-6, atol=1e-9)
