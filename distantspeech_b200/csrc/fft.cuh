@@ -15,10 +15,17 @@
 
 namespace ds {
 
-// element index -> padded element index (one pad element every 8)
-__host__ __device__ __forceinline__ constexpr int FPAD(int i) { return i + (i >> 3); }
-// number of V2 elements a frame buffer needs (H+1 bins, padded)
-__host__ __device__ constexpr int fft_buf_elems(int n_fft) { return FPAD(n_fft / 2 + 1) + 1; }
+// element index -> swizzled / padded element index.  Chosen by exhaustive search over
+// every warp-level access of the transforms below (Stockham passes, real-FFT split,
+// frame load, bin read-out):
+//   8-byte elements (float2):  XOR swizzle of the 16-element group index  -> 1.10 x the
+//                              conflict-free wavefront count (pad-per-8 was 1.78 x)
+//   16-byte elements (double2): one pad element every 8                    -> 1.10 x
+template <typename T> __host__ __device__ __forceinline__ constexpr int FPAD(int i) {
+  return sizeof(T) == 4 ? (i ^ ((i >> 4) & 7) ^ (((i >> 6) & 1) << 3)) : (i + (i >> 3));
+}
+// number of V2 elements a frame buffer needs (H+1 bins, swizzled within 16-element groups / padded)
+__host__ __device__ constexpr int fft_buf_elems(int n_fft) { return (n_fft / 2 + 1) + (n_fft / 2 + 1) / 8 + 17; }
 
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
@@ -63,7 +70,7 @@ template <int H, int NS, typename T> struct FftPass {
       const int j = lane + 32 * i;
       if (NB % 32 == 0 || j < NB) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[i][r] = buf[FPAD(j + r * NB)];
+        for (int r = 0; r < R; ++r) v[i][r] = buf[FPAD<T>(j + r * NB)];
       }
     }
     __syncwarp();
@@ -82,7 +89,7 @@ template <int H, int NS, typename T> struct FftPass {
         else dft2(v[i]);
         const int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) buf[FPAD(j0 + r * NS)] = v[i][r];
+        for (int r = 0; r < R; ++r) buf[FPAD<T>(j0 + r * NS)] = v[i][r];
       }
     }
     __syncwarp();
@@ -90,14 +97,14 @@ template <int H, int NS, typename T> struct FftPass {
   }
 };
 
-// in-place forward complex FFT of H points held in buf[FPAD(i)], one warp
+// in-place forward complex FFT of H points held in buf[FPAD<T>(i)], one warp
 template <int H, typename T>
 __device__ __forceinline__ void warp_cfft(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h, int lane) {
   FftPass<H, 1, T>::run(buf, tw_h, lane);
 }
 
-// Forward real FFT of N = 2H samples.  On entry buf[FPAD(n)] = (x[2n], x[2n+1]);
-// on exit buf[FPAD(k)] = X[k], k = 0..H.   (numpy.fft.rfft)
+// Forward real FFT of N = 2H samples.  On entry buf[FPAD<T>(n)] = (x[2n], x[2n+1]);
+// on exit buf[FPAD<T>(k)] = X[k], k = 0..H.   (numpy.fft.rfft)
 template <int N, typename T>
 __device__ __forceinline__ void warp_rfft(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h,
                                           const typename V2<T>::type *__restrict__ tw_n, int lane) {
@@ -108,26 +115,26 @@ __device__ __forceinline__ void warp_rfft(typename V2<T>::type *buf, const typen
   // X[k] = s/2 - e ; X[H-k] = conj(s/2 + e)
   for (int k = lane; k <= H / 2; k += 32) {
     if (k == 0) {
-      C a = buf[FPAD(0)];
-      buf[FPAD(0)] = mk2<T>(a.x + a.y, (T)0);
-      buf[FPAD(H)] = mk2<T>(a.x - a.y, (T)0);
+      C a = buf[FPAD<T>(0)];
+      buf[FPAD<T>(0)] = mk2<T>(a.x + a.y, (T)0);
+      buf[FPAD<T>(H)] = mk2<T>(a.x - a.y, (T)0);
     } else {
-      C a = buf[FPAD(k)], b = buf[FPAD(H - k)];
+      C a = buf[FPAD<T>(k)], b = buf[FPAD<T>(H - k)];
       C w = tw_n[k];
       T sx = (T)0.5 * (a.x + b.x), sy = (T)0.5 * (a.y - b.y);
       T dx = (T)0.5 * (a.x - b.x), dy = (T)0.5 * (a.y + b.y);
       // e = i * (w * d)
       T px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;
       T ex = -py, ey = px;
-      buf[FPAD(k)] = mk2<T>(sx - ex, sy - ey);
-      buf[FPAD(H - k)] = mk2<T>(sx + ex, -(sy + ey));
+      buf[FPAD<T>(k)] = mk2<T>(sx - ex, sy - ey);
+      buf[FPAD<T>(H - k)] = mk2<T>(sx + ex, -(sy + ey));
     }
   }
   __syncwarp();
 }
 
-// Inverse real FFT.  On entry buf[FPAD(k)] = Y[k], k = 0..H (imaginary parts of
-// Y[0], Y[H] are ignored like numpy.fft.irfft); on exit buf[FPAD(n)] =
+// Inverse real FFT.  On entry buf[FPAD<T>(k)] = Y[k], k = 0..H (imaginary parts of
+// Y[0], Y[H] are ignored like numpy.fft.irfft); on exit buf[FPAD<T>(n)] =
 // (x[2n], x[2n+1]) * N, i.e. UNSCALED -- the caller folds 1/N into its window.
 template <int N, typename T>
 __device__ __forceinline__ void warp_irfft_unscaled(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h,
@@ -139,27 +146,27 @@ __device__ __forceinline__ void warp_irfft_unscaled(typename V2<T>::type *buf, c
   // we store conj(Z) so that a forward FFT followed by a conjugate is the inverse.
   for (int k = lane; k <= H / 2; k += 32) {
     if (k == 0) {
-      T a = buf[FPAD(0)].x, b = buf[FPAD(H)].x;
-      buf[FPAD(0)] = mk2<T>(a + b, -(a - b));
+      T a = buf[FPAD<T>(0)].x, b = buf[FPAD<T>(H)].x;
+      buf[FPAD<T>(0)] = mk2<T>(a + b, -(a - b));
     } else {
-      C a = buf[FPAD(k)], b = buf[FPAD(H - k)];
+      C a = buf[FPAD<T>(k)], b = buf[FPAD<T>(H - k)];
       C w = tw_n[k];
       T sx = a.x + b.x, sy = a.y - b.y;
       T dx = a.x - b.x, dy = a.y + b.y;
       // conj(w) * d
       T px = w.x * dx + w.y * dy, py = w.x * dy - w.y * dx;
       T fx = -py, fy = px;
-      buf[FPAD(k)] = mk2<T>(sx + fx, -(sy + fy));          // conj(Z[k])
-      buf[FPAD(H - k)] = mk2<T>(sx - fx, (sy - fy));       // conj(Z[H-k]) = s - f
+      buf[FPAD<T>(k)] = mk2<T>(sx + fx, -(sy + fy));          // conj(Z[k])
+      buf[FPAD<T>(H - k)] = mk2<T>(sx - fx, (sy - fy));       // conj(Z[H-k]) = s - f
     }
   }
   __syncwarp();
   warp_cfft<H, T>(buf, tw_h, lane);
   // result r[n] = conj(z[n]) * (2H): x[2n] = r.x, x[2n+1] = -r.y
   for (int n = lane; n < H; n += 32) {
-    C r = buf[FPAD(n)];
+    C r = buf[FPAD<T>(n)];
     r.y = -r.y;
-    buf[FPAD(n)] = r;
+    buf[FPAD<T>(n)] = r;
   }
   __syncwarp();
 }

@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
       for (int i = 0; i < N / 128; ++i) {
         const int q = lane + 32 * i;                     // samples 4q .. 4q+3 = complex 2q, 2q+1
         const T w0 = win[4 * q], w1 = win[4 * q + 1], w2 = win[4 * q + 2], w3 = win[4 * q + 3];
-        buf[FPAD(2 * q)] = mk2<T>((T)v[i].x * w0, (T)v[i].y * w1);
-        buf[FPAD(2 * q + 1)] = mk2<T>((T)v[i].z * w2, (T)v[i].w * w3);
+        buf[FPAD<T>(2 * q)] = mk2<T>((T)v[i].x * w0, (T)v[i].y * w1);
+        buf[FPAD<T>(2 * q + 1)] = mk2<T>((T)v[i].z * w2, (T)v[i].w * w3);
       }
     } else {
       const float *hs = a.history ? a.history + (size_t)sc * ov : nullptr;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
           if (g >= a.Ns) g = 2 * (a.Ns - 1) - g;
           v = xs[g];
         }
-        fbuf[2 * FPAD(n >> 1) + (n & 1)] = (T)v * win[n];
+        fbuf[2 * FPAD<T>(n >> 1) + (n & 1)] = (T)v * win[n];
       }
     }
     __syncwarp();
@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
     const size_t o = (((size_t)s * a.T + t) * a.C + c) * K;
     if (a.out_c128) {
       double2 *out = reinterpret_cast<double2 *>(a.X) + o;
-      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD(k)]; out[k] = make_double2((double)v.x, (double)v.y); }
+      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD<T>(k)]; out[k] = make_double2((double)v.x, (double)v.y); }
     } else {
       float2 *out = reinterpret_cast<float2 *>(a.X) + o;
-      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD(k)]; out[k] = make_float2((float)v.x, (float)v.y); }
+      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD<T>(k)]; out[k] = make_float2((float)v.x, (float)v.y); }
     }
     __syncwarp();
   }
@@ -171,17 +171,17 @@ __device__ __forceinline__ void istft_frame(const IstftArgs &a, int s, int c, in
   const long long ibase = (((long long)s * a.T + t) * a.C + c) * K;
   if (a.in_c128) {
     const double2 *in = reinterpret_cast<const double2 *>(a.Y) + ibase;
-    for (int k = lane; k < K; k += 32) { double2 v = in[k]; buf[FPAD(k)] = mk2<T>((T)v.x, (T)v.y); }
+    for (int k = lane; k < K; k += 32) { double2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
   } else {
     const float2 *in = reinterpret_cast<const float2 *>(a.Y) + ibase;
-    for (int k = lane; k < K; k += 32) { float2 v = in[k]; buf[FPAD(k)] = mk2<T>((T)v.x, (T)v.y); }
+    for (int k = lane; k < K; k += 32) { float2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
   }
   __syncwarp();
   warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
   const T *fb = reinterpret_cast<const T *>(buf);
   const T inv_n = (T)1 / (T)N;
   for (int n = lane; n < N; n += 32) {
-    T v = fb[2 * FPAD(n >> 1) + (n & 1)] * inv_n;      // numpy irfft value
+    T v = fb[2 * FPAD<T>(n >> 1) + (n & 1)] * inv_n;      // numpy irfft value
     dst[n] = (float)((double)v * a.window[n]);         // ifft_window * irfft   (:368)
   }
   __syncwarp();
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(FBF_WARPS * 32) fixedbf_kernel(FixedBfArgs a, 
       for (int n = lane; n < N; n += 32) {
         int g = t * a.hop + n - ov;
         float v = (g < 0) ? hs[ov + g] : xs[g];
-        fb[2 * FPAD(n >> 1) + (n & 1)] = v * win[n];
+        fb[2 * FPAD<float>(n >> 1) + (n & 1)] = v * win[n];
       }
       __syncwarp();
       warp_rfft<N, float>(buf, tw_h, tw_n, lane);
@@ -354,12 +354,12 @@ __global__ void __launch_bounds__(FBF_WARPS * 32) fixedbf_kernel(FixedBfArgs a, 
       const float2 *w = a.W + ((size_t)b * K + k) * a.M;
       float yr = 0.f, yi = 0.f;
       for (int m = 0; m < a.M; ++m) {
-        float2 xv = micbuf[(size_t)m * BE + FPAD(k)];
+        float2 xv = micbuf[(size_t)m * BE + FPAD<float>(k)];
         float2 wv = __ldg(w + m);
         yr += wv.x * xv.x + wv.y * xv.y;
         yi += wv.x * xv.y - wv.y * xv.x;
       }
-      beambuf[(size_t)b * BE + FPAD(k)] = make_float2(yr, yi);
+      beambuf[(size_t)b * BE + FPAD<float>(k)] = make_float2(yr, yi);
     }
     __syncthreads();
     // ---- synthesis + overlap-add: one warp per beam -------------------------
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(FBF_WARPS * 32) fixedbf_kernel(FixedBfArgs a, 
       float *acc = ola + (size_t)b * N;
       // ring: sample g lives at acc[g % N]
       for (int n = lane; n < N; n += 32) {
-        float v = fb[2 * FPAD(n >> 1) + (n & 1)] * inv_n * win[n];
+        float v = fb[2 * FPAD<float>(n >> 1) + (n & 1)] * inv_n * win[n];
         int pos = (t * a.hop + n) & (N - 1);
         acc[pos] = acc[pos] + v;
       }
