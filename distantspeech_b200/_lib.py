@@ -70,6 +70,16 @@ class AmvdrParams(C.Structure):
                 ("mcra_alpha_p", C.c_double), ("mcra_p_min", C.c_double), ("mcra_p_max", C.c_double)]
 
 
+class FdgscParams(C.Structure):
+    _fields_ = [("frame_len", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_samples", C.c_int32),
+                ("filter_len", C.c_int32), ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32),
+                ("fp64", C.c_int32), ("dc_notch", C.c_int32), ("reserved", C.c_int32), ("reserved2", C.c_int32),
+                ("mu_bm", C.c_double), ("mu_aic", C.c_double), ("alpha", C.c_double), ("notch_radius", C.c_double),
+                ("maxnorm", C.c_double), ("delta", C.c_double),
+                ("mcra_alpha_d", C.c_double), ("mcra_alpha_s", C.c_double), ("mcra_delta_s", C.c_double),
+                ("mcra_alpha_p", C.c_double), ("mcra_p_min", C.c_double), ("mcra_p_max", C.c_double)]
+
+
 class ChainParams(C.Structure):
     _fields_ = [("est", McsppParams), ("hop", C.c_int32), ("n_samples", C.c_int32), ("fft_fp64", C.c_int32),
                 ("apply_gain", C.c_int32), ("scale", C.c_double)]
@@ -111,6 +121,12 @@ def _declare(lib):
     lib.ds_amvdr_state_bytes.restype = C.c_size_t
     lib.ds_amvdr_run.argtypes = [C.POINTER(AmvdrParams), vp, vp, vp, vp, vp, vp, vp]
     lib.ds_amvdr_export.argtypes = [C.POINTER(AmvdrParams), vp, i32, vp, vp]
+    lib.ds_fdgsc_default_params.argtypes = [C.POINTER(FdgscParams), i32, i32, i32, i32]
+    lib.ds_fdgsc_default_params.restype = None
+    lib.ds_fdgsc_state_bytes.argtypes = [C.POINTER(FdgscParams)]
+    lib.ds_fdgsc_state_bytes.restype = C.c_size_t
+    lib.ds_fdgsc_run.argtypes = [C.POINTER(FdgscParams), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ds_fir_run.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.ds_chain_state_bytes.argtypes = [C.POINTER(ChainParams)]
     lib.ds_chain_state_bytes.restype = C.c_size_t
     lib.ds_chain_workspace_bytes.argtypes = [C.POINTER(ChainParams)]

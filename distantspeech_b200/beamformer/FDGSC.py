@@ -1,0 +1,170 @@
+"""Overlap-save frequency-domain GSC -- drop-in for ``DistantSpeech/beamformer/FDGSC.py``
+(FDGSC :37, process :201) with its building blocks ``TimeAlignment``
+(fixedbeamformer.py:51-93), ``AdaptiveBlockingMatrixFilter`` (gsc_bm.py),
+``AdaptiveInterferenceCancellation`` (gsc_aic.py), ``FilterDcNotch16`` (feature.py:32-49)
+and the delay lines, all fused into ds_fdgsc_run: one CTA per stream, every filter
+state resident in shared memory for the whole utterance.
+
+``process(x[N, M])`` returns the reference's 9-tuple; ``x`` is overwritten with the
+DC-notched signal like the reference does (FDGSC.py:213).  A leading stream axis
+``x[S, N, M]`` batches independent streams.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib as L
+from ..transform.multirate import fractional_delay_filter_bank
+from ..transform.transform import _sqrt_hann
+from .MicArray import MicArray
+
+
+class TimeAlignment(object):
+    """Fractional-delay alignment towards ``angle`` (fixedbeamformer.py:51-93)."""
+
+    def __init__(self, mic_array: MicArray, angle=[197, 0], frame_len=256, hop=None, nfft=None, r=0.032, fs=16000):
+        self.M = mic_array.M
+        self.angle = np.array(angle) / 180 * np.pi if isinstance(angle, list) else angle
+        self.tau = mic_array.compute_tau(self.angle)
+        self.tau = -(self.tau - np.max(self.tau))
+        delay_samples = np.array(self.tau)[:, 0] * mic_array.fs
+        self.delay_filter = fractional_delay_filter_bank(delay_samples)           # [filter_len, M]
+        self.delay_filter_len = self.delay_filter.shape[0]
+        self.fir_cache = np.zeros((self.delay_filter_len - 1, self.M))
+        self._cache_dev = None
+
+    def process(self, x):
+        """x [samples, chs] -> time-aligned [samples, chs] (streaming FIR, ds_fir_run)."""
+        t = L.require_cuda()
+        xd = t.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64).T)).to("cuda")[None]     # [1, M, N]
+        _, M, N = xd.shape
+        if self._cache_dev is None:
+            self._cache_dev = t.as_tensor(np.ascontiguousarray(self.fir_cache.T)).to("cuda")[None].contiguous()
+        h = t.as_tensor(np.ascontiguousarray(self.delay_filter.T)).to("cuda")
+        y = t.empty_like(xd)
+        scratch = t.empty_like(xd)
+        L.check(L.lib().ds_fir_run(1, M, N, self.delay_filter_len, L.ptr(h), L.ptr(self._cache_dev), L.ptr(xd), L.ptr(y),
+                                   L.ptr(scratch), L.stream_ptr()), "ds_fir_run")
+        self.fir_cache = self._cache_dev[0].t().cpu().numpy()
+        return y[0].t().cpu().numpy()
+
+
+class _FilterView(object):
+    """Read-only view of one adaptive filter (``W`` [257, chs] complex, ``w`` [256, chs]) of the fused kernel."""
+
+    def __init__(self, W):
+        self.W = W
+        self.n_fft = 2 * (W.shape[0] - 1)
+        self.filter_len = self.n_fft // 2
+        self.w = np.fft.irfft(W, n=self.n_fft, axis=0)[: self.filter_len, :]
+
+
+class _McraView(object):
+    def __init__(self):
+        self.L = 60
+        self.alpha_d, self.alpha_s, self.delta_s, self.alpha_p = 0.95, 0.8, 5, 0.2
+        self.p_max, self.p_min = 0.999, 1e-3
+        self.ell, self.frm_cnt = 1, 0
+        self.half_bin = 257
+        self.p = np.zeros(257)
+
+
+class FDGSC(object):
+    def __init__(self, mic_array: MicArray, frameLen=256, angle=[197, 0], precision="fp32"):
+        if frameLen != 256:
+            raise L.DsError("the CUDA FDGSC is compiled for frameLen = 256 (reference default)")
+        self.MicArray = mic_array
+        self.M = mic_array.M
+        self.frameLen = frameLen
+        self.hop = frameLen // 2
+        self.nfft = frameLen * 2
+        self.fs = mic_array.fs
+        self.angle = np.array(angle) / 180 * np.pi if isinstance(angle, list) else angle
+        self.time_alignment = TimeAlignment(mic_array, angle=self.angle)
+        self.gamma = mic_array.gamma
+        self.spp = _McraView()
+        self.precision = precision
+        self.mu_bm, self.mu_aic, self.alpha = 0.1, 0.1, 0.9
+        self.phi, self.psi = None, None          # ccafbounds: computed by the reference ctor but never used
+        self._state = None
+        self._S = None
+        self.bm = None
+        self.aic_filter = None
+
+    def _params(self, S, N):
+        p = L.FdgscParams()
+        L.lib().ds_fdgsc_default_params(C.byref(p), S, self.M, N, self.time_alignment.delay_filter_len)
+        m = self.spp
+        p.frm_cnt, p.ell, p.mcra_L = int(m.frm_cnt), int(m.ell), int(m.L)
+        p.fp64 = int(self.precision == "fp64")
+        p.mu_bm, p.mu_aic, p.alpha = float(self.mu_bm), float(self.mu_aic), float(self.alpha)
+        return p
+
+    def reset(self):
+        self._state = None
+        self.spp.frm_cnt, self.spp.ell = 0, 1
+
+    def process(self, x, postfilter=False, dc_notch=True):
+        """x [n_samples, n_chs] (or [S, n_samples, n_chs]) -> (output, p, fix_output, fix_output_delayed,
+        bm_output, aligned_output, aligned_output_delayed, bm, aic_filter) like FDGSC.py:307-317.
+        ``aligned_output`` / the delayed copies are diagnostics the kernel does not materialise (None)."""
+        if postfilter:
+            raise NotImplementedError("postfilter=True (NsOmlsaMulti inside FDGSC) is not part of this path yet")
+        t = L.require_cuda()
+        L.ensure_init()
+        as_torch = isinstance(x, t.Tensor)
+        xd = L.to_device(x, t.float32)
+        batched = xd.dim() == 3
+        if not batched:
+            xd = xd[None]
+        S, N, M = xd.shape
+        if M != self.M:
+            raise ValueError("expected %d channels, got %d" % (self.M, M))
+        Nb = (N // self.frameLen) * self.frameLen
+        xs = xd.permute(0, 2, 1).contiguous()                                    # [S, M, N]
+        if self._state is None or self._S != S:
+            self._state = t.zeros(L.lib().ds_fdgsc_state_bytes(C.byref(self._params(S, Nb))), dtype=t.uint8, device="cuda")
+            self._S = S
+            self.spp.frm_cnt, self.spp.ell = 0, 1
+        prm = self._params(S, Nb)
+        prm.dc_notch = int(bool(dc_notch))
+        nblk = Nb // self.frameLen
+        xrun = xs if Nb == N else xs[:, :, :Nb].contiguous()
+        y = t.zeros((S, N), dtype=t.float32, device="cuda")
+        yrun = y if Nb == N else t.empty((S, Nb), dtype=t.float32, device="cuda")
+        bm_out = t.zeros((S, M, Nb), dtype=t.float32, device="cuda")
+        fix_out = t.zeros((S, Nb), dtype=t.float32, device="cuda")
+        p_out = t.empty((S, nblk, 257), dtype=t.float64, device="cuda")
+        h = t.as_tensor(np.ascontiguousarray(self.time_alignment.delay_filter.T)).to("cuda")       # [M, FL]
+        L.check(L.lib().ds_fdgsc_run(C.byref(prm), L.ptr(h), L.ptr(L.device_window(_sqrt_hann(512), 512)), L.ptr(self._state),
+                                     L.ptr(xrun), L.ptr(yrun), L.ptr(bm_out), L.ptr(fix_out), L.ptr(p_out), L.stream_ptr()),
+                "ds_fdgsc_run")
+        f, e = C.c_int32(self.spp.frm_cnt), C.c_int32(self.spp.ell)
+        L.lib().ds_mcra_advance(int(self.spp.L), nblk, C.byref(f), C.byref(e))
+        self.spp.frm_cnt, self.spp.ell = f.value, e.value
+        if Nb != N:
+            y[:, :Nb] = yrun
+        # quirk 11: the caller's array now holds the DC-notched signal
+        if dc_notch:
+            notched = xrun.permute(0, 2, 1)
+            if as_torch:
+                (x if batched else x[None])[:, :Nb, :] = notched.to(x.dtype)
+            elif isinstance(x, np.ndarray) and x.flags.writeable:
+                xv = x if batched else x[None]
+                xv[:, :Nb, :] = notched.cpu().numpy().astype(x.dtype)
+        # filter views from the state blob
+        K = 257
+        st = self._state.view(t.float64).view(S, -1)
+        nW = 2 * M * K
+        Wbm = t.view_as_complex(st[:, :nW].reshape(S, M, K, 2).contiguous()).cpu().numpy()
+        Waic = t.view_as_complex(st[:, nW:2 * nW].reshape(S, M, K, 2).contiguous()).cpu().numpy()
+        self.bm = [_FilterView(Wbm[0, m][:, None]) for m in range(M)]
+        self.aic_filter = _FilterView(Waic[0].T)
+        p = p_out.permute(0, 2, 1)
+        self.spp.p = p[0, :, -1].cpu().numpy()
+        outs = [y, p, fix_out, None, bm_out.permute(0, 2, 1), None, None]
+        if not batched:
+            outs = [o[0] if o is not None else None for o in outs]
+        if not as_torch:
+            outs = [o.double().cpu().numpy() if o is not None else None for o in outs]
+        return (outs[0], outs[1], outs[2], outs[3], outs[4], outs[5], outs[6], self.bm, self.aic_filter)

@@ -258,6 +258,49 @@ int ds_amvdr_run(const ds_amvdr_params *p, void *state, const void *a, const voi
 /* dense view of one state field: 0 Rvv, 1 Rvv_inv, 2 Ryy -> [S][K][M][M] c128    */
 int ds_amvdr_export(const ds_amvdr_params *p, const void *state, int field, void *out, void *stream);
 
+/* ---- frequency-domain GSC (beamformer/FDGSC.py) ------------------------- */
+typedef struct ds_fdgsc_params {
+  int32_t frame_len;  /* 256 (block = filter length; FFT length 512)               */
+  int32_t n_streams;
+  int32_t n_mics;     /* 2..8                                                      */
+  int32_t n_samples;  /* multiple of frame_len                                     */
+  int32_t filter_len; /* taps of the time-alignment FIR bank (<= 128)              */
+  int32_t frm_cnt;    /* MCRA frames already processed (host-tracked)              */
+  int32_t ell;        /* MCRA window counter at entry                              */
+  int32_t mcra_L;     /* 60                                          FDGSC.py:99   */
+  int32_t fp64;       /* 0: fp32 filters / FFTs, 1: fp64                           */
+  int32_t dc_notch;   /* 1: apply FilterDcNotch16 in place first     FDGSC.py:211  */
+  int32_t reserved;
+  int32_t reserved2;
+  double mu_bm, mu_aic;   /* 0.1, 0.1                                  FDGSC.py:66,77 */
+  double alpha;           /* 0.9 power smoothing            FastFreqLms.py:158      */
+  double notch_radius;    /* 0.98                                     FDGSC.py:115  */
+  double maxnorm;         /* 0.003                                   gsc_aic.py:85  */
+  double delta;           /* 0.001 tap bound                         gsc_bm.py:51   */
+  double mcra_alpha_d, mcra_alpha_s, mcra_delta_s, mcra_alpha_p, mcra_p_min, mcra_p_max;
+} ds_fdgsc_params;
+
+void ds_fdgsc_default_params(ds_fdgsc_params *p, int n_streams, int n_mics, int n_samples, int filter_len);
+size_t ds_fdgsc_state_bytes(const ds_fdgsc_params *p);
+/* replaces FDGSC.process(x, postfilter=False, dc_notch=...) (FDGSC.py:201-317).
+ *   delay_filter [M][filter_len] float64: fractional_delay_filter_bank of TimeAlignment
+ *                (fixedbeamformer.py:66-72, multirate.py:4-51), host precompute
+ *   window       [512] float64 sqrt-Hann (Transform of FDGSC.py:104)
+ *   x            [S][M][N] float32, IN/OUT: overwritten with the DC-notched signal (FDGSC.py:213)
+ *   y            [S][N] float32 enhanced output (tuple element 0)
+ *   bm_out       [S][M][N] blocking-matrix outputs (element 4) or NULL
+ *   fix_out      [S][N] fixed beamformer output (element 2) or NULL
+ *   p_out        [S][N/256][257] float64 adaptation-control SPP (element 1) or NULL   */
+int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const double *window,
+                 void *state, float *x, float *y, float *bm_out, float *fix_out, double *p_out,
+                 void *stream);
+
+/* replaces TimeAlignment.process / fir_filter (fixedbeamformer.py:13-93): streaming per-channel
+ * FIR y[n] = sum_k h[k] x[n-k] with a (filter_len-1)-sample cache.  All float64:
+ *   h [C][filter_len]   cache [S][C][filter_len-1] in/out   x, y, scratch [S][C][N]   */
+int ds_fir_run(int n_streams, int n_ch, int n_samples, int filter_len, const double *h,
+               double *cache, const double *x, double *y, double *scratch, void *stream);
+
 /* ---- config-4 chain: STFT -> McSppBase -> MVDR -> OMLSA -> ISTFT ------- */
 typedef struct ds_chain_params {
   ds_mcspp_params est; /* n_frames is derived: n_samples / hop                    */

@@ -115,6 +115,22 @@ def main():
         ya = ab.process(x4.astype(np.float64), ang, method=2)["data"]
     save("adaptive_mvdr.npz", x=x4, angle_rad=ang, y=ya, H_last=ab.H, Rvv_last=ab.Rvv, p_last=ab.mcra.p)
 
+    # ---- a17: FDGSC (config 3 shape: 6-mic linear r=0.05, frameLen 256) ------------
+    import contextlib
+    import io
+    from DistantSpeech.beamformer.FDGSC import FDGSC
+    geo6 = O.MicGeometry("linear", r=0.05, M=6, n_fft=256)
+    x6 = O.synth_streams(1, geo6, 256 * 60, look_deg=(60.0, 0.0), interf_deg=(140.0, 0.0), seed0=33)[0].T.copy()
+    mic6 = MicArray(arrayType="linear", r=0.05, M=6, n_fft=256)
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference prints tau / filter shapes
+        fd = FDGSC(mic6, frameLen=256, angle=[60, 0])
+    xin = x6.astype(np.float64)
+    res = fd.process(xin, postfilter=False, dc_notch=True)   # mutates xin (DC notch in place)
+    save("fdgsc.npz", x=x6, angle_deg=np.array([60, 0]), y=res[0], p=res[1].astype(np.float32),
+         fix_output=res[2].astype(np.float32), bm_output=res[4].astype(np.float32),
+         x_notched=xin.astype(np.float32), delay_filter=fd.time_alignment.delay_filter,
+         W_aic_last=fd.aic_filter.W, W_bm0_last=fd.bm[0].W)
+
 
 if __name__ == "__main__":
     main()

@@ -307,3 +307,70 @@ def test_adaptive_other_methods(cuda):
     u = np.zeros((4, 1)); u[0] = 1
     w = ((temp - np.eye(4)) @ u)[:, :, 0] / (np.trace(temp, axis1=-2, axis2=-1) - 4)[:, None]
     assert np.allclose(ab.H.T, w, rtol=1e-6, atol=1e-9)
+
+
+# ---------------------------------------------------------------- a10 / a17 (config 3)
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_fdgsc_golden(cuda, precision):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.FDGSC import FDGSC
+    g = golden("fdgsc.npz")
+    mic = MicArray(arrayType="linear", r=0.05, M=6, n_fft=256)
+    fd = FDGSC(mic, frameLen=256, angle=[int(g["angle_deg"][0]), int(g["angle_deg"][1])], precision=precision)
+    assert np.allclose(fd.time_alignment.delay_filter, g["delay_filter"], rtol=0, atol=1e-15)
+    x = g["x"].copy()
+    res = fd.process(x, postfilter=False, dc_notch=True)
+    assert len(res) == 9
+    assert np.array_equal(x, g["x_notched"])                                  # in-place DC notch, bit exact (quirk 11)
+    err, s = assert_wave_parity(g["y"], res[0], "FDGSC %s" % precision)
+    print("FDGSC %s: max-abs %.2e SNR %.1f dB" % (precision, err, s))
+    assert np.max(np.abs(res[2] - g["fix_output"])) < 2e-6
+    assert np.max(np.abs(res[4] - g["bm_output"])) < 1e-4
+    assert np.mean(np.abs(res[1] - g["p"]) > 1e-6) < 0.01                     # MCRA decisions (fp32 STFT input)
+    rel = np.linalg.norm(fd.aic_filter.W - g["W_aic_last"]) / np.linalg.norm(g["W_aic_last"])
+    assert rel < (1e-3 if precision == "fp32" else 1e-5), rel
+
+
+def test_fdgsc_streaming_batch_and_time_alignment(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.FDGSC import FDGSC, TimeAlignment
+    geo = O.MicGeometry("linear", r=0.05, M=4, n_fft=256)
+    xs = O.synth_streams(3, geo, 256 * 50, look_deg=(75.0, 0.0), interf_deg=(150.0, 0.0), seed0=44)
+    x_nm = np.ascontiguousarray(xs.transpose(0, 2, 1))
+    mic = MicArray(arrayType="linear", r=0.05, M=4, n_fft=256)
+    ang = np.array([75, 0]) / 180 * np.pi
+    fd = FDGSC(mic, frameLen=256, angle=[75, 0])
+    y = fd.process(x_nm.copy())[0]
+    for s in range(3):
+        ref = O.FdgscOracle(geo, 256, ang).process(x_nm[s].astype(np.float64))[0]
+        assert_wave_parity(ref, y[s], "FDGSC stream %d" % s)
+    fd2 = FDGSC(mic, frameLen=256, angle=[75, 0])
+    ya = fd2.process(x_nm[:, :256 * 20].copy())[0]
+    yb = fd2.process(x_nm[:, 256 * 20:].copy())[0]
+    assert np.max(np.abs(np.concatenate([ya, yb], axis=1) - y)) < 1e-6
+    # TimeAlignment.process == oracle FIR, streaming in two blocks
+    ta = TimeAlignment(mic, angle=[75, 0])
+    h = O.alignment_filters(geo, ang)
+    assert np.allclose(ta.delay_filter, h, rtol=0, atol=1e-15)
+    xin = x_nm[0].astype(np.float64)
+    out = np.vstack([ta.process(xin[:1000]), ta.process(xin[1000:3000])])
+    ref = np.stack([np.convolve(xin[:3000, m], h[:, m])[:3000] for m in range(4)], axis=1)
+    assert np.max(np.abs(out - ref)) < 1e-12
+
+
+def test_delay_samples_reference_unittest(cuda):
+    # the reference's own unit test (tests/unittests/test_delay.py:5-23) against our DelaySamples
+    from distantspeech_b200.beamformer.utils import DelaySamples
+    rng = np.random.default_rng(0)
+    for ch in (1, 2):
+        for data_len in (1, 10, 100):
+            for delay in (0, 1, 5, 50, 150):
+                obj = DelaySamples(data_len, delay, channel=ch)
+                x = rng.random((1000, ch))
+                y = np.zeros((1000, ch))
+                for n in range(1000 // data_len):
+                    y[n * data_len:(n + 1) * data_len] = obj.delay(x[n * data_len:(n + 1) * data_len])
+                if delay == 0:
+                    assert np.sum(np.abs(y - x)) < 1e-5
+                else:
+                    assert np.sum(np.abs(y[delay:] - x[:-delay])) < 1e-5
