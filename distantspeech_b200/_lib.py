@@ -80,6 +80,16 @@ class FdgscParams(C.Structure):
                 ("mcra_alpha_p", C.c_double), ("mcra_p_min", C.c_double), ("mcra_p_max", C.c_double)]
 
 
+class OmlsaMultiParams(C.Structure):
+    _fields_ = [("n_bins", C.c_int32), ("n_streams", C.c_int32), ("n_frames", C.c_int32), ("n_mics", C.c_int32),
+                ("first_frame", C.c_int32), ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32),
+                ("cal_weights", C.c_int32), ("reserved", C.c_int32),
+                ("alpha_d", C.c_double), ("alpha_s", C.c_double), ("alpha_xi", C.c_double), ("beta", C.c_double),
+                ("Gmin", C.c_double), ("q_min", C.c_double), ("q_max", C.c_double),
+                ("mcra_alpha_d", C.c_double), ("mcra_alpha_s", C.c_double), ("mcra_delta_s", C.c_double),
+                ("mcra_alpha_p", C.c_double), ("mcra_p_min", C.c_double), ("mcra_p_max", C.c_double)]
+
+
 class ChainParams(C.Structure):
     _fields_ = [("est", McsppParams), ("hop", C.c_int32), ("n_samples", C.c_int32), ("fft_fp64", C.c_int32),
                 ("apply_gain", C.c_int32), ("scale", C.c_double)]
@@ -127,6 +137,14 @@ def _declare(lib):
     lib.ds_fdgsc_state_bytes.restype = C.c_size_t
     lib.ds_fdgsc_run.argtypes = [C.POINTER(FdgscParams), vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ds_fir_run.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.ds_omlsa_multi_default_params.argtypes = [C.POINTER(OmlsaMultiParams), i32, i32, i32, i32]
+    lib.ds_omlsa_multi_default_params.restype = None
+    lib.ds_omlsa_multi_state_bytes.argtypes = [C.POINTER(OmlsaMultiParams)]
+    lib.ds_omlsa_multi_state_bytes.restype = C.c_size_t
+    lib.ds_omlsa_multi_run.argtypes = [C.POINTER(OmlsaMultiParams), vp, vp, vp, vp, vp, vp, vp]
+    lib.ds_zelinski_state_bytes.argtypes = [i32, i32, i32]
+    lib.ds_zelinski_state_bytes.restype = C.c_size_t
+    lib.ds_zelinski_run.argtypes = [i32, i32, i32, i32, dbl, dbl, vp, vp, vp, vp, vp]
     lib.ds_chain_state_bytes.argtypes = [C.POINTER(ChainParams)]
     lib.ds_chain_state_bytes.restype = C.c_size_t
     lib.ds_chain_workspace_bytes.argtypes = [C.POINTER(ChainParams)]

@@ -227,6 +227,34 @@ int ds_mcspp_run(const ds_mcspp_params *p, void *state, const void *a0, const vo
  * 2 mcra block ([S][5][K] float64).                                              */
 int ds_mcspp_export(const ds_mcspp_params *p, const void *state, int field, void *out, void *stream);
 
+/* ---- postfilter gains ------------------------------------------------------ */
+typedef struct ds_omlsa_multi_params {
+  int32_t n_bins, n_streams, n_frames;
+  int32_t n_mics;      /* M: beam output + M-1 references, 2..8                     */
+  int32_t first_frame; /* 1 until the first frame has been seen (host-tracked) omlsa_multi.py:87 */
+  int32_t frm_cnt, ell, mcra_L; /* shared by the M MCRA trackers (15)                */
+  int32_t cal_weights; /* compute the OMLSA gain G                           :152   */
+  int32_t reserved;
+  double alpha_d, alpha_s, alpha_xi; /* 0.85, 0.8, 0.921                  :53,70,96 */
+  double beta;                       /* 1.47                                   :149  */
+  double Gmin, q_min, q_max;         /* 10^-1.2, 1e-6, 0.9999998            :35-50   */
+  double mcra_alpha_d, mcra_alpha_s, mcra_delta_s, mcra_alpha_p, mcra_p_min, mcra_p_max;
+} ds_omlsa_multi_params;
+void ds_omlsa_multi_default_params(ds_omlsa_multi_params *p, int n_bins, int n_streams, int n_frames, int n_mics);
+size_t ds_omlsa_multi_state_bytes(const ds_omlsa_multi_params *p);
+/* replaces NsOmlsaMulti.estimation (noise_estimation/omlsa_multi.py:73-156) over T frames.
+ *   y [S][T][K] beam-output power, u [S][T][M-1][K] reference powers (float64)
+ *   G_out / lambda_out / p_out [S][T][K] or NULL                                  */
+int ds_omlsa_multi_run(const ds_omlsa_multi_params *p, void *state, const double *y, const double *u,
+                       double *G_out, double *lambda_out, double *p_out, void *stream);
+
+size_t ds_zelinski_state_bytes(int n_streams, int n_mics, int n_bins);
+/* replaces PostFilter.update_CSD_PSD + getweights (postfilter/postfilter.py:19-84).
+ *   Z [S][T][M][K] c128, Fvv [K][M][M] float64 diffuse coherence, W [S][T][K] float64 out
+ *   alpha 0.8 (:52), coh_max 0.7 (:68)                                             */
+int ds_zelinski_run(int n_streams, int n_frames, int n_mics, int n_bins, double alpha, double coh_max,
+                    void *state, const void *Z, const double *Fvv, double *W, void *stream);
+
 /* ---- online MVDR with MCRA-VAD gate (beamformer/adaptivebeamformer.py) ---- */
 typedef struct ds_amvdr_params {
   int32_t n_fft;

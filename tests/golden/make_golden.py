@@ -131,6 +131,25 @@ def main():
          x_notched=xin.astype(np.float32), delay_filter=fd.time_alignment.delay_filter,
          W_aic_last=fd.aic_filter.W, W_bm0_last=fd.bm[0].W)
 
+    # ---- a15: NsOmlsaMulti on the FDGSC outputs, a16: Zelinski postfilter weights -------
+    from DistantSpeech.noise_estimation.omlsa_multi import NsOmlsaMulti
+    from DistantSpeech.postfilter.postfilter import PostFilter
+    tfy = Transform(n_fft=512, hop_length=256, channel=1)
+    tfu = Transform(n_fft=512, hop_length=256, channel=5)
+    Yp = (np.abs(tfy.stft(res[0])[:, :, 0]) ** 2).astype(np.float32).astype(np.float64)      # [257, T]
+    Up = (np.abs(tfu.stft(res[4][:, :5])) ** 2).astype(np.float32).astype(np.float64)        # [257, T, 5]
+    om = NsOmlsaMulti(nfft=512, cal_weights=True, M=6)
+    Gs, lams, ps = [], [], []
+    for n in range(Yp.shape[1]):
+        om.estimation(Yp[:, n], Up[:, n, :])
+        Gs.append(om.G.copy()); lams.append(np.array(om.lambda_d, dtype=float).copy()); ps.append(om.p.copy())
+    save("omlsa_multi.npz", Y=Yp.astype(np.float32), U=Up.astype(np.float32), G=np.array(Gs), lambda_d=np.array(lams),
+         p=np.array(ps))
+    pf = PostFilter(mic8, 256, 128, 256)
+    Z8 = D8[:, :40, :].transpose(2, 0, 1)                              # [M, K, T] from the fixed-BF fixture
+    Ws = np.array([pf.getweights(Z8[:, :, n]).squeeze() for n in range(40)])
+    save("zelinski.npz", Z=Z8.astype(np.complex64), W=Ws, Pxii=pf.Pxii, Pxij=pf.Pxij)
+
 
 if __name__ == "__main__":
     main()

@@ -374,3 +374,35 @@ def test_delay_samples_reference_unittest(cuda):
                     assert np.sum(np.abs(y - x)) < 1e-5
                 else:
                     assert np.sum(np.abs(y[delay:] - x[:-delay])) < 1e-5
+
+
+# ---------------------------------------------------------------- a15 / a16
+def test_omlsa_multi_golden(cuda):
+    from distantspeech_b200.noise_estimation.omlsa_multi import NsOmlsaMulti
+    g = golden("omlsa_multi.npz")
+    Y, U = g["Y"].astype(np.float64), g["U"].astype(np.float64)
+    om = NsOmlsaMulti(nfft=512, cal_weights=True, M=6)
+    assert om.estimation(Y[:, 0], U[:, 0, :]) is None
+    for n in range(1, 6):                                              # per-frame API
+        lam = om.estimation(Y[:, n], U[:, n, :])
+        assert np.allclose(lam, g["lambda_d"][n], rtol=1e-12, atol=1e-300)
+        assert np.allclose(om.G, g["G"][n], rtol=1e-9) and np.allclose(om.p, g["p"][n], rtol=1e-9, atol=1e-15)
+    res = om.estimation_frames(Y[:, 6:].T.copy(), U[:, 6:, :].transpose(1, 0, 2).copy())
+    assert np.allclose(res["G"], g["G"][6:], rtol=1e-9)
+    assert np.allclose(res["p"], g["p"][6:], rtol=1e-9, atol=1e-15)
+    assert np.allclose(res["lambda_d"], g["lambda_d"][6:], rtol=1e-12, atol=1e-300)
+
+
+def test_zelinski_postfilter_golden(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.postfilter.postfilter import PostFilter
+    g = golden("zelinski.npz")
+    pf = PostFilter(MicArray(arrayType="circular", r=0.05, M=8, n_fft=256), 256, 128, 256)
+    for n in range(g["Z"].shape[2]):
+        W = pf.getweights(g["Z"][:, :, n].astype(complex))
+        assert W.shape == (129,)
+        assert np.allclose(W, g["W"][n], rtol=1e-10, atol=1e-14)
+    assert np.allclose(pf.Pxii, g["Pxii"], rtol=1e-12)
+    assert np.allclose(pf.Pxij, g["Pxij"], rtol=1e-12, atol=1e-30)
+    with pytest.raises(AttributeError):
+        pf.process(None, None, None)

@@ -1,0 +1,38 @@
+"""CPU: oracle vs reference-generated goldens for the FDGSC / postfilter rows (a10, a15, a16, a17)."""
+import numpy as np
+
+from conftest import golden, snr_db
+from oracle import np_oracle as O
+
+
+def test_fdgsc_golden():
+    g = golden("fdgsc.npz")
+    geo = O.MicGeometry("linear", r=0.05, M=6, n_fft=256)
+    o = O.FdgscOracle(geo, 256, g["angle_deg"] / 180 * np.pi)
+    assert np.allclose(o.h, g["delay_filter"], rtol=0, atol=1e-15)
+    out, p, fix, bm, xn = o.process(g["x"].astype(np.float64))
+    assert np.max(np.abs(out - g["y"])) < 1e-9 and snr_db(g["y"], out) > 150
+    assert np.array_equal(xn.astype(np.float32), g["x_notched"])
+    assert np.max(np.abs(p - g["p"])) < 1e-6
+    assert np.max(np.abs(fix - g["fix_output"])) < 1e-6 and np.max(np.abs(bm - g["bm_output"])) < 1e-6
+    assert np.allclose(o.aic.W, g["W_aic_last"], rtol=1e-6, atol=1e-9)
+
+
+def test_omlsa_multi_golden():
+    g = golden("omlsa_multi.npz")
+    Y, U = g["Y"].astype(np.float64), g["U"].astype(np.float64)
+    o = O.OmlsaMulti(nfft=512, M=6, cal_weights=True)
+    assert o.estimation(Y[:, 0], U[:, 0, :]) is None                  # first frame returns None (omlsa_multi.py:87-93)
+    for n in range(1, Y.shape[1]):
+        lam = o.estimation(Y[:, n], U[:, n, :])
+        assert np.array_equal(o.G, g["G"][n]) and np.array_equal(o.p, g["p"][n]) and np.array_equal(lam, g["lambda_d"][n])
+
+
+def test_zelinski_golden():
+    g = golden("zelinski.npz")
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=256)
+    pf = O.ZelinskiPostFilter(8, 129, O.noise_msc(geo, 256))
+    for n in range(g["Z"].shape[2]):
+        W = pf.getweights(g["Z"][:, :, n].astype(complex))
+        assert np.allclose(W, g["W"][n], rtol=1e-12, atol=0)
+    assert np.allclose(pf.Pxii, g["Pxii"], rtol=1e-13) and np.allclose(pf.Pxij, g["Pxij"], rtol=1e-13, atol=1e-30)
