@@ -210,12 +210,14 @@ def main():
     from distantspeech_b200.pipelines import MvdrMcsppChain
     _lib.ensure_init()
 
-    S = args.streams_per_gpu
+    from distantspeech_b200.sharding import shard_bounds, gather_validation_streams, max_over_ranks
+    lo, hi = shard_bounds(args.streams_per_gpu * world, rank, world)      # weak scaling: fixed streams per GPU
+    S = hi - lo
     N = int(args.seconds * FS) // HOP * HOP
     mic = MicArray(arrayType="circular", r=0.05, M=M, n_fft=N_FFT)
     chain = MvdrMcsppChain(mic, look_angle=LOOK, n_fft=N_FFT, hop=HOP, full_state=bool(args.full_state),
                            fft_precision=args.fft)
-    x = synth_device(torch, S, mic, N, seed=0x5EED + rank)
+    x = synth_device(torch, S, mic, N, seed=0x5EED + lo)
     y = torch.empty((S, N), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
 
@@ -243,10 +245,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
-    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
+    ms_max = max_over_ranks(ms, device="cuda")
     audio_total = world * S * (N / FS) * args.steps
     value = audio_total / (ms_max / 1e3)
 
@@ -283,13 +282,8 @@ def main():
     n_chk = HOP * 125
     y_first = y[0, :n_chk].clone()
     x_first = x[0, :, :n_chk].clone()
-    if world > 1:
-        ys = [torch.empty_like(y_first) for _ in range(world)] if rank == 0 else None
-        xs = [torch.empty_like(x_first) for _ in range(world)] if rank == 0 else None
-        dist.gather(y_first, ys, dst=0)          # NCCL gather: validation only, outside the timed region
-        dist.gather(x_first, xs, dst=0)
-    else:
-        ys, xs = [y_first], [x_first]
+    ys = gather_validation_streams(y_first, dst=0)     # NCCL gather: validation only, outside the timed region
+    xs = gather_validation_streams(x_first, dst=0)
     if rank == 0:
         from oracle import np_oracle as O       # checker only
         geo = O.MicGeometry("circular", r=0.05, M=M, n_fft=N_FFT)
@@ -319,10 +313,7 @@ def main():
         e1.record()
         barrier()
         ms_e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0)     # device clock
-        tme = torch.tensor([ms_e], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tme, op=dist.ReduceOp.MAX)
-        e2e = {"value": audio_total / (float(tme.item()) / 1e3), "unit": "audio-s/s",
+        e2e = {"value": audio_total / (max_over_ranks(ms_e, device="cuda") / 1e3), "unit": "audio-s/s",
                "h2d_bytes_per_step": int(S * M * N * 4), "d2h_bytes_per_step": int(S * N * 4),
                "api": "MvdrMcsppChain.process_host (pinned host buffers, 128-stream groups, copy/compute overlap)"}
 
