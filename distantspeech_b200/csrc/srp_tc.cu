@@ -1,0 +1,267 @@
+// srp_tc.cu -- SRP-PHAT steered-response contraction on the 5th-generation tensor cores.
+//
+//   P[d, t] = sum_k | sum_m conj(a[d,k,m]) yhat[k,t,m] |          (doa/srp.py:45-51)
+//
+// Per frequency bin the inner sum is a real GEMM with a contraction depth of only 2M:
+//   [Re Z | Im Z] (128 directions x 2*64 frames) = A' (128 x 2M) . B'^T (2M x 128)
+//   A'[d]      = [ cos(w tau_dm) ... | -sin(w tau_dm) ... ]                 (a = cos - j sin)
+//   B'[t]      = [ yr_m ... |  yi_m ... ]   -> Re Z = sum ar yr + ai yi
+//   B'[64 + t] = [ yi_m ... | -yr_m ... ]   -> Im Z = sum ar yi - ai yr
+// so the kernel is bound by what surrounds the MMA: generating the steering tile on
+// chip (it is never stored: D x K x M complex would be 4 GB) and the |.| + sum_k
+// epilogue out of tensor memory.  One CTA = 128 directions x 64 frames, looping over
+// all bins:
+//   warps 0-3   epilogue: tcgen05.ld the 128 x 128 fp32 accumulator, |z|, accumulate over bins
+//   warp  4     one elected thread issues tcgen05.mma (kind::tf32, M128 N128 K8, 2M/8 per bin)
+//   warps 5-12  producers: sincospi steering tile + spectrum tile into shared memory in
+//               the canonical no-swizzle K-major core-matrix layout, 3 stages
+// TMEM: 2 accumulator stages x 128 columns.  Synchronisation: mbarriers
+// (producer -> MMA -> producer, MMA -> epilogue -> MMA) with tcgen05.commit.
+#include "common.cuh"
+
+namespace ds {
+
+namespace tc {
+
+constexpr int TILE_D = 128, TILE_T = 64, UMMA_N = 2 * TILE_T;
+constexpr int STAGES = 3, ACC_STAGES = 2;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int NTHREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// shared-memory matrix descriptor: no swizzle, K-major, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// round-to-nearest conversion to tf32 (the MMA itself truncates the low mantissa bits, which
+// would bias every product low by ~5e-4; rounding first makes the error zero-mean)
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// canonical K-major no-swizzle layout: element (row r, k c) of a tile with ROWS rows, 4-byte elements
+//   16-byte chunk q = c / 4 ; offset = q * (ROWS * 16) + (r / 8) * 128 + (r % 8) * 16 + (c % 4) * 4
+template <int ROWS> __device__ __forceinline__ int tile_off(int r, int c) {
+  return (c >> 2) * (ROWS * 16) + (r >> 3) * 128 + (r & 7) * 16 + (c & 3) * 4;
+}
+
+template <int MM>   // microphones
+__global__ void __launch_bounds__(NTHREADS, 1) srp_tc_kernel(const float *__restrict__ tau, const float2 *__restrict__ Yhat,
+                                                             float *__restrict__ P, int D, int T, int K, float two_f0) {
+  constexpr int KD = 2 * MM;                      // contraction depth (fp32 / tf32 elements)
+  constexpr int A_BYTES = TILE_D * KD * 4, B_BYTES = UMMA_N * KD * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *tiles = smem;                                            // [STAGES][A | B]
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *acc_full = empty_bar + STAGES;
+  uint64_t *acc_empty = acc_full + ACC_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES);
+  float *tau_s = reinterpret_cast<float *>(tmem_slot + 4);                 // [TILE_D][MM]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d0 = blockIdx.x * TILE_D, t0 = blockIdx.y * TILE_T;
+
+  for (int i = threadIdx.x; i < TILE_D * MM; i += NTHREADS) {
+    const int d = d0 + i / MM;
+    tau_s[i] = (d < D) ? tau[(size_t)d * MM + (i % MM)] : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PROD_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS) {      // the MMA warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(ACC_STAGES * UMMA_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < EPI_WARPS) {
+    // ===================== epilogue: |z| and sum over bins ==========================
+    float acc[TILE_T];
+#pragma unroll
+    for (int j = 0; j < TILE_T; ++j) acc[j] = 0.f;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    for (int k = 0; k < K; ++k) {
+      const int as = k % ACC_STAGES;
+      mbar_wait(&acc_full[as], (k / ACC_STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tcol = tmem_base + lane_addr + as * UMMA_N;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t re[32], im[32];
+        tmem_ld32(tcol + h * 32, re);
+        tmem_ld32(tcol + TILE_T + h * 32, im);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float zr = __uint_as_float(re[j]), zi = __uint_as_float(im[j]);
+          acc[h * 32 + j] += sqrtf(fmaf(zr, zr, zi * zi));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&acc_empty[as]);
+    }
+    const int d = d0 + warp * 32 + lane;
+    if (d < D) {
+      float *out = P + (size_t)d * T + t0;
+      const bool vec = (t0 + TILE_T <= T) && ((reinterpret_cast<size_t>(out) & 15) == 0);
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < TILE_T; j += 4) *reinterpret_cast<float4 *>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < TILE_T; ++j)
+          if (t0 + j < T) out[j] = acc[j];
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    // ===================== MMA issuer ==================================================
+    // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UMMA_N >> 3) << 17) | ((uint32_t)(TILE_D >> 4) << 24);
+    for (int k = 0; k < K; ++k) {
+      const int s = k % STAGES, as = k % ACC_STAGES;
+      if (k >= ACC_STAGES) mbar_wait(&acc_empty[as], ((k / ACC_STAGES) - 1) & 1);
+      mbar_wait(&full_bar[s], (k / STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KD / 8; ++kk) {
+          // one K = 8 step = two 16-byte chunks of the canonical layout
+          const uint64_t ad = make_desc(a_addr + kk * 2 * (TILE_D * 16), TILE_D * 16, 128);
+          const uint64_t bd = make_desc(b_addr + kk * 2 * (UMMA_N * 16), UMMA_N * 16, 128);
+          umma_tf32(tmem_base + as * UMMA_N, ad, bd, IDESC, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);     // smem stage may be refilled once these MMAs retire
+        umma_commit(&acc_full[as]);     // accumulator ready for the epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== producers ====================================================
+    const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;     // 0 .. PROD_THREADS-1
+    for (int k = 0; k < K; ++k) {
+      const int s = k % STAGES;
+      if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1);
+      unsigned char *At = tiles + s * STAGE_BYTES;
+      unsigned char *Bt = At + A_BYTES;
+      const float fk2 = two_f0 * (float)k;                 // 2 f_k
+      // steering tile: a = exp(-j 2 pi f tau) -> row [cos | -sin]
+      for (int i = pt; i < TILE_D * MM; i += PROD_THREADS) {
+        const int r = i / MM, m = i % MM;
+        float sn, cs;
+        sincospif(fk2 * tau_s[i], &sn, &cs);
+        *reinterpret_cast<float *>(At + tile_off<TILE_D>(r, m)) = to_tf32(cs);
+        *reinterpret_cast<float *>(At + tile_off<TILE_D>(r, MM + m)) = -to_tf32(sn);
+      }
+      // spectrum tile
+      const float2 *src = Yhat + ((size_t)k * T + t0) * MM;
+      for (int i = pt; i < TILE_T * MM; i += PROD_THREADS) {
+        const int tt = i / MM, m = i % MM;
+        float2 v = (t0 + tt < T) ? src[i] : make_float2(0.f, 0.f);
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y);
+        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(tt, m)) = v.x;
+        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(tt, MM + m)) = v.y;
+        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(TILE_T + tt, m)) = v.y;
+        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(TILE_T + tt, MM + m)) = -v.x;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (tensor core)
+      mbar_arrive(&full_bar[s]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ACC_STAGES * UMMA_N));
+  }
+}
+
+template <int MM> static int launch(const float *tau, const float2 *Yhat, float *P, int D, int T, int K, float two_f0, cudaStream_t st) {
+  constexpr int KD = 2 * MM;
+  const size_t smem = (size_t)STAGES * (TILE_D + UMMA_N) * KD * 4 + (2 * STAGES + 2 * ACC_STAGES) * 8 + 16 + (size_t)TILE_D * MM * 4 + 128;
+  auto kern = srp_tc_kernel<MM>;
+  DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((D + TILE_D - 1) / TILE_D, (T + TILE_T - 1) / TILE_T);
+  kern<<<grid, NTHREADS, smem, st>>>(tau, Yhat, P, D, T, K, two_f0);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
+}  // namespace tc
+
+bool srp_tc_supported(int D, int T, int M, int K) { return (M == 4 || M == 8 || M == 16) && D >= 1 && T >= 1 && K >= 1; }
+
+int srp_tc_launch(const float *tau, const float2 *Yhat, float *P, int D, int T, int M, int K, float two_f0, cudaStream_t st) {
+  switch (M) {
+    case 4: return tc::launch<4>(tau, Yhat, P, D, T, K, two_f0, st);
+    case 8: return tc::launch<8>(tau, Yhat, P, D, T, K, two_f0, st);
+    case 16: return tc::launch<16>(tau, Yhat, P, D, T, K, two_f0, st);
+  }
+  set_error("srp tensor-core path: unsupported microphone count %d", M);
+  return DS_EUNSUPPORTED;
+}
+
+}  // namespace ds

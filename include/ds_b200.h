@@ -329,6 +329,17 @@ int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const dou
 int ds_fir_run(int n_streams, int n_ch, int n_samples, int filter_len, const double *h,
                double *cache, const double *x, double *y, double *scratch, void *stream);
 
+/* ---- SRP-PHAT (doa/srp.py) ------------------------------------------------ */
+/* PHAT normalisation + transpose for the contraction (srp.py:49-50):
+ *   X [T][M][K] c64 (one stream of ds_stft_run)  ->  Yhat [K][T][M] c64 = X / (|X| + 1e-6) (phat=1) or X */
+int ds_phat_run(int n_frames, int n_mics, int n_bins, int phat, const void *X, void *Yhat, void *stream);
+/* replaces the direction x frame loops of srp.compute_angle_spectrum (srp.py:45-51):
+ *   P[d, t] = sum_k | sum_m conj(a[d,k,m]) Yhat[k,t,m] |,  a = exp(-j 2 pi f_k tau[d,m]),  f_k = k fs / n_fft
+ *   tau [D][M] float32 (MicArray.compute_tau per direction), P [D][T] float32
+ *   use_tensor_cores = 1: tcgen05 (tf32) path, n_mics in {4, 8, 16}; 0: CUDA-core path, n_mics <= 16 */
+int ds_srp_run(int n_dirs, int n_frames, int n_mics, int n_bins, double fs, int n_fft, const float *tau,
+               const void *Yhat, float *P, int use_tensor_cores, void *stream);
+
 /* ---- config-4 chain: STFT -> McSppBase -> MVDR -> OMLSA -> ISTFT ------- */
 typedef struct ds_chain_params {
   ds_mcspp_params est; /* n_frames is derived: n_samples / hop                    */

@@ -406,3 +406,52 @@ def test_zelinski_postfilter_golden(cuda):
     assert np.allclose(pf.Pxij, g["Pxij"], rtol=1e-12, atol=1e-30)
     with pytest.raises(AttributeError):
         pf.process(None, None, None)
+
+
+# ---------------------------------------------------------------- a18 (config 5)
+@pytest.mark.parametrize("engine", ["simt", "tensor"])
+def test_srp_angle_spectrum_vs_oracle(cuda, engine):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.doa.srp import srp
+    geo = O.MicGeometry("circular", r=0.032, M=4, n_fft=512)
+    x = np.ascontiguousarray(O.synth_streams(1, geo, 256 * 40, look_deg=(75.0, 0.0), interf_deg=(250.0, 0.0), seed0=9)[0].T)
+    mic = MicArray(arrayType="circular", r=0.032, M=4, n_fft=512)
+    P, p = srp(mic, engine=engine).compute_angle_spectrum(x)
+    Pref, pref = O.srp_angle_spectrum(x.astype(np.float64), geo)
+    assert P.shape == (360, 40) and p.shape == (257, 40)
+    rel = np.max(np.abs(P - Pref) / np.abs(Pref))
+    print("SRP %s: max rel err %.2e" % (engine, rel))
+    assert rel <= 1e-3                                                       # SURVEY 8d tolerance for the map
+    assert np.array_equal(np.argmax(P[:, 5:].sum(axis=1)), np.argmax(Pref[:, 5:].sum(axis=1)))
+    assert np.mean(np.abs(p - pref) > 1e-9) < 0.01
+
+
+def test_srp_grid_16mic_48k_tensor_vs_simt_vs_oracle(cuda):
+    # config-5 shape at reduced grid: 16 mics, 48 kHz, n_fft 1024, az x el grid through compute_tau([az, el])
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.doa.srp import srp
+    mic = MicArray(arrayType="circular", r=0.05, M=16, n_fft=1024)
+    mic.fs = 48000                                                           # the reference hard-wires 16 kHz (MicArray.py:27)
+    mic.omega = 2 * np.pi * mic.freq_bin * mic.fs / mic.n_fft
+    geo = O.MicGeometry("circular", r=0.05, M=16, n_fft=1024, fs=48000)
+    assert np.allclose(geo.mic_loc, mic.mic_loc)
+    x = np.ascontiguousarray(O.synth_streams(1, geo, 512 * 70, look_deg=(100.0, 20.0), interf_deg=(300.0, 5.0), seed0=12, fs=48000)[0].T)
+    az, el = np.arange(0, 360, 3), np.arange(0, 90, 10)
+    Pt = srp(mic, engine="tensor").compute_grid_spectrum(x, az, el)
+    Ps = srp(mic, engine="simt").compute_grid_spectrum(x, az, el)
+    assert Pt.shape == (120, 9, 70)
+    assert np.max(np.abs(Pt - Ps) / np.abs(Ps)) <= 1e-3
+    # oracle on 12 random frames x 40 random directions
+    rng = np.random.default_rng(0)
+    Y = O.Transform(channel=16, n_fft=1024, hop_length=512).stft(x.astype(np.float64))
+    di = rng.choice(120 * 9, 40, replace=False)
+    ti = rng.choice(70, 12, replace=False)
+    tau = np.stack([O.method_tau(geo, np.array([az[i // 9], el[i % 9]]) * np.pi / 180)[:, 0] for i in di])
+    Pref = O.srp_map(Y[:, ti, :], geo.omega, tau)
+    got = Pt.reshape(-1, 70)[di][:, ti]
+    rel = np.max(np.abs(got - Pref) / np.abs(Pref))
+    print("SRP 16-mic grid: max rel err vs oracle %.2e" % rel)
+    assert rel <= 1e-3
+    flat = Pt.sum(axis=2)
+    ia, ie = np.unravel_index(np.argmax(flat), flat.shape)
+    assert abs(az[ia] - 100) <= 6                                            # finds the source azimuth
