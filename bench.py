@@ -315,7 +315,21 @@ def main():
         ms_e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0)     # device clock
         e2e = {"value": audio_total / (max_over_ranks(ms_e, device="cuda") / 1e3), "unit": "audio-s/s",
                "h2d_bytes_per_step": int(S * M * N * 4), "d2h_bytes_per_step": int(S * N * 4),
-               "api": "MvdrMcsppChain.process_host (pinned host buffers, 128-stream groups, copy/compute overlap)"}
+               "api": "MvdrMcsppChain.process_host (pinned float32 host buffers, 128-stream groups, copy/compute overlap)"}
+        # same call with int16 PCM host buffers (the reference's on-disk format; load_audio's /32767 runs on the device)
+        x_pcm = torch.empty((S, M, N), dtype=torch.int16, pin_memory=True)
+        x_pcm.copy_((x_host * 32767.0).round_().clamp_(-32768, 32767))
+        del x_host
+        chain.process_host(x_pcm, y_host, chunk_streams=128)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            chain.process_host(x_pcm, y_host, chunk_streams=128)
+        e1.record()
+        barrier()
+        e2e["pcm16"] = {"value": audio_total / (max_over_ranks(e0.elapsed_time(e1), device="cuda") / 1e3), "unit": "audio-s/s",
+                        "h2d_bytes_per_step": int(S * M * N * 2), "d2h_bytes_per_step": int(S * N * 4),
+                        "api": "MvdrMcsppChain.process_host with int16 PCM host buffers"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -145,6 +145,8 @@ def _declare(lib):
     lib.ds_zelinski_state_bytes.argtypes = [i32, i32, i32]
     lib.ds_zelinski_state_bytes.restype = C.c_size_t
     lib.ds_zelinski_run.argtypes = [i32, i32, i32, i32, dbl, dbl, vp, vp, vp, vp, vp]
+    lib.ds_pcm16_to_float_run.argtypes = [C.c_size_t, vp, vp, vp]
+    lib.ds_float_to_pcm16_run.argtypes = [C.c_size_t, vp, vp, vp]
     lib.ds_phat_run.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     lib.ds_srp_run.argtypes = [i32, i32, i32, i32, dbl, i32, vp, vp, vp, i32, vp]
     lib.ds_chain_state_bytes.argtypes = [C.POINTER(ChainParams)]

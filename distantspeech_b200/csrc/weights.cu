@@ -139,3 +139,45 @@ extern "C" int ds_omlsa_gain_run(int n_rows, int n_bins, const double *xi, const
   DS_LAUNCH_CHECK();
   return DS_OK;
 }
+
+// ---- PCM ingest / egress (beamformer/utils.py:182-196) --------------------------------
+namespace ds {
+// load_audio: int16 -> float32 / float(iinfo(int16).max)   (:184-185, note 32767 not 32768)
+__global__ void pcm16_to_float_kernel(const short *__restrict__ in, float *__restrict__ out, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n && ((reinterpret_cast<size_t>(in + i) & 15) == 0) && ((reinterpret_cast<size_t>(out + i) & 15) == 0)) {
+    const int4 v = *reinterpret_cast<const int4 *>(in + i);
+    const short *s = reinterpret_cast<const short *>(&v);
+    float4 a, b;
+    a.x = __fdiv_rn((float)s[0], 32767.0f); a.y = __fdiv_rn((float)s[1], 32767.0f);
+    a.z = __fdiv_rn((float)s[2], 32767.0f); a.w = __fdiv_rn((float)s[3], 32767.0f);
+    b.x = __fdiv_rn((float)s[4], 32767.0f); b.y = __fdiv_rn((float)s[5], 32767.0f);
+    b.z = __fdiv_rn((float)s[6], 32767.0f); b.w = __fdiv_rn((float)s[7], 32767.0f);
+    *reinterpret_cast<float4 *>(out + i) = a;
+    *reinterpret_cast<float4 *>(out + i + 4) = b;
+  } else {
+    for (size_t j = i; j < n && j < i + 8; ++j) out[j] = __fdiv_rn((float)in[j], 32767.0f);
+  }
+}
+// save_audio: (audio * 32767).astype(int16)   (:193) -- C cast truncates toward zero like numpy
+__global__ void float_to_pcm16_kernel(const float *__restrict__ in, short *__restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (short)(int)(in[i] * 32767.0f);
+}
+}  // namespace ds
+
+extern "C" int ds_pcm16_to_float_run(size_t n, const void *pcm, float *out, void *stream) {
+  DS_CHECK_ARG(pcm && out, "ds_pcm16_to_float_run: null argument");
+  if (n == 0) return DS_OK;
+  const size_t threads = (n + 7) / 8;
+  ds::pcm16_to_float_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const short *)pcm, out, n);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+extern "C" int ds_float_to_pcm16_run(size_t n, const float *in, void *pcm, void *stream) {
+  DS_CHECK_ARG(pcm && in, "ds_float_to_pcm16_run: null argument");
+  if (n == 0) return DS_OK;
+  ds::float_to_pcm16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (short *)pcm, n);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}

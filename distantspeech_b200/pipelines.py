@@ -121,7 +121,8 @@ class MvdrMcsppChain(object):
         return y if as_torch else y.double().cpu().numpy()
 
     def process_host(self, x_host, y_host=None, chunk_streams=128):
-        """End-to-end call with HOST buffers: x_host [S, M, N] float32 (pinned for speed) ->
+        """End-to-end call with HOST buffers: x_host [S, M, N] float32 -- or int16 PCM, converted on the
+        device exactly like load_audio (float32(pcm) / 32767, utils.py:184-185) -- (pinned for speed) ->
         y_host [S, N] float32.  Streams are independent, so the batch is cut into groups of
         ``chunk_streams`` and H2D copy / kernels / D2H copy of consecutive groups overlap on
         three CUDA streams.  Each group is a fresh utterance (state reset)."""
@@ -133,7 +134,9 @@ class MvdrMcsppChain(object):
         n_chunks = (S + cs - 1) // cs
         cur = t.cuda.current_stream()
         s_in, s_out = t.cuda.Stream(), t.cuda.Stream()
+        pcm = x_host.dtype == t.int16
         xbuf = [t.empty((cs, M, N), dtype=t.float32, device="cuda") for _ in range(2)]
+        pbuf = [t.empty((cs, M, N), dtype=t.int16, device="cuda") for _ in range(2)] if pcm else None
         ybuf = [t.empty((cs, N), dtype=t.float32, device="cuda") for _ in range(2)]
         ev_in = [t.cuda.Event() for _ in range(2)]
         ev_done = [t.cuda.Event() for _ in range(2)]
@@ -150,9 +153,12 @@ class MvdrMcsppChain(object):
             with t.cuda.stream(s_in):
                 if c >= 2:
                     s_in.wait_event(ev_done[b])          # kernels of chunk c-2 finished reading xbuf[b]
-                xbuf[b][:n].copy_(x_host[lo:hi], non_blocking=True)
+                (pbuf if pcm else xbuf)[b][:n].copy_(x_host[lo:hi], non_blocking=True)
                 ev_in[b].record(s_in)
             cur.wait_event(ev_in[b])
+            if pcm:
+                L.check(L.lib().ds_pcm16_to_float_run(n * M * N, L.ptr(pbuf[b]), L.ptr(xbuf[b]), L.stream_ptr()),
+                        "ds_pcm16_to_float_run")
             if c >= 2:
                 cur.wait_event(ev_out[b])                # D2H of chunk c-2 finished reading ybuf[b]
             if n != cs:

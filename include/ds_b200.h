@@ -329,6 +329,12 @@ int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const dou
 int ds_fir_run(int n_streams, int n_ch, int n_samples, int filter_len, const double *h,
                double *cache, const double *x, double *y, double *scratch, void *stream);
 
+/* ---- PCM ingest / egress (beamformer/utils.py) ------------------------------ */
+/* replaces the arithmetic of load_audio (utils.py:182-187): out = float32(pcm) / 32767.0f       */
+int ds_pcm16_to_float_run(size_t n, const void *pcm_int16, float *out, void *stream);
+/* replaces the arithmetic of save_audio (utils.py:190-196): pcm = int16(audio * 32767)          */
+int ds_float_to_pcm16_run(size_t n, const float *in, void *pcm_int16, void *stream);
+
 /* ---- SRP-PHAT (doa/srp.py) ------------------------------------------------ */
 /* PHAT normalisation + transpose for the contraction (srp.py:49-50):
  *   X [T][M][K] c64 (one stream of ds_stft_run)  ->  Yhat [K][T][M] c64 = X / (|X| + 1e-6) (phat=1) or X */

@@ -455,3 +455,32 @@ def test_srp_grid_16mic_48k_tensor_vs_simt_vs_oracle(cuda):
     flat = Pt.sum(axis=2)
     ia, ie = np.unravel_index(np.argmax(flat), flat.shape)
     assert abs(az[ia] - 100) <= 6                                            # finds the source azimuth
+
+
+# ---------------------------------------------------------------- f2: PCM ingest / egress
+def test_pcm16_ingest_matches_load_audio(cuda):
+    import ctypes as C
+    import torch
+    from distantspeech_b200 import _lib as L
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.pipelines import MvdrMcsppChain
+    rng = np.random.default_rng(1)
+    pcm = rng.integers(-32768, 32768, size=100003, dtype=np.int16)
+    d = torch.from_numpy(pcm).cuda()
+    out = torch.empty(pcm.shape[0], dtype=torch.float32, device="cuda")
+    L.check(L.lib().ds_pcm16_to_float_run(pcm.shape[0], L.ptr(d), L.ptr(out), L.stream_ptr()))
+    ref = pcm.astype(np.float32) / float(np.iinfo(np.int16).max)              # utils.py:184-185
+    assert np.array_equal(out.cpu().numpy(), ref)
+    back = torch.empty(pcm.shape[0], dtype=torch.int16, device="cuda")
+    L.check(L.lib().ds_float_to_pcm16_run(pcm.shape[0], L.ptr(out), L.ptr(back), L.stream_ptr()))
+    assert np.array_equal(back.cpu().numpy(), (ref * np.iinfo(np.int16).max).astype(np.int16))   # :193
+    # int16 host buffers through the chain == float path on the dequantised signal
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    xs = O.synth_streams(3, geo, 256 * 40, seed0=77)
+    xi = np.round(xs * 32767).astype(np.int16)
+    mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=512)
+    ch = MvdrMcsppChain(mic, look_angle=(30, 0))
+    y_pcm = ch.process_host(torch.from_numpy(xi).pin_memory(), chunk_streams=2).numpy().copy()
+    xf = xi.astype(np.float32) / 32767.0
+    ref0 = O.mvdr_mcspp_chain(xf[0].T.astype(np.float64), geo, (30, 0), 512, 256)
+    assert_wave_parity(ref0, y_pcm[0], "pcm16 chain")
