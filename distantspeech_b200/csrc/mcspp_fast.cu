@@ -93,15 +93,31 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
 
 #pragma unroll 1
   for (int t = 0; t < a.T; ++t) {
-    // ---- P0: spectrum of this frame, prior from MCRA on channel 0          mcspp_base.py:98-122
+    // ---- P0: issue the loads of this frame's spectrum (kept as float until the inverse is done,
+    //          so the HBM latency hides behind the Gauss-Jordan sweeps instead of stalling the warp)
+    float2 yf[M], ynb[2];
+#pragma unroll
+    for (int m = 0; m < M; ++m) yf[m] = ld_f2_once(Xp + m * K);
+    ynb[0] = (k > 0) ? ld_f2_once(Xp - 1) : make_float2(0.f, 0.f);
+    ynb[1] = (k < K - 1) ? ld_f2_once(Xp + 1) : make_float2(0.f, 0.f);
+    Xp += M * K;
+
+    // ---- P1: A = inv(Re Phi_vv + eps I)                                     mcspp_base.py:278
+    double A[NP];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = i; j < M; ++j) A[pidx<M>(i, j)] = smv[pidx<M>(i, j) * NT] + ((i == j) ? a.eps : 0.0);
+    spd_inverse_packed<M>(A);
+
+    // ---- prior from MCRA on channel 0                                       :98-122
     double yr[M], yi[M];
 #pragma unroll
-    for (int m = 0; m < M; ++m) { const float2 v = ld_f2_once(Xp + m * K); yr[m] = (double)v.x; yi[m] = (double)v.y; }
+    for (int m = 0; m < M; ++m) { yr[m] = (double)yf[m].x; yi[m] = (double)yf[m].y; }
     double q;
     {
-      double Ym1 = 0.0, Yp1 = 0.0;
-      if (k > 0) { const float2 v = ld_f2_once(Xp - 1); Ym1 = power_c((double)v.x, (double)v.y); }
-      if (k < K - 1) { const float2 v = ld_f2_once(Xp + 1); Yp1 = power_c((double)v.x, (double)v.y); }
+      const double Ym1 = (k > 0) ? power_c((double)ynb[0].x, (double)ynb[0].y) : 0.0;
+      const double Yp1 = (k < K - 1) ? power_c((double)ynb[1].x, (double)ynb[1].y) : 0.0;
       const double Y0 = power_c(yr[0], yi[0]);
       const bool reset = (frm > 0) && (ell % a.mc.L == 0);
       mcra_step(mS, mSmin, mStmp, mp, mlam, Ym1, Y0, Yp1, k, K, frm, reset, a.mc);
@@ -109,15 +125,6 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
       ++ell; ++frm;
       q = fmin(fmax(sqrt_pos(1.0 - mp), a.q_min), a.q_max);
     }
-    Xp += M * K;
-
-    // ---- P1: A = inv(Re Phi_vv + eps I)                                     :278
-    double A[NP];
-#pragma unroll
-    for (int i = 0; i < M; ++i)
-#pragma unroll
-      for (int j = i; j < M; ++j) A[pidx<M>(i, j)] = smv[pidx<M>(i, j) * NT] + ((i == j) ? a.eps : 0.0);
-    spd_inverse_packed<M>(A);
 #define AS(i, j) (((i) <= (j)) ? A[pidx<M>(i, j)] : A[pidx<M>(j, i)])
 
     // ---- P2/P3: MVDR numerator b = A a and denominator a^H b, applied on the fly:
@@ -228,7 +235,9 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
     // ---- OMLSA gain and output  Y = (w^H y) G,  w = A a / den                :140-155
     double scale = rcp_pos(den);
     if (a.apply_gain) {
-      double G = exp(p * log(xi * rxi1) + (1.0 - p) * a.logGmin);
+      // the gain only scales the output (no feedback into the recursions): fp32 exp/log are enough
+      const float pf = (float)p;
+      double G = (double)expf(pf * logf((float)(xi * rxi1)) + (1.0f - pf) * (float)a.logGmin);
       G = fmax(fmin(G, 1.0), a.Gmin);
       if (k < 2) G = 0.0;
       scale *= G;

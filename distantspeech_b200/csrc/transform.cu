@@ -294,15 +294,15 @@ struct FixedBfArgs {
   double scale;
 };
 
-constexpr int FBF_WARPS = 8;
+constexpr int FBF_WARPS = 9;     // 8 analysis warps + 1 synthesis warp
 
 __host__ __device__ inline size_t fbf_half_bytes(int S, int M, int B, int ov) {
   return ((size_t)S * M * ov + (size_t)S * B * ov) * sizeof(float);
 }
 
 template <int N>
-__global__ void __launch_bounds__(FBF_WARPS * 32) fixedbf_kernel(FixedBfArgs a, const float2 *__restrict__ tw_h,
-                                                                const float2 *__restrict__ tw_n) {
+__global__ void __launch_bounds__(FBF_WARPS * 32, 3) fixedbf_kernel(FixedBfArgs a, const float2 *__restrict__ tw_h_g,
+                                                                const float2 *__restrict__ tw_n_g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int H = N / 2, K = H + 1;
   constexpr int BE = fft_buf_elems(N);
@@ -314,6 +314,10 @@ __global__ void __launch_bounds__(FBF_WARPS * 32) fixedbf_kernel(FixedBfArgs a, 
   float2 *beambuf = micbuf + (size_t)a.M * BE;                     // [B][BE]
   float *ola = reinterpret_cast<float *>(beambuf + (size_t)a.B * BE);   // [B][N] ring accumulator
   float *win = ola + (size_t)a.B * N;                              // [N]
+  float2 *tw_h = reinterpret_cast<float2 *>(win + N);             // [H]   twiddles staged once per CTA
+  float2 *tw_n = tw_h + H;                                         // [H/2 + 1]
+  for (int i = tid; i < H; i += blockDim.x) tw_h[i] = tw_h_g[i];
+  for (int i = tid; i <= H / 2; i += blockDim.x) tw_n[i] = tw_n_g[i];
   for (int n = tid; n < N; n += blockDim.x) win[n] = (float)a.window[n];
   for (int i = tid; i < a.B * N; i += blockDim.x) ola[i] = 0.0f;
 
@@ -332,65 +336,88 @@ __global__ void __launch_bounds__(FBF_WARPS * 32) fixedbf_kernel(FixedBfArgs a, 
   // frames before t0 that still overlap the segment's first output block are
   // recomputed (halo) so that each segment is self-contained.
   const int th0 = max(0, t0 - (R - 1));
-  for (int t = th0; t < t1; ++t) {
-    // ---- analysis: one warp per mic ------------------------------------
-    for (int m = warp; m < a.M; m += FBF_WARPS) {
-      const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
-      const float *hs = hist_in + ((long long)s * a.M + m) * ov;
-      float2 *buf = micbuf + (size_t)m * BE;
-      float *fb = reinterpret_cast<float *>(buf);
-      for (int n = lane; n < N; n += 32) {
-        int g = t * a.hop + n - ov;
-        float v = (g < 0) ? hs[ov + g] : xs[g];
-        fb[2 * FPAD<float>(n >> 1) + (n & 1)] = v * win[n];
-      }
-      __syncwarp();
-      warp_rfft<N, float>(buf, tw_h, tw_n, lane);
-    }
-    __syncthreads();
-    // ---- weights: Y_b[k] = sum_m conj(W[b,k,m]) X_m[k] --------------------
-    for (int i = tid; i < a.B * K; i += blockDim.x) {
-      const int b = i / K, k = i - b * K;
-      const float2 *w = a.W + ((size_t)b * K + k) * a.M;
-      float yr = 0.f, yi = 0.f;
-      for (int m = 0; m < a.M; ++m) {
-        float2 xv = micbuf[(size_t)m * BE + FPAD<float>(k)];
-        float2 wv = __ldg(w + m);
-        yr += wv.x * xv.x + wv.y * xv.y;
-        yi += wv.x * xv.y - wv.y * xv.x;
-      }
-      beambuf[(size_t)b * BE + FPAD<float>(k)] = make_float2(yr, yi);
-    }
-    __syncthreads();
-    // ---- synthesis + overlap-add: one warp per beam -------------------------
-    for (int b = warp; b < a.B; b += FBF_WARPS) {
-      float2 *buf = beambuf + (size_t)b * BE;
-      warp_irfft_unscaled<N, float>(buf, tw_h, tw_n, lane);
-      const float *fb = reinterpret_cast<const float *>(buf);
-      float *acc = ola + (size_t)b * N;
-      // ring: sample g lives at acc[g % N]
-      for (int n = lane; n < N; n += 32) {
-        float v = fb[2 * FPAD<float>(n >> 1) + (n & 1)] * inv_n * win[n];
-        int pos = (t * a.hop + n) & (N - 1);
-        acc[pos] = acc[pos] + v;
-      }
-      __syncwarp();
-      // samples [t*hop, (t+1)*hop) are complete now
-      if (t >= t0) {
-        float *ys = a.y + ((long long)s * a.B + b) * a.Ns;
-        const float *tl = tail_in + ((long long)s * a.B + b) * ov;
-        for (int j = lane; j < a.hop; j += 32) {
-          int g = t * a.hop + j;
-          int pos = g & (N - 1);
-          float v = acc[pos];
-          if (g < ov) v = v + tl[g];
-          ys[g] = (float)((double)v * a.scale);
-          acc[pos] = 0.0f;
+  // Software pipeline over frames: in iteration t the analysis warps (0 .. FBF_WARPS-2) transform
+  // frame t while the synthesis warp (FBF_WARPS-1) inverse-transforms and overlap-adds frame t-1;
+  // the weight apply of frame t follows.  Two block barriers per frame, no idle phase.
+  constexpr int AW = FBF_WARPS - 1;
+  for (int t = th0; t <= t1; ++t) {
+    if (warp < AW) {
+      if (t < t1) {
+        for (int m = warp; m < a.M; m += AW) {
+          const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
+          float2 *buf = micbuf + (size_t)m * BE;
+          const int g0 = t * a.hop - ov;
+          if (g0 >= 0 && ((reinterpret_cast<size_t>(xs + g0) & 15) == 0)) {
+            const float4 *src = reinterpret_cast<const float4 *>(xs + g0);
+            float4 v[N / 128];
+#pragma unroll
+            for (int i = 0; i < N / 128; ++i) v[i] = __ldg(src + lane + 32 * i);
+#pragma unroll
+            for (int i = 0; i < N / 128; ++i) {
+              const int q = lane + 32 * i;
+              const float4 w = *reinterpret_cast<const float4 *>(win + 4 * q);
+              buf[FPAD<float>(2 * q)] = make_float2(v[i].x * w.x, v[i].y * w.y);
+              buf[FPAD<float>(2 * q + 1)] = make_float2(v[i].z * w.z, v[i].w * w.w);
+            }
+          } else {
+            const float *hs = hist_in + ((long long)s * a.M + m) * ov;
+            float *fb = reinterpret_cast<float *>(buf);
+            for (int n = lane; n < N; n += 32) {
+              const int g = g0 + n;
+              const float v = (g < 0) ? hs[ov + g] : xs[g];
+              fb[2 * FPAD<float>(n >> 1) + (n & 1)] = v * win[n];
+            }
+          }
+          __syncwarp();
+          warp_rfft<N, float>(buf, tw_h, tw_n, lane);
         }
-      } else {
-        for (int j = lane; j < a.hop; j += 32) acc[(t * a.hop + j) & (N - 1)] = 0.0f;
       }
-      __syncwarp();
+    } else if (t > th0) {
+      // ---- synthesis + overlap-add of frame tp = t-1 ----------------------------------
+      const int tp = t - 1;
+      for (int b = 0; b < a.B; ++b) {
+        float2 *buf = beambuf + (size_t)b * BE;
+        warp_irfft_unscaled<N, float>(buf, tw_h, tw_n, lane);
+        const float *fb = reinterpret_cast<const float *>(buf);
+        float *acc = ola + (size_t)b * N;
+        for (int n = lane; n < N; n += 32) {               // ring: sample g lives at acc[g % N]
+          const float v = fb[2 * FPAD<float>(n >> 1) + (n & 1)] * inv_n * win[n];
+          const int pos = (tp * a.hop + n) & (N - 1);
+          acc[pos] = acc[pos] + v;
+        }
+        __syncwarp();
+        if (tp >= t0) {                                    // samples [tp*hop, (tp+1)*hop) are complete now
+          float *ys = a.y + ((long long)s * a.B + b) * a.Ns;
+          const float *tl = tail_in + ((long long)s * a.B + b) * ov;
+          for (int j = lane; j < a.hop; j += 32) {
+            const int g = tp * a.hop + j;
+            const int pos = g & (N - 1);
+            float v = acc[pos];
+            if (g < ov) v = v + tl[g];
+            ys[g] = (float)((double)v * a.scale);
+            acc[pos] = 0.0f;
+          }
+        } else {
+          for (int j = lane; j < a.hop; j += 32) acc[(tp * a.hop + j) & (N - 1)] = 0.0f;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- weights: Y_b[k] = sum_m conj(W[b,k,m]) X_m[k] --------------------------------
+    if (t < t1) {
+      for (int i = tid; i < a.B * K; i += blockDim.x) {
+        const int b = i / K, k = i - b * K;
+        const float2 *w = a.W + ((size_t)b * K + k) * a.M;
+        float yr = 0.f, yi = 0.f;
+        for (int m = 0; m < a.M; ++m) {
+          const float2 xv = micbuf[(size_t)m * BE + FPAD<float>(k)];
+          const float2 wv = __ldg(w + m);
+          yr += wv.x * xv.x + wv.y * xv.y;
+          yi += wv.x * xv.y - wv.y * xv.x;
+        }
+        beambuf[(size_t)b * BE + FPAD<float>(k)] = make_float2(yr, yi);
+      }
     }
     __syncthreads();
   }
@@ -422,7 +449,8 @@ template <int N>
 static int launch_fixedbf(const FixedBfArgs &a0, const TwiddleSet &tw, cudaStream_t st) {
   FixedBfArgs a = a0;
   constexpr int BE = fft_buf_elems(N);
-  const size_t smem = ((size_t)a.M + a.B) * BE * sizeof(float2) + (size_t)a.B * N * sizeof(float) + (size_t)N * sizeof(float);
+  const size_t smem = ((size_t)a.M + a.B) * BE * sizeof(float2) + (size_t)a.B * N * sizeof(float) + (size_t)N * sizeof(float) +
+                      (size_t)(N / 2 + N / 4 + 2) * sizeof(float2);
   if (smem > 227 * 1024) { set_error("fixedbf: M=%d B=%d n_fft=%d does not fit shared memory", a.M, a.B, N); return DS_EUNSUPPORTED; }
   auto kern = fixedbf_kernel<N>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
