@@ -25,7 +25,8 @@ namespace tc {
 
 constexpr int TILE_D = 128, TILE_T = 64, UMMA_N = 2 * TILE_T;
 constexpr int STAGES = 3, ACC_STAGES = 2;
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
+constexpr int RESYNC = 32;            // bins between exact re-evaluations of the steering phasors
 constexpr int NTHREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 
@@ -86,6 +87,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 // round-to-nearest conversion to tf32 (the MMA itself truncates the low mantissa bits, which
 // would bias every product low by ~5e-4; rounding first makes the error zero-mean)
 __device__ __forceinline__ float to_tf32(float x) {
@@ -101,7 +111,7 @@ template <int ROWS> __device__ __forceinline__ int tile_off(int r, int c) {
 }
 
 template <int MM>   // microphones
-__global__ void __launch_bounds__(NTHREADS, 1) srp_tc_kernel(const float *__restrict__ tau, const float2 *__restrict__ Yhat,
+__global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__restrict__ tau, const float2 *__restrict__ Yhat,
                                                              float *__restrict__ P, int D, int T, int K, float two_f0) {
   constexpr int KD = 2 * MM;                      // contraction depth (fp32 / tf32 elements)
   constexpr int A_BYTES = TILE_D * KD * 4, B_BYTES = UMMA_N * KD * 4;
@@ -148,15 +158,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) srp_tc_kernel(const float *__rest
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tcol = tmem_base + lane_addr + as * UMMA_N;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t re[32], im[32];
-        tmem_ld32(tcol + h * 32, re);
-        tmem_ld32(tcol + TILE_T + h * 32, im);
+      for (int h = 0; h < 4; ++h) {
+        uint32_t re[16], im[16];
+        tmem_ld16(tcol + h * 16, re);
+        tmem_ld16(tcol + TILE_T + h * 16, im);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float zr = __uint_as_float(re[j]), zi = __uint_as_float(im[j]);
-          acc[h * 32 + j] += sqrtf(fmaf(zr, zr, zi * zi));
+          const float zz = fmaf(zr, zr, zi * zi);
+          acc[h * 16 + j] = fmaf(zz, rsqrtf(fmaxf(zz, 1e-30f)), acc[h * 16 + j]);     // |z| = zz * rsqrt(zz)
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -201,34 +212,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) srp_tc_kernel(const float *__rest
     }
   } else {
     // ===================== producers ====================================================
-    const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;     // 0 .. PROD_THREADS-1
+    // Thread pt owns steering row pt (one direction, all MM mics): its phasors advance from bin to
+    // bin by one complex rotation exp(-j 2 pi df tau) and are re-evaluated exactly every RESYNC bins.
+    // Threads 0..63 also write the "real" spectrum rows [yr | yi] of frame pt, threads 64..127 the
+    // "imaginary" rows [yi | -yr] of frame pt-64.  All shared-memory traffic is 16-byte vectors.
+    const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;     // 0 .. 127
+    float cs[MM], sn[MM], rc[MM], rs[MM];
+#pragma unroll
+    for (int m = 0; m < MM; ++m) sincospif(two_f0 * tau_s[pt * MM + m], &rs[m], &rc[m]);   // rotation per bin
+    const int a_row = (pt >> 3) * 128 + (pt & 7) * 16;
+    const int tt = pt & (TILE_T - 1);
+    const bool im_row = pt >= TILE_T;
+    const int b_row = ((pt >> 3) * 128) + (pt & 7) * 16;   // row pt of the B tile (rows 64.. are the imaginary rows)
+    const bool t_ok = (t0 + tt) < T;
     for (int k = 0; k < K; ++k) {
       const int s = k % STAGES;
+      if ((k % RESYNC) == 0) {
+        const float fk2 = two_f0 * (float)k;
+#pragma unroll
+        for (int m = 0; m < MM; ++m) sincospif(fk2 * tau_s[pt * MM + m], &sn[m], &cs[m]);
+      }
+      // spectrum row of this frame (global loads issued before the wait)
+      float4 yv[MM / 2];
+      const float4 *src = reinterpret_cast<const float4 *>(Yhat + ((size_t)k * T + t0 + tt) * MM);
+#pragma unroll
+      for (int i = 0; i < MM / 2; ++i) yv[i] = t_ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1);
       unsigned char *At = tiles + s * STAGE_BYTES;
       unsigned char *Bt = At + A_BYTES;
-      const float fk2 = two_f0 * (float)k;                 // 2 f_k
-      // steering tile: a = exp(-j 2 pi f tau) -> row [cos | -sin]
-      for (int i = pt; i < TILE_D * MM; i += PROD_THREADS) {
-        const int r = i / MM, m = i % MM;
-        float sn, cs;
-        sincospif(fk2 * tau_s[i], &sn, &cs);
-        *reinterpret_cast<float *>(At + tile_off<TILE_D>(r, m)) = to_tf32(cs);
-        *reinterpret_cast<float *>(At + tile_off<TILE_D>(r, MM + m)) = -to_tf32(sn);
+      // steering row: [cos_0 .. cos_{M-1} | -sin_0 .. -sin_{M-1}]   (a = cos - j sin)
+#pragma unroll
+      for (int q = 0; q < MM / 4; ++q) {
+        *reinterpret_cast<float4 *>(At + q * (TILE_D * 16) + a_row) =
+            make_float4(to_tf32(cs[4 * q]), to_tf32(cs[4 * q + 1]), to_tf32(cs[4 * q + 2]), to_tf32(cs[4 * q + 3]));
+        *reinterpret_cast<float4 *>(At + (MM / 4 + q) * (TILE_D * 16) + a_row) =
+            make_float4(-to_tf32(sn[4 * q]), -to_tf32(sn[4 * q + 1]), -to_tf32(sn[4 * q + 2]), -to_tf32(sn[4 * q + 3]));
       }
-      // spectrum tile
-      const float2 *src = Yhat + ((size_t)k * T + t0) * MM;
-      for (int i = pt; i < TILE_T * MM; i += PROD_THREADS) {
-        const int tt = i / MM, m = i % MM;
-        float2 v = (t0 + tt < T) ? src[i] : make_float2(0.f, 0.f);
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y);
-        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(tt, m)) = v.x;
-        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(tt, MM + m)) = v.y;
-        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(TILE_T + tt, m)) = v.y;
-        *reinterpret_cast<float *>(Bt + tile_off<UMMA_N>(TILE_T + tt, MM + m)) = -v.x;
+      // spectrum row: yv[i] = (re_{2i}, im_{2i}, re_{2i+1}, im_{2i+1})
+#pragma unroll
+      for (int q = 0; q < MM / 4; ++q) {
+        const float4 u = yv[2 * q], v = yv[2 * q + 1];
+        const float4 re4 = make_float4(to_tf32(u.x), to_tf32(u.z), to_tf32(v.x), to_tf32(v.z));
+        const float4 im4 = make_float4(to_tf32(u.y), to_tf32(u.w), to_tf32(v.y), to_tf32(v.w));
+        if (!im_row) {
+          *reinterpret_cast<float4 *>(Bt + q * (UMMA_N * 16) + b_row) = re4;
+          *reinterpret_cast<float4 *>(Bt + (MM / 4 + q) * (UMMA_N * 16) + b_row) = im4;
+        } else {
+          *reinterpret_cast<float4 *>(Bt + q * (UMMA_N * 16) + b_row) = im4;
+          *reinterpret_cast<float4 *>(Bt + (MM / 4 + q) * (UMMA_N * 16) + b_row) = make_float4(-re4.x, -re4.y, -re4.z, -re4.w);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (tensor core)
       mbar_arrive(&full_bar[s]);
+      // advance the phasors to the next bin
+#pragma unroll
+      for (int m = 0; m < MM; ++m) {
+        const float c = cs[m], sv = sn[m];
+        cs[m] = fmaf(c, rc[m], -sv * rs[m]);
+        sn[m] = fmaf(sv, rc[m], c * rs[m]);
+      }
     }
   }
 
