@@ -115,7 +115,7 @@ template <typename T> struct FdSmem {
                + (size_t)M * FD_L                           // bm_prev
                + (size_t)M * (FD_L / 2)                     // dl_al
                + 5 * FD_L;                                  // fbf, fbf_prev, fbf_d, dl_fbf, x0_prev
-    size_t d = (size_t)6 * FD_K + 64;                       // mcra (5K) + P0 (K) + reduction scratch (doubles)
+    size_t d = (size_t)FD_K + 64;                           // P0 (K) + reduction scratch (doubles); MCRA state lives in registers
     return c2 * sizeof(C2) + t * sizeof(T) + d * sizeof(double) + 64;
   }
 };
@@ -135,7 +135,7 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(FD_NT) fdgsc_kernel(FdgscArgs a, const typename V2<T>::type *__restrict__ tw_h_g,
+__global__ void __launch_bounds__(FD_NT, 2) fdgsc_kernel(FdgscArgs a, const typename V2<T>::type *__restrict__ tw_h_g,
                                                       const typename V2<T>::type *__restrict__ tw_n_g) {
   typedef typename V2<T>::type C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -168,8 +168,7 @@ __global__ void __launch_bounds__(FD_NT) fdgsc_kernel(FdgscArgs a, const typenam
   T *fbf_d = fbf_prev + L;
   T *dl_fbf = fbf_d + L;
   T *x0_prev = dl_fbf + L;
-  double *mcra = reinterpret_cast<double *>((reinterpret_cast<size_t>(x0_prev + L) + 15) & ~(size_t)15);   // [5][K]
-  double *P0 = mcra + 5 * K;
+  double *P0 = reinterpret_cast<double *>((reinterpret_cast<size_t>(x0_prev + L) + 15) & ~(size_t)15);     // [K]
   double *red = P0 + K;                          // 64 doubles scratch
   const int IS = FD_FLMAX - 1 + L;               // inp row stride
 
@@ -194,7 +193,11 @@ __global__ void __launch_bounds__(FD_NT) fdgsc_kernel(FdgscArgs a, const typenam
   o += (size_t)M * (L / 2);
   for (int i = tid; i < L; i += FD_NT) dl_fbf[i] = (T)st[o + i];
   o += L;
-  for (int i = tid; i < 5 * K; i += FD_NT) mcra[i] = st[o + i];
+  // MCRA state of bin tid (and of bin 256 for thread 0) stays in registers for the whole utterance
+  double mst[2][5];
+  const size_t mcra_off = o;
+#pragma unroll
+  for (int e = 0; e < 5; ++e) { mst[0][e] = st[o + (size_t)e * K + tid]; mst[1][e] = (tid == 0) ? st[o + (size_t)e * K + (K - 1)] : 0.0; }
   for (int i = tid; i < H; i += FD_NT) tw_h[i] = tw_h_g[i];
   for (int i = tid; i <= H / 2; i += FD_NT) tw_n[i] = tw_n_g[i];
   for (int i = tid; i < N; i += FD_NT) win[i] = (T)a.window[i];
@@ -282,11 +285,10 @@ __global__ void __launch_bounds__(FD_NT) fdgsc_kernel(FdgscArgs a, const typenam
         const C2 v = Xf[k];
         T pf = (T)a.alpha * Pf[k] + ((T)1 - (T)a.alpha) * (v.x * v.x + v.y * v.y);      // FastFreqLms.py:158
         Pf[k] = (pf < (T)1e-4) ? (T)1e-4 : pf;                                          // :189
-        double S_ = mcra[k], Smin = mcra[K + k], Stmp = mcra[2 * K + k], pp = mcra[3 * K + k], lam = mcra[4 * K + k];
         const double Ym1 = (k > 0) ? P0[k - 1] : 0.0, Yp1 = (k < K - 1) ? P0[k + 1] : 0.0;
-        mcra_step(S_, Smin, Stmp, pp, lam, Ym1, P0[k], Yp1, k, K, frm, reset, a.mc);
-        mcra[k] = S_; mcra[K + k] = Smin; mcra[2 * K + k] = Stmp; mcra[3 * K + k] = pp; mcra[4 * K + k] = lam;
-        p_loc[q] = pp;
+        if (q == 0) mcra_step(mst[0][0], mst[0][1], mst[0][2], mst[0][3], mst[0][4], Ym1, P0[k], Yp1, k, K, frm, reset, a.mc);
+        else mcra_step(mst[1][0], mst[1][1], mst[1][2], mst[1][3], mst[1][4], Ym1, P0[k], Yp1, k, K, frm, reset, a.mc);
+        p_loc[q] = (q == 0) ? mst[0][3] : mst[1][3];
       }
       if (reset) ell = 0;
       ++ell; ++frm;
@@ -444,7 +446,8 @@ __global__ void __launch_bounds__(FD_NT) fdgsc_kernel(FdgscArgs a, const typenam
   o += (size_t)M * (L / 2);
   for (int i = tid; i < L; i += FD_NT) st[o + i] = (double)dl_fbf[i];
   o += L;
-  for (int i = tid; i < 5 * K; i += FD_NT) st[o + i] = mcra[i];
+#pragma unroll
+  for (int e = 0; e < 5; ++e) { st[mcra_off + (size_t)e * K + tid] = mst[0][e]; if (tid == 0) st[mcra_off + (size_t)e * K + (K - 1)] = mst[1][e]; }
 }
 
 template <typename T>

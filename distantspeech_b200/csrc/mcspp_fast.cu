@@ -81,11 +81,22 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
   double *blob = a.state + (long long)s * NE * K + k;
   double *smy = sm + tid;                 // Phi_yy (real part), element e at smy[e * NT]
   double *smv = sm + NP * NT + tid;       // Phi_vv (real part)
+  double *smc = sm + 2 * NP * NT + tid;   // (2 - delta_ij) Re(conj(a_i) a_j), constant per bin
 #pragma unroll
   for (int e = 0; e < NP; ++e) { smy[e * NT] = blob[(long long)(OFF_YR + e) * K]; smv[e * NT] = blob[(long long)(OFF_VR + e) * K]; }
   double mS = blob[(long long)(OFF_MC + 0) * K], mSmin = blob[(long long)(OFF_MC + 1) * K], mStmp = blob[(long long)(OFF_MC + 2) * K],
          mp = blob[(long long)(OFF_MC + 3) * K], mlam = blob[(long long)(OFF_MC + 4) * K];
 
+  {
+    double ar[M], ai[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { const double2 v = a.a0[(long long)m * K + k]; ar[m] = v.x; ai[m] = v.y; }
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = i; j < M; ++j)
+        smc[pidx<M>(i, j) * NT] = ((i == j) ? 1.0 : 2.0) * fma(ai[i], ai[j], ar[i] * ar[j]);
+  }
   int frm = a.frm_cnt, ell = a.ell;
   const float2 *Xp = reinterpret_cast<const float2 *>(a.X) + (long long)s * a.T * M * K + k;
   float2 *Yp = a.Yout + (long long)s * a.T * K + k;
@@ -127,49 +138,32 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
     }
 #define AS(i, j) (((i) <= (j)) ? A[pidx<M>(i, j)] : A[pidx<M>(j, i)])
 
-    // ---- P2/P3: MVDR numerator b = A a and denominator a^H b, applied on the fly:
-    //      den = a^H A a,  Y = b^H y                                          beamformer.py:152-153
-    double den = 0.0, Yr = 0.0, Yi = 0.0;
-    {
-      double ar[M];
+    // ---- MVDR denominator den = a^H A a = sum_{i<=j} A_ij C_ij with the per-bin constants
+    //      C_ij = (2 - delta_ij) Re(conj(a_i) a_j) staged in shared memory      beamformer.py:152-153
+    // (all long reductions below use several independent accumulators: with two warps per
+    //  scheduler the kernel is bound by dependent-issue latency, not by fp64 throughput)
+    double den4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int m = 0; m < M; ++m) ar[m] = ld_f64_once(a0 + 2 * m * K);
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        double b = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) b = fma(AS(i, j), ar[j], b);
-        den = fma(ar[i], b, den);
-        Yr = fma(b, yr[i], Yr);
-        Yi = fma(b, yi[i], Yi);
-      }
-    }
-    {
-      double ai[M];
-#pragma unroll
-      for (int m = 0; m < M; ++m) ai[m] = ld_f64_once(a0 + 2 * m * K + 1);
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        double b = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) b = fma(AS(i, j), ai[j], b);
-        den = fma(ai[i], b, den);
-        Yr = fma(b, yi[i], Yr);      // conj(b) y: (br - j bi)(yr + j yi)
-        Yi = fma(-b, yr[i], Yi);
-      }
-    }
+    for (int e = 0; e < NP; ++e) den4[e & 3] = fma(A[e], smc[e * NT], den4[e & 3]);
+    const double den = (den4[0] + den4[1]) + (den4[2] + den4[3]);
+    double Yr = 0.0, Yi = 0.0, Yr2 = 0.0, Yi2 = 0.0;   // numerator (A a)^H y = a^H u, accumulated below from u = A y
 
     // ---- P4: Phi_yy update, Xr = Re(Phi_yy - Phi_vv), xi = tr(A Xr), real half of gamma   :84-90,274-284
     const double alpha = a.alpha, one_m_alpha = 1.0 - a.alpha;
-    double trd = 0.0, tro = 0.0, gmd = 0.0, gmo = 0.0;
+    double trd[2] = {0.0, 0.0}, tro[4] = {0.0, 0.0, 0.0, 0.0}, gmd[2] = {0.0, 0.0}, gmo[4] = {0.0, 0.0, 0.0, 0.0};
     {
       double ur[M];
 #pragma unroll
       for (int i = 0; i < M; ++i) {
-        double sr = 0.0;
+        double sr = 0.0, sr2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < M; ++j) sr = fma(AS(i, j), yr[j], sr);
-        ur[i] = sr;
+        for (int j = 0; j < M; ++j) { if (j & 1) sr2 = fma(AS(i, j), yr[j], sr2); else sr = fma(AS(i, j), yr[j], sr); }
+        ur[i] = sr + sr2;
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {          // conj(a) * u, real half of u
+        Yr = fma(ld_f64_once(a0 + 2 * m * K), ur[m], Yr);
+        Yi = fma(-ld_f64_once(a0 + 2 * m * K + 1), ur[m], Yi);
       }
       // every product chain starts at the shared-memory operand, so nothing can be
       // pre-computed (and spilled) ahead of the loads by the instruction scheduler
@@ -182,8 +176,8 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
           const double pyy = fma(tr_i, yr[j], fma(ti_i, yi[j], alpha * smy[e * NT]));
           smy[e * NT] = pyy;
           const double x = pyy - smv[e * NT];
-          if (i == j) { trd = fma(A[e], x, trd); gmd = fma(x * ur[i], ur[j], gmd); }
-          else { tro = fma(A[e], x, tro); gmo = fma(x * ur[i], ur[j], gmo); }
+          if (i == j) { trd[i & 1] = fma(A[e], x, trd[i & 1]); gmd[i & 1] = fma(x * ur[i], ur[j], gmd[i & 1]); }
+          else { tro[e & 3] = fma(A[e], x, tro[e & 3]); gmo[e & 3] = fma(x * ur[i], ur[j], gmo[e & 3]); }
         }
       }
     }
@@ -192,10 +186,15 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
       double ui[M];
 #pragma unroll
       for (int i = 0; i < M; ++i) {
-        double si = 0.0;
+        double si = 0.0, si2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < M; ++j) si = fma(AS(i, j), yi[j], si);
-        ui[i] = si;
+        for (int j = 0; j < M; ++j) { if (j & 1) si2 = fma(AS(i, j), yi[j], si2); else si = fma(AS(i, j), yi[j], si); }
+        ui[i] = si + si2;
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {          // conj(a) * u, imaginary half of u
+        Yr2 = fma(ld_f64_once(a0 + 2 * m * K + 1), ui[m], Yr2);
+        Yi2 = fma(ld_f64_once(a0 + 2 * m * K), ui[m], Yi2);
       }
 #pragma unroll
       for (int i = 0; i < M; ++i) {
@@ -203,13 +202,14 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
         for (int j = i; j < M; ++j) {
           const int e = pidx<M>(i, j);
           const double x = smy[e * NT] - smv[e * NT];
-          if (i == j) gmd = fma(x * ui[i], ui[j], gmd);
-          else gmo = fma(x * ui[i], ui[j], gmo);
+          if (i == j) gmd[i & 1] = fma(x * ui[i], ui[j], gmd[i & 1]);
+          else gmo[e & 3] = fma(x * ui[i], ui[j], gmo[e & 3]);
         }
       }
     }
 #undef AS
-    double xi = fma(2.0, tro, trd), gam = fma(2.0, gmo, gmd);
+    double xi = fma(2.0, (tro[0] + tro[1]) + (tro[2] + tro[3]), trd[0] + trd[1]);
+    double gam = fma(2.0, (gmo[0] + gmo[1]) + (gmo[2] + gmo[3]), gmd[0] + gmd[1]);
     xi = fmin(fmax(xi, a.snr_min), a.snr_max);                               // :286-287
     gam = fmin(fmax(gam, a.snr_min), a.snr_max);
 
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
       if (k < 2) G = 0.0;
       scale *= G;
     }
-    *Yp = make_float2((float)(Yr * scale), (float)(Yi * scale));
+    *Yp = make_float2((float)((Yr + Yr2) * scale), (float)((Yi + Yi2) * scale));
     if (a.k_first == 2 && k == 2) { Yp[-1] = make_float2(0.f, 0.f); Yp[-2] = make_float2(0.f, 0.f); }
     Yp += K;
   }
@@ -258,7 +258,7 @@ static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
   constexpr int NT = 64;
   constexpr int NP = M * (M + 1) / 2;
   constexpr int MINB = 4;            // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
-  const size_t smem = (size_t)2 * NP * NT * sizeof(double);
+  const size_t smem = (size_t)3 * NP * NT * sizeof(double);
   auto kern = mcspp_fast_kernel<M, NT, MINB>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)a.S * (a.K - a.k_first);
