@@ -97,6 +97,60 @@ template <int H, int NS, typename T> struct FftPass {
   }
 };
 
+// First Stockham pass fed from registers: v[i][r] = z[(lane + 32 i) + r * NB].  Saves one full
+// shared-memory round trip per transform when the caller can load its frame straight from
+// global memory in this (coalesced) order.  Continues with the remaining passes in `buf`.
+template <int H, typename T> struct FftFirst {
+  typedef typename V2<T>::type C;
+  static constexpr int R = FftPass<H, 1, T>::R;
+  static constexpr int NB = H / R;
+  static constexpr int PER = (NB + 31) / 32;
+  __device__ __forceinline__ static void run(C (&v)[PER][R], C *buf, const C *__restrict__ tw, int lane) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = lane + 32 * i;
+      if (NB % 32 == 0 || j < NB) {
+        if (R == 8) dft8<T>(v[i]);
+        else if (R == 4) dft4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        else dft2(v[i]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[FPAD<T>(j * R + r)] = v[i][r];
+      }
+    }
+    __syncwarp();
+    if constexpr (R < H) FftPass<H, R, T>::run(buf, tw, lane);
+  }
+};
+
+// Real-FFT split of the H-point complex spectrum in `buf`, written straight to `out[0..H]`
+// (global memory) instead of back to shared memory.  OutC is float2 or double2.
+template <int N, typename T, typename OutC>
+__device__ __forceinline__ void warp_rfft_split_store(const typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_n,
+                                                      OutC *__restrict__ out, int lane) {
+  typedef typename V2<T>::type C;
+  constexpr int H = N / 2;
+  for (int k = lane; k <= H / 2; k += 32) {
+    if (k == 0) {
+      const C a = buf[FPAD<T>(0)];
+      OutC o0, oh;
+      o0.x = a.x + a.y; o0.y = 0;
+      oh.x = a.x - a.y; oh.y = 0;
+      out[0] = o0; out[H] = oh;
+    } else {
+      const C a = buf[FPAD<T>(k)], b = buf[FPAD<T>(H - k)];
+      const C w = tw_n[k];
+      const T sx = (T)0.5 * (a.x + b.x), sy = (T)0.5 * (a.y - b.y);
+      const T dx = (T)0.5 * (a.x - b.x), dy = (T)0.5 * (a.y + b.y);
+      const T px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;
+      const T ex = -py, ey = px;
+      OutC o1, o2;
+      o1.x = sx - ex; o1.y = sy - ey;
+      o2.x = sx + ex; o2.y = -(sy + ey);
+      out[k] = o1; out[H - k] = o2;
+    }
+  }
+}
+
 // in-place forward complex FFT of H points held in buf[FPAD<T>(i)], one warp
 template <int H, typename T>
 __device__ __forceinline__ void warp_cfft(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h, int lane) {

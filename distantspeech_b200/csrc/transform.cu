@@ -50,19 +50,30 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
     if (a.mode == DS_STFT_STREAMING) g0 = t * a.hop - ov;
     else if (a.mode == DS_STFT_CENTER) g0 = t * a.hop - N / 2;
     else g0 = t * a.hop;
-    const bool interior = (g0 >= 0) && (g0 + N <= a.Ns) && ((reinterpret_cast<size_t>(xs + g0) & 15) == 0);
+    const unsigned s = sc / (unsigned)a.C;
+    const unsigned c = sc - s * (unsigned)a.C;
+    const size_t o = (((size_t)s * a.T + t) * a.C + c) * K;
+    const bool interior = (g0 >= 0) && (g0 + N <= a.Ns) && ((reinterpret_cast<size_t>(xs + g0) & 7) == 0);
     if (interior) {
-      const float4 *src = reinterpret_cast<const float4 *>(xs + g0);
-      float4 v[N / 128];
+      // frame read straight from global memory in first-pass order (coalesced float2 rows)
+      typedef FftFirst<H, T> F1;
+      C2 v[F1::PER][F1::R];
+      const float2 *src = reinterpret_cast<const float2 *>(xs + g0);
+      const C2 *w2 = reinterpret_cast<const C2 *>(win);
 #pragma unroll
-      for (int i = 0; i < N / 128; ++i) v[i] = __ldg(src + lane + 32 * i);
+      for (int i = 0; i < F1::PER; ++i) {
+        const int j = lane + 32 * i;
+        if (F1::NB % 32 == 0 || j < F1::NB) {
 #pragma unroll
-      for (int i = 0; i < N / 128; ++i) {
-        const int q = lane + 32 * i;                     // samples 4q .. 4q+3 = complex 2q, 2q+1
-        const T w0 = win[4 * q], w1 = win[4 * q + 1], w2 = win[4 * q + 2], w3 = win[4 * q + 3];
-        buf[FPAD<T>(2 * q)] = mk2<T>((T)v[i].x * w0, (T)v[i].y * w1);
-        buf[FPAD<T>(2 * q + 1)] = mk2<T>((T)v[i].z * w2, (T)v[i].w * w3);
+          for (int r = 0; r < F1::R; ++r) {
+            const int e = j + r * F1::NB;
+            const float2 xv = __ldg(src + e);
+            const C2 wv = w2[e];
+            v[i][r] = mk2<T>((T)xv.x * wv.x, (T)xv.y * wv.y);
+          }
+        }
       }
+      F1::run(v, buf, tw_h, lane);
     } else {
       const float *hs = a.history ? a.history + (size_t)sc * ov : nullptr;
       for (int n = lane; n < N; n += 32) {
@@ -77,21 +88,12 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
         }
         fbuf[2 * FPAD<T>(n >> 1) + (n & 1)] = (T)v * win[n];
       }
+      __syncwarp();
+      warp_cfft<H, T>(buf, tw_h, lane);
     }
-    __syncwarp();
-    warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-    const size_t obase = (size_t)f * K;                  // [S][T][C][K] with f = (s*C + c)*T + t  -> reorder below
-    (void)obase;
-    const unsigned s = sc / (unsigned)a.C;
-    const unsigned c = sc - s * (unsigned)a.C;
-    const size_t o = (((size_t)s * a.T + t) * a.C + c) * K;
-    if (a.out_c128) {
-      double2 *out = reinterpret_cast<double2 *>(a.X) + o;
-      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD<T>(k)]; out[k] = make_double2((double)v.x, (double)v.y); }
-    } else {
-      float2 *out = reinterpret_cast<float2 *>(a.X) + o;
-      for (int k = lane; k < K; k += 32) { C2 v = buf[FPAD<T>(k)]; out[k] = make_float2((float)v.x, (float)v.y); }
-    }
+    // real-FFT split, written straight to the spectrum (complex64 rounding, transform.py:212)
+    if (a.out_c128) warp_rfft_split_store<N, T, double2>(buf, tw_n, reinterpret_cast<double2 *>(a.X) + o, lane);
+    else warp_rfft_split_store<N, T, float2>(buf, tw_n, reinterpret_cast<float2 *>(a.X) + o, lane);
     __syncwarp();
   }
 }
@@ -347,18 +349,25 @@ __global__ void __launch_bounds__(FBF_WARPS * 32, 3) fixedbf_kernel(FixedBfArgs 
           const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
           float2 *buf = micbuf + (size_t)m * BE;
           const int g0 = t * a.hop - ov;
-          if (g0 >= 0 && ((reinterpret_cast<size_t>(xs + g0) & 15) == 0)) {
-            const float4 *src = reinterpret_cast<const float4 *>(xs + g0);
-            float4 v[N / 128];
+          if (g0 >= 0 && ((reinterpret_cast<size_t>(xs + g0) & 7) == 0)) {
+            typedef FftFirst<H, float> F1;
+            float2 v[F1::PER][F1::R];
+            const float2 *src = reinterpret_cast<const float2 *>(xs + g0);
+            const float2 *w2 = reinterpret_cast<const float2 *>(win);
 #pragma unroll
-            for (int i = 0; i < N / 128; ++i) v[i] = __ldg(src + lane + 32 * i);
+            for (int i = 0; i < F1::PER; ++i) {
+              const int j = lane + 32 * i;
+              if (F1::NB % 32 == 0 || j < F1::NB) {
 #pragma unroll
-            for (int i = 0; i < N / 128; ++i) {
-              const int q = lane + 32 * i;
-              const float4 w = *reinterpret_cast<const float4 *>(win + 4 * q);
-              buf[FPAD<float>(2 * q)] = make_float2(v[i].x * w.x, v[i].y * w.y);
-              buf[FPAD<float>(2 * q + 1)] = make_float2(v[i].z * w.z, v[i].w * w.w);
+                for (int r = 0; r < F1::R; ++r) {
+                  const int e = j + r * F1::NB;
+                  const float2 xv = __ldg(src + e);
+                  const float2 wv = w2[e];
+                  v[i][r] = make_float2(xv.x * wv.x, xv.y * wv.y);
+                }
+              }
             }
+            F1::run(v, buf, tw_h, lane);
           } else {
             const float *hs = hist_in + ((long long)s * a.M + m) * ov;
             float *fb = reinterpret_cast<float *>(buf);
@@ -367,9 +376,9 @@ __global__ void __launch_bounds__(FBF_WARPS * 32, 3) fixedbf_kernel(FixedBfArgs 
               const float v = (g < 0) ? hs[ov + g] : xs[g];
               fb[2 * FPAD<float>(n >> 1) + (n & 1)] = v * win[n];
             }
+            __syncwarp();
+            warp_cfft<H, float>(buf, tw_h, lane);
           }
-          __syncwarp();
-          warp_rfft<N, float>(buf, tw_h, tw_n, lane);
         }
       }
     } else if (t > th0) {
@@ -404,19 +413,35 @@ __global__ void __launch_bounds__(FBF_WARPS * 32, 3) fixedbf_kernel(FixedBfArgs 
       }
     }
     __syncthreads();
-    // ---- weights: Y_b[k] = sum_m conj(W[b,k,m]) X_m[k] --------------------------------
+    // ---- weights fused with the real-FFT split: micbuf holds the H-point complex spectra Z_m;
+    //      X_m[k] = s/2 - e, X_m[H-k] = conj(s/2 + e) (see warp_rfft); Y_b[k] = sum_m conj(W[b,k,m]) X_m[k]
     if (t < t1) {
-      for (int i = tid; i < a.B * K; i += blockDim.x) {
-        const int b = i / K, k = i - b * K;
-        const float2 *w = a.W + ((size_t)b * K + k) * a.M;
-        float yr = 0.f, yi = 0.f;
-        for (int m = 0; m < a.M; ++m) {
-          const float2 xv = micbuf[(size_t)m * BE + FPAD<float>(k)];
-          const float2 wv = __ldg(w + m);
-          yr += wv.x * xv.x + wv.y * xv.y;
-          yi += wv.x * xv.y - wv.y * xv.x;
+      for (int kk = tid; kk <= H / 2; kk += blockDim.x) {
+        const float2 wn = tw_n[kk];
+        for (int b = 0; b < a.B; ++b) {
+          const float2 *w1 = a.W + ((size_t)b * K + kk) * a.M;
+          const float2 *w2p = a.W + ((size_t)b * K + (H - kk)) * a.M;
+          float y1r = 0.f, y1i = 0.f, y2r = 0.f, y2i = 0.f;
+          for (int m = 0; m < a.M; ++m) {
+            const float2 za = micbuf[(size_t)m * BE + FPAD<float>(kk)];
+            const float2 zb = micbuf[(size_t)m * BE + FPAD<float>((H - kk) & (H - 1))];
+            float x1r, x1i, x2r, x2i;
+            if (kk == 0) {
+              x1r = za.x + za.y; x1i = 0.f; x2r = za.x - za.y; x2i = 0.f;
+            } else {
+              const float sx = 0.5f * (za.x + zb.x), sy = 0.5f * (za.y - zb.y);
+              const float dx = 0.5f * (za.x - zb.x), dy = 0.5f * (za.y + zb.y);
+              const float px = wn.x * dx - wn.y * dy, py = wn.x * dy + wn.y * dx;
+              x1r = sx + py; x1i = sy - px;          // s/2 - e, e = (-py, px)
+              x2r = sx - py; x2i = -(sy + px);       // conj(s/2 + e)
+            }
+            const float2 wa = __ldg(w1 + m), wb = __ldg(w2p + m);
+            y1r += wa.x * x1r + wa.y * x1i; y1i += wa.x * x1i - wa.y * x1r;
+            y2r += wb.x * x2r + wb.y * x2i; y2i += wb.x * x2i - wb.y * x2r;
+          }
+          beambuf[(size_t)b * BE + FPAD<float>(kk)] = make_float2(y1r, y1i);
+          beambuf[(size_t)b * BE + FPAD<float>(H - kk)] = make_float2(y2r, y2i);
         }
-        beambuf[(size_t)b * BE + FPAD<float>(k)] = make_float2(yr, yi);
       }
     }
     __syncthreads();
