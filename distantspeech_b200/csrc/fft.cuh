@@ -27,6 +27,11 @@ template <typename T> __host__ __device__ __forceinline__ constexpr int FPAD(int
 // number of V2 elements a frame buffer needs (H+1 bins, swizzled within 16-element groups / padded)
 __host__ __device__ constexpr int fft_buf_elems(int n_fft) { return (n_fft / 2 + 1) + (n_fft / 2 + 1) / 8 + 17; }
 
+// product rounded on its own (never contracted into an FMA with the first butterfly), so a frame gives
+// the same bits whether its windowed samples went through shared memory or straight into registers
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
 // multiply by -i : (x + iy)(-i) = y - ix

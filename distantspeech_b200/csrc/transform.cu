@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
             const int e = j + r * F1::NB;
             const float2 xv = __ldg(src + e);
             const C2 wv = w2[e];
-            v[i][r] = mk2<T>((T)xv.x * wv.x, (T)xv.y * wv.y);
+            v[i][r] = mk2<T>(mul_rn((T)xv.x, wv.x), mul_rn((T)xv.y, wv.y));
           }
         }
       }
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(FBF_WARPS * 32, 3) fixedbf_kernel(FixedBfArgs 
                   const int e = j + r * F1::NB;
                   const float2 xv = __ldg(src + e);
                   const float2 wv = w2[e];
-                  v[i][r] = make_float2(xv.x * wv.x, xv.y * wv.y);
+                  v[i][r] = make_float2(mul_rn(xv.x, wv.x), mul_rn(xv.y, wv.y));
                 }
               }
             }

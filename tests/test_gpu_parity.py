@@ -231,6 +231,12 @@ def test_chain_batch_and_streaming(cuda):
     ya = ch2.process(x_nm[:, :256 * 50])
     yb = ch2.process(x_nm[:, 256 * 50:])
     assert np.max(np.abs(np.concatenate([ya, yb], axis=1) - y)) < 1e-6      # chunked == whole
+    # ... down to single-hop chunks: the first frame of a chunk (history path) and interior frames
+    # (register-fed path) round identically, so the hard MCRA decisions cannot flip between the two
+    ch3 = MvdrMcsppChain(mic, look_angle=(30, 0))
+    cuts = [0, 256, 256 * 3, 256 * 4, 256 * 40, 256 * 125]
+    yc = np.concatenate([ch3.process(x_nm[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:])], axis=1)
+    assert np.array_equal(yc, y)
     # host-buffer pipeline == device path
     import torch
     yh = ch.process_host(torch.from_numpy(xs).pin_memory(), chunk_streams=3)
