@@ -62,6 +62,23 @@ class McsppTaps(C.Structure):
                 ("w_mvdr", C.c_void_p), ("w_pmwf", C.c_void_p), ("Phi_vv_inv_last", C.c_void_p)]
 
 
+class McsppCdrParams(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_frames", C.c_int32),
+                ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32), ("cdr_only", C.c_int32),
+                ("band_lo_bin", C.c_int32), ("band_hi_bin", C.c_int32), ("init_frames", C.c_int32),
+                ("fallback_loaded_frames", C.c_int32),
+                ("alpha", C.c_double), ("alpha_d", C.c_double), ("alpha_cdr", C.c_double),
+                ("load_min", C.c_double), ("load_max", C.c_double), ("snr_min", C.c_double), ("snr_max", C.c_double),
+                ("pmwf_beta", C.c_double), ("q_init", C.c_double),
+                ("mcra_alpha_d", C.c_double), ("mcra_alpha_s", C.c_double), ("mcra_delta_s", C.c_double),
+                ("mcra_alpha_p", C.c_double), ("mcra_p_min", C.c_double), ("mcra_p_max", C.c_double)]
+
+
+class McsppCdrTaps(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("xi", C.c_void_p), ("gamma", C.c_void_p), ("q", C.c_void_p), ("cdr", C.c_void_p),
+                ("w", C.c_void_p)]
+
+
 class AmvdrParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_frames", C.c_int32),
                 ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32), ("method", C.c_int32),
@@ -149,6 +166,17 @@ def _declare(lib):
     lib.ds_float_to_pcm16_run.argtypes = [C.c_size_t, vp, vp, vp]
     lib.ds_phat_run.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     lib.ds_srp_run.argtypes = [i32, i32, i32, i32, dbl, i32, vp, vp, vp, i32, vp]
+    lib.ds_mcspp_cdr_default_params.argtypes = [C.POINTER(McsppCdrParams), C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ds_mcspp_cdr_default_params.restype = None
+    lib.ds_mcspp_cdr_state_bytes.argtypes = [C.POINTER(McsppCdrParams)]
+    lib.ds_mcspp_cdr_state_bytes.restype = C.c_size_t
+    lib.ds_mcspp_cdr_workspace_bytes.argtypes = [C.POINTER(McsppCdrParams)]
+    lib.ds_mcspp_cdr_workspace_bytes.restype = C.c_size_t
+    lib.ds_mcspp_cdr_run.argtypes = [C.POINTER(McsppCdrParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.POINTER(McsppCdrTaps), C.c_void_p]
+    lib.ds_mcspp_cdr_run.restype = C.c_int
+    lib.ds_mcspp_cdr_export.argtypes = [C.POINTER(McsppCdrParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ds_mcspp_cdr_export.restype = C.c_int
     lib.ds_chain_state_bytes.argtypes = [C.POINTER(ChainParams)]
     lib.ds_chain_state_bytes.restype = C.c_size_t
     lib.ds_chain_workspace_bytes.argtypes = [C.POINTER(ChainParams)]

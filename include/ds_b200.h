@@ -227,6 +227,54 @@ int ds_mcspp_run(const ds_mcspp_params *p, void *state, const void *a0, const vo
  * 2 mcra block ([S][5][K] float64).                                              */
 int ds_mcspp_export(const ds_mcspp_params *p, const void *state, int field, void *out, void *stream);
 
+/* ---- McSpp with the McCDR prior (noise_estimation/mcspp.py, mccdr.py) ------ */
+typedef struct ds_mcspp_cdr_params {
+  int32_t n_fft;
+  int32_t n_streams;
+  int32_t n_mics;   /* must be 4: McSpp builds McCDR with its default 4 channels
+                       (mcspp.py:54) and the reference raises IndexError above that  */
+  int32_t n_frames;
+  int32_t frm_cnt;  /* frames already processed (host-tracked; McSpp.frm_cnt)        */
+  int32_t ell;      /* window counter of McCDR's MCRA at entry                       */
+  int32_t mcra_L;   /* 65                                              mccdr.py:56   */
+  int32_t cdr_only; /* 1: only McCDR.estimation (taps->cdr), state of the prior only */
+  int32_t band_lo_bin, band_hi_bin; /* int(500 nfft/16000), int(2000 nfft/16000) :266-267 */
+  int32_t init_frames;              /* 10: Phi_vv = Phi_yy, q = q_init     :276-278  */
+  int32_t fallback_loaded_frames;   /* 5: loaded fallback inverse          :224-227  */
+  double alpha, alpha_d;            /* .92 .92                             :64-65    */
+  double alpha_cdr;                 /* .9                               mccdr.py:126 */
+  double load_min, load_max;        /* 1e-4 1e-1                           :262-263  */
+  double snr_min, snr_max;          /* 1e-6 1e8  (xi, gamma clip)          :229,236  */
+  double pmwf_beta;                 /* 10                                  :286      */
+  double q_init;                    /* .99                                 :278      */
+  double mcra_alpha_d, mcra_alpha_s, mcra_delta_s, mcra_alpha_p, mcra_p_min, mcra_p_max;
+} ds_mcspp_cdr_params;
+void ds_mcspp_cdr_default_params(ds_mcspp_cdr_params *p, int n_fft, int n_streams, int n_mics, int n_frames);
+size_t ds_mcspp_cdr_state_bytes(const ds_mcspp_cdr_params *p);     /* zero-filled = reset */
+size_t ds_mcspp_cdr_workspace_bytes(const ds_mcspp_cdr_params *p); /* scratch, per call   */
+
+typedef struct ds_mcspp_cdr_taps { /* optional per-frame outputs, any may be NULL  */
+  double *p;     /* [S][T][K] posterior SPP (the return value of McSpp.estimation) */
+  double *xi;    /* [S][T][K]                                                      */
+  double *gamma; /* [S][T][K]                                                      */
+  double *q;     /* [S][T][K] prior speech absence probability used by compute_p   */
+  double *cdr;   /* [S][T][K] McCDR.estimation return value sqrt(CDR^2 p_mcra)     */
+  void *w;       /* [S][T][4][K] c128 PMWF weights (beta = pmwf_beta)              */
+} ds_mcspp_cdr_taps;
+
+/* replaces, per frame, McSpp.estimation (mcspp.py:248-305) including McCDR.estimation
+ * (mccdr.py:164-177) and compute_pmwf_weight (mcspp_base.py:220-240).
+ *   Fn   [K] float64: diffuse coherence Fvv[:, 1, 2] of the 4-mic circular r = 0.032 array
+ *        McCDR owns (mccdr.py:58-59, gen_noise_msc.py)
+ *   X    [S][T][4][K] c64 (x_is_c128 = 0) or c128
+ *   Yout [S][T][K] c64 = w^H y (or NULL)                                            */
+int ds_mcspp_cdr_run(const ds_mcspp_cdr_params *p, void *state, void *workspace, const double *Fn,
+                     const void *X, int x_is_c128, void *Yout, const ds_mcspp_cdr_taps *taps, void *stream);
+/* state views. field: 0 Phi_yy, 1 Phi_vv, 2 Phi_vv_inv, 3 Phi_xx (c128 [S][K][4][4]; 2-3 as of the
+ * last frame); 4 w [S][8][K] (re[4], im[4]); 5 [S][4][K] xi gamma q cdr^2; 6 [S][16][K] Pxii[4]
+ * Re Pxij[6] Im Pxij[6]; 7 [S][6][K] MCRA S Smin Stmp p lambda_d, posterior p      */
+int ds_mcspp_cdr_export(const ds_mcspp_cdr_params *p, const void *state, int field, void *out, void *stream);
+
 /* ---- postfilter gains ------------------------------------------------------ */
 typedef struct ds_omlsa_multi_params {
   int32_t n_bins, n_streams, n_frames;

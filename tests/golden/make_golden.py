@@ -150,6 +150,22 @@ def main():
     Ws = np.array([pf.getweights(Z8[:, :, n]).squeeze() for n in range(40)])
     save("zelinski.npz", Z=Z8.astype(np.complex64), W=Ws, Pxii=pf.Pxii, Pxij=pf.Pxij)
 
+    # ---- a14: McSpp (CDR-driven prior, complex inverse with SNR-dependent loading), 4 mics ----
+    from DistantSpeech.noise_estimation.mcspp import McSpp
+    geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=512)
+    x4 = np.ascontiguousarray(O.synth_streams(1, geo4, 256 * 240, seed0=0xCD4)[0].T)           # [N, 4] float32
+    D4 = Transform(n_fft=512, hop_length=256, channel=4).stft(x4.astype(np.float64))          # [257, 240, 4]
+    with contextlib.redirect_stdout(io.StringIO()):
+        est = McSpp(nfft=512, channels=4)
+    taps = {k: [] for k in ("p", "xi", "gamma", "q")}
+    for n in range(D4.shape[1]):
+        est.estimation(D4[:, n, :])
+        taps["p"].append(est.p.copy()); taps["xi"].append(est.xi.copy()); taps["gamma"].append(est.gamma.copy())
+        taps["q"].append(est.q.copy())
+    save("mcspp_cdr.npz", x=x4, **{k: np.array(v).T for k, v in taps.items()}, w_last=est.w, Phi_yy_last=est.Phi_yy,
+         Phi_vv_last=est.Phi_vv, Phi_vv_inv_last=est.Phi_vv_inv, Phi_xx_last=est.Phi_xx,
+         mcra_p_last=est.mccdr.mcra.p, Pxii_last=est.mccdr.Gamma_estimator.Pxii, Pxij_last=est.mccdr.Gamma_estimator.Pxij)
+
 
 if __name__ == "__main__":
     main()

@@ -199,6 +199,44 @@ def test_mcspp_estimator_golden(cuda):
     assert np.allclose(np.sum(np.conj(w) * g["a0"], axis=1), 1.0, atol=1e-9)      # distortionless
 
 
+# ---------------------------------------------------------------- a14
+def test_mcspp_cdr_golden(cuda):
+    """McSpp with the McCDR prior against the reference's own per-frame outputs (240 frames, 4 mics)."""
+    from distantspeech_b200.noise_estimation.mcspp import McSpp
+    from distantspeech_b200.noise_estimation.mccdr import McCDR
+    from distantspeech_b200.transform.transform import Transform
+    g = golden("mcspp_cdr.npz")
+    D = O.Transform(channel=4, n_fft=512, hop_length=256).stft(g["x"].astype(np.float64))   # the reference's spectrum
+    est = McSpp(nfft=512, channels=4)
+    res = est.estimation_frames(D, want_Y=True)
+    for k in ("p", "xi", "gamma", "q"):
+        assert np.allclose(res[k], g[k], rtol=1e-8, atol=1e-12), k
+    assert np.array_equal(est.mccdr.mcra.p, g["mcra_p_last"])                   # MCRA decisions of the prior identical
+    scale = lambda a: np.max(np.abs(a))
+    for nm, a in (("w_last", est.w), ("Phi_yy_last", est.Phi_yy), ("Phi_vv_last", est.Phi_vv),
+                  ("Phi_vv_inv_last", est.Phi_vv_inv), ("Phi_xx_last", est.Phi_xx)):
+        assert np.max(np.abs(a - g[nm])) <= 1e-10 * scale(g[nm]), nm
+    assert np.allclose(res["cdr"][:, 10:], 1 - g["q"][:, 10:], rtol=0, atol=1e-12)   # q = 1 - McCDR.estimation (:117-118)
+    Yref = np.einsum("ktm,ktm->kt", np.conj(res["w"]), D)
+    assert np.max(np.abs(res["Y"] - Yref)) <= 2e-7 * scale(Yref)                # complex64 output
+    # one frame per call == many frames per call; McCDR alone == the prior inside McSpp
+    e2, cdr = McSpp(nfft=512, channels=4), McCDR(nfft=512)
+    for n in range(25):
+        p = e2.estimation(D[:, n, :])
+        G = cdr.estimation(D[:, n, :])
+    assert np.array_equal(p, res["p"][:, 24]) and np.array_equal(e2.w, res["w"][:, 24]) and np.array_equal(e2.q, res["q"][:, 24])
+    assert np.array_equal(G, res["cdr"][:, 24])
+    # from the waveform through the fp32 device STFT: same decisions, probabilities within 1e-4
+    e3 = McSpp(nfft=512, channels=4)
+    r3 = e3.estimation_frames(Transform(n_fft=512, hop_length=256, channel=4).stft(g["x"]))
+    assert np.max(np.abs(r3["p"] - g["p"])) < 1e-4 and np.max(np.abs(r3["q"] - g["q"])) < 1e-4
+    # streams are independent: batch of two == two singles
+    rb = McSpp(nfft=512, channels=4).estimation_frames(np.stack([D[:, :60], D[:, 60:120]]))
+    assert np.array_equal(rb["p"][0], res["p"][:, :60]) and rb["p"].shape == (2, 257, 60)
+    with pytest.raises(ValueError):
+        McSpp(nfft=512, channels=8)                                            # IndexError in the reference
+
+
 @pytest.mark.parametrize("prec", ["fp32", "fp64"])
 @pytest.mark.parametrize("full", [False, True])
 def test_chain_golden(cuda, prec, full):

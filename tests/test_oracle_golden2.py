@@ -1,5 +1,6 @@
 """CPU: oracle vs reference-generated goldens for the FDGSC / postfilter rows (a10, a15, a16, a17)."""
 import numpy as np
+import pytest
 
 from conftest import golden, snr_db
 from oracle import np_oracle as O
@@ -36,3 +37,20 @@ def test_zelinski_golden():
         W = pf.getweights(g["Z"][:, :, n].astype(complex))
         assert np.allclose(W, g["W"][n], rtol=1e-12, atol=0)
     assert np.allclose(pf.Pxii, g["Pxii"], rtol=1e-13) and np.allclose(pf.Pxij, g["Pxij"], rtol=1e-13, atol=1e-30)
+
+
+def test_mcspp_cdr_golden():
+    """a14: McSpp with the McCDR prior, 4 microphones, 240 frames (MCRA of the prior leaves its
+    2 x 65-frame warm-up) -- the restatement reproduces the reference to the last bit."""
+    g = golden("mcspp_cdr.npz")
+    D = O.Transform(channel=4, n_fft=512, hop_length=256).stft(g["x"].astype(np.float64))      # [257, 240, 4]
+    est = O.McSpp(nfft=512, channels=4)
+    for n in range(D.shape[1]):
+        p = est.estimation(D[:, n, :])
+        assert np.array_equal(p, g["p"][:, n]) and np.array_equal(est.xi, g["xi"][:, n])
+        assert np.array_equal(est.gamma, g["gamma"][:, n]) and np.array_equal(est.q, g["q"][:, n])
+    assert np.array_equal(est.w, g["w_last"]) and np.array_equal(est.Phi_vv, g["Phi_vv_last"])
+    assert np.array_equal(est.Phi_vv_inv, g["Phi_vv_inv_last"]) and np.array_equal(est.Phi_xx, g["Phi_xx_last"])
+    assert np.array_equal(est.mccdr.mcra.p, g["mcra_p_last"])
+    with pytest.raises(ValueError):
+        O.McSpp(nfft=512, channels=6)                     # the reference raises IndexError above 4 channels
