@@ -100,7 +100,7 @@ class FdgscParams(C.Structure):
 class OmlsaMultiParams(C.Structure):
     _fields_ = [("n_bins", C.c_int32), ("n_streams", C.c_int32), ("n_frames", C.c_int32), ("n_mics", C.c_int32),
                 ("first_frame", C.c_int32), ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32),
-                ("cal_weights", C.c_int32), ("reserved", C.c_int32),
+                ("cal_weights", C.c_int32), ("u_const", C.c_int32),
                 ("alpha_d", C.c_double), ("alpha_s", C.c_double), ("alpha_xi", C.c_double), ("beta", C.c_double),
                 ("Gmin", C.c_double), ("q_min", C.c_double), ("q_max", C.c_double),
                 ("mcra_alpha_d", C.c_double), ("mcra_alpha_s", C.c_double), ("mcra_delta_s", C.c_double),
@@ -166,6 +166,10 @@ def _declare(lib):
     lib.ds_float_to_pcm16_run.argtypes = [C.c_size_t, vp, vp, vp]
     lib.ds_phat_run.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     lib.ds_srp_run.argtypes = [i32, i32, i32, i32, dbl, i32, vp, vp, vp, i32, vp]
+    lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ds_power_run.restype = C.c_int
+    lib.ds_spectral_gain_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ds_spectral_gain_run.restype = C.c_int
     lib.ds_mcspp_cdr_default_params.argtypes = [C.POINTER(McsppCdrParams), C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ds_mcspp_cdr_default_params.restype = None
     lib.ds_mcspp_cdr_state_bytes.argtypes = [C.POINTER(McsppCdrParams)]

@@ -15,7 +15,8 @@ import numpy as np
 
 from .. import _lib as L
 from ..transform.multirate import fractional_delay_filter_bank
-from ..transform.transform import _sqrt_hann
+from ..noise_estimation.omlsa_multi import NsOmlsaMulti
+from ..transform.transform import _sqrt_hann, stft_device, istft_device
 from .MicArray import MicArray
 
 
@@ -87,6 +88,7 @@ class FDGSC(object):
         self.mu_bm, self.mu_aic, self.alpha = 0.1, 0.1, 0.9
         self.phi, self.psi = None, None          # ccafbounds: computed by the reference ctor but never used
         self._state = None
+        self._pf = None
         self._S = None
         self.bm = None
         self.aic_filter = None
@@ -102,14 +104,54 @@ class FDGSC(object):
 
     def reset(self):
         self._state = None
+        self._pf = None
         self.spp.frm_cnt, self.spp.ell = 0, 1
+
+    def _postfilter(self, y_aic, fix_out, bm_out):
+        """postfilter=True exactly as FDGSC.py:283-295 behaves (all on the device):
+          * the beam spectrum comes from ``transform_fbf``, the Transform that :270 has just fed the delayed
+            fixed-beamformer block -> analysed frame n = window * [fixed_output_delayed_n | aic_output_n];
+          * ``transform_bm.stft(bm_output[:, :-1])`` sees the WHOLE output buffer every block and only its
+            frame 0 is used -> the reference powers are those of [tail of the previous call's buffer | block 0],
+            the same for every block of a call;
+          * gain sqrt(G) of NsOmlsaMulti (G = 1 on the very first frame), then transform_fbf.istft.
+        y_aic, fix_out [S, Nb] float32, bm_out [S, M, Nb] float32 -> [S, Nb] float32."""
+        t = L.require_cuda()
+        S, Nb = y_aic.shape
+        Lf, M, K = self.frameLen, self.M, self.frameLen + 1
+        nblk = Nb // Lf
+        win = L.device_window(_sqrt_hann(2 * Lf), 2 * Lf)
+        if getattr(self, "_pf", None) is None or self._pf["S"] != S:
+            self._pf = dict(S=S, fix_last=t.zeros((S, Lf), dtype=t.float32, device="cuda"),
+                            bm_hist=t.zeros((S, M - 1, Lf), dtype=t.float32, device="cuda"),
+                            tail=t.zeros((S, 1, Lf), dtype=t.float32, device="cuda"),
+                            omlsa=NsOmlsaMulti(nfft=2 * Lf, cal_weights=True, M=M))
+        pf = self._pf
+        # frames [fixed_output_delayed_n | aic_output_n]: a hop = n_fft transform of the interleaved blocks
+        fixdel = t.cat([pf["fix_last"], fix_out[:, :Nb - Lf]], dim=1)
+        pf["fix_last"] = fix_out[:, Nb - Lf:Nb].clone()
+        z = t.stack([fixdel.view(S, nblk, Lf), y_aic.view(S, nblk, Lf)], dim=2).reshape(S, 1, 2 * Nb).contiguous()
+        Y = stft_device(z, 2 * Lf, 2 * Lf, win, L.DS_STFT_PLAIN)                                    # [S, nblk, 1, K] c64
+        # reference powers: frame 0 of the buffer-wide transform
+        hist = pf["bm_hist"].clone()
+        U0 = stft_device(bm_out[:, :M - 1, :Lf].contiguous(), 2 * Lf, Lf, win, L.DS_STFT_STREAMING, history=hist)
+        pf["bm_hist"] = bm_out[:, :M - 1, Nb - Lf:Nb].contiguous()
+        Ypow = t.empty((S, nblk, K), dtype=t.float64, device="cuda")
+        Upow = t.empty((S, M - 1, K), dtype=t.float64, device="cuda")
+        L.check(L.lib().ds_power_run(Ypow.numel(), L.ptr(Y), 0, L.ptr(Ypow), L.stream_ptr()), "ds_power_run")
+        L.check(L.lib().ds_power_run(Upow.numel(), L.ptr(U0), 0, L.ptr(Upow), L.stream_ptr()), "ds_power_run")
+        G, _, _ = pf["omlsa"]._run(Ypow, Upow, u_const=True)
+        Yg = t.empty((S, nblk, 1, K), dtype=t.complex128, device="cuda")
+        L.check(L.lib().ds_spectral_gain_run(Ypow.numel(), L.ptr(Y), 0, L.ptr(G), 1, L.ptr(Yg), L.stream_ptr()),
+                "ds_spectral_gain_run")
+        out = istft_device(Yg, 2 * Lf, Lf, win, L.DS_STFT_STREAMING, tail=pf["tail"], scale=Lf / float(np.sum(_sqrt_hann(2 * Lf) ** 2)),
+                           fft_fp64=self.precision == "fp64")
+        return out[:, 0, :]
 
     def process(self, x, postfilter=False, dc_notch=True):
         """x [n_samples, n_chs] (or [S, n_samples, n_chs]) -> (output, p, fix_output, fix_output_delayed,
         bm_output, aligned_output, aligned_output_delayed, bm, aic_filter) like FDGSC.py:307-317.
         ``aligned_output`` / the delayed copies are diagnostics the kernel does not materialise (None)."""
-        if postfilter:
-            raise NotImplementedError("postfilter=True (NsOmlsaMulti inside FDGSC) is not part of this path yet")
         t = L.require_cuda()
         L.ensure_init()
         as_torch = isinstance(x, t.Tensor)
@@ -142,6 +184,10 @@ class FDGSC(object):
         f, e = C.c_int32(self.spp.frm_cnt), C.c_int32(self.spp.ell)
         L.lib().ds_mcra_advance(int(self.spp.L), nblk, C.byref(f), C.byref(e))
         self.spp.frm_cnt, self.spp.ell = f.value, e.value
+        if postfilter:
+            yrun = self._postfilter(yrun, fix_out, bm_out)
+            if Nb == N:
+                y = yrun
         if Nb != N:
             y[:, :Nb] = yrun
         # quirk 11: the caller's array now holds the DC-notched signal

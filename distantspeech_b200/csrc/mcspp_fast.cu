@@ -61,6 +61,16 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
     const float2 ynb0 = (k > 0) ? ld_f2_once(Xp - 1) : make_float2(0.f, 0.f);
     const float2 ynb1 = (k < K - 1) ? ld_f2_once(Xp + 1) : make_float2(0.f, 0.f);
     Xp += M * K;
+#ifndef DS_X_PREFETCH
+#define DS_X_PREFETCH 4
+#endif
+    // pull the spectrum of a later frame into L2 now: the loads above then hit L2 instead of
+    // HBM (the profile showed the float->double conversions of yf waiting on the long scoreboard)
+    if (DS_X_PREFETCH > 0 && t + DS_X_PREFETCH < a.T) {
+#pragma unroll
+      for (int m = 0; m < M; ++m)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(Xp + (long long)(DS_X_PREFETCH - 1) * M * K + m * K));
+    }
     const bool reset = (frm > 0) && (ell % a.mc.L == 0);
     *Yp = chain_bin_step<M, NT, true>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a);
     if (reset) ell = 0;

@@ -17,7 +17,8 @@ constexpr int PF_MAXM = 8;
 struct OmlsaArgs {
   double *state;       // [S][NE][K]
   const double *y;     // [S][T][K]      beamformer output power
-  const double *u;     // [S][T][M-1][K] reference (blocking matrix) powers
+  const double *u;     // [S][T][M-1][K] reference (blocking matrix) powers, or [S][M-1][K] when u_const
+  int u_const;
   double *G_out, *lam_out, *p_out;   // [S][T][K] or null
   int S, K, T, M, first_frame, frm_cnt, ell, cal_weights;
   double alpha_d, alpha_s, alpha_xi, beta, Gmin, q_min, q_max;
@@ -52,7 +53,7 @@ __global__ void omlsa_multi_kernel(OmlsaArgs a) {
     const double MU_Y = mc[0][4];
     double u0[PF_MAXM], um[PF_MAXM], up[PF_MAXM], MU_U[PF_MAXM];
     for (int c = 0; c < M - 1; ++c) {
-      const double *ut = a.u + (((long long)s * a.T + t) * (M - 1) + c) * K;
+      const double *ut = a.u + (((long long)s * (a.u_const ? 1 : a.T) + (a.u_const ? 0 : t)) * (M - 1) + c) * K;
       u0[c] = ut[k]; um[c] = (k > 0) ? ut[k - 1] : 0.0; up[c] = (k < K - 1) ? ut[k + 1] : 0.0;
       mcra_step(mc[c + 1][0], mc[c + 1][1], mc[c + 1][2], mc[c + 1][3], mc[c + 1][4], um[c], u0[c], up[c], k, K, frm, reset, a.mc);
       MU_U[c] = mc[c + 1][4];
@@ -154,7 +155,7 @@ extern "C" {
 void ds_omlsa_multi_default_params(ds_omlsa_multi_params *p, int n_bins, int n_streams, int n_frames, int n_mics) {
   if (!p) return;
   p->n_bins = n_bins; p->n_streams = n_streams; p->n_frames = n_frames; p->n_mics = n_mics;
-  p->first_frame = 1; p->frm_cnt = 0; p->ell = 1; p->mcra_L = 15; p->cal_weights = 0; p->reserved = 0;
+  p->first_frame = 1; p->frm_cnt = 0; p->ell = 1; p->mcra_L = 15; p->cal_weights = 0; p->u_const = 0;
   p->alpha_d = 0.85; p->alpha_s = 0.8; p->alpha_xi = 0.921; p->beta = 1.47; p->Gmin = pow(10.0, -12.0 / 10.0);
   p->q_min = 1e-6; p->q_max = 0.9999998;
   p->mcra_alpha_d = 0.95; p->mcra_alpha_s = 0.8; p->mcra_delta_s = 5.0; p->mcra_alpha_p = 0.2;
@@ -174,7 +175,7 @@ int ds_omlsa_multi_run(const ds_omlsa_multi_params *p, void *state, const double
   OmlsaArgs a;
   a.state = (double *)state; a.y = y; a.u = u; a.G_out = G_out; a.lam_out = lambda_out; a.p_out = p_out;
   a.S = p->n_streams; a.K = p->n_bins; a.T = p->n_frames; a.M = p->n_mics; a.first_frame = p->first_frame;
-  a.frm_cnt = p->frm_cnt; a.ell = p->ell; a.cal_weights = p->cal_weights;
+  a.frm_cnt = p->frm_cnt; a.ell = p->ell; a.cal_weights = p->cal_weights; a.u_const = p->u_const;
   a.alpha_d = p->alpha_d; a.alpha_s = p->alpha_s; a.alpha_xi = p->alpha_xi; a.beta = p->beta; a.Gmin = p->Gmin;
   a.q_min = p->q_min; a.q_max = p->q_max;
   a.mc.alpha_d = p->mcra_alpha_d; a.mc.alpha_s = p->mcra_alpha_s; a.mc.delta_s = p->mcra_delta_s;

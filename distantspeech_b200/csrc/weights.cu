@@ -4,6 +4,7 @@
 // Y = einsum('ij,ij->i', W.conj(), X)  (fixedbeamformer.py:163).
 // Arrays use the reference's own row-major layouts ([bins, M], [bins, M, M]).
 #include "common.cuh"
+#include "perbin.cuh"
 
 namespace ds {
 
@@ -136,6 +137,47 @@ extern "C" int ds_omlsa_gain_run(int n_rows, int n_bins, const double *xi, const
   DS_CHECK_ARG(n_rows >= 1 && n_bins >= 1, "ds_omlsa_gain_run: bad shape");
   const long long n = (long long)n_rows * n_bins;
   ds::omlsa_gain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, n_bins, xi, p, Gmin, G, G_H1);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
+// ---- spectral power / gain (FDGSC.py:288-294) -------------------------------------------
+namespace ds {
+template <typename C2>
+__global__ void power_kernel(long long n, const C2 *__restrict__ X, double *__restrict__ out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const C2 v = X[g];
+  out[g] = power_c((double)v.x, (double)v.y);
+}
+template <typename C2>
+__global__ void spectral_gain_kernel(long long n, const C2 *__restrict__ Yin, const double *__restrict__ G, int take_sqrt,
+                                     double2 *__restrict__ Yout) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const C2 v = Yin[g];
+  const double w = take_sqrt ? sqrt(G[g]) : G[g];
+  Yout[g] = make_double2((double)v.x * w, (double)v.y * w);
+}
+}  // namespace ds
+
+extern "C" int ds_power_run(long long n, const void *X, int x_is_c128, double *out, void *stream) {
+  DS_CHECK_ARG(X && out && n >= 1, "ds_power_run: bad argument");
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (x_is_c128) ds::power_kernel<double2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const double2 *)X, out);
+  else ds::power_kernel<float2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const float2 *)X, out);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
+extern "C" int ds_spectral_gain_run(long long n, const void *Yin, int y_is_c128, const double *G, int take_sqrt, void *Yout,
+                                    void *stream) {
+  DS_CHECK_ARG(Yin && G && Yout && n >= 1, "ds_spectral_gain_run: bad argument");
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (y_is_c128)
+    ds::spectral_gain_kernel<double2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const double2 *)Yin, G, take_sqrt, (double2 *)Yout);
+  else
+    ds::spectral_gain_kernel<float2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const float2 *)Yin, G, take_sqrt, (double2 *)Yout);
   DS_LAUNCH_CHECK();
   return DS_OK;
 }

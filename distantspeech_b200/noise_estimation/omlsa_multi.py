@@ -37,8 +37,9 @@ class NsOmlsaMulti(NoiseEstimationBase):
         p.q_min, p.q_max = float(self.q_min), float(self.q_max)
         return p
 
-    def _run(self, yd, ud):
-        """yd [S, T, K], ud [S, T, M-1, K] float64 CUDA -> (G, lambda_d, p) [S, T, K]."""
+    def _run(self, yd, ud, u_const=False):
+        """yd [S, T, K], ud [S, T, M-1, K] (u_const: [S, M-1, K], shared by all frames) float64 CUDA
+        -> (G, lambda_d, p) [S, T, K]."""
         t = L.require_cuda()
         S, T, K = yd.shape
         assert K == self.half_bin
@@ -54,6 +55,7 @@ class NsOmlsaMulti(NoiseEstimationBase):
             st[:, o + 6] = 1.0   # xi_hat
             self._S = S
         prm = self._params(S, T)
+        prm.u_const = int(bool(u_const))
         G = t.empty((S, T, K), dtype=t.float64, device="cuda")
         lam = t.empty_like(G)
         p = t.empty_like(G)

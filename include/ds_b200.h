@@ -147,6 +147,14 @@ int ds_pmwf_weight_run(int n_bins, int n_mics, const double *xi, const void *Rxx
 int ds_apply_weights_run(int n_streams, int n_frames, int n_mics, int n_bins, const void *X,
                          int x_is_c128, const void *W, void *Y, void *stream);
 
+/* |X|^2 the way the reference writes it, np.real(X * np.conj(X)) (FDGSC.py:288, GSC.py:286):
+ * re*re + im*im with each product rounded.  X: n complex values, c64 or c128; out: n float64.    */
+int ds_power_run(long long n, const void *X, int x_is_c128, double *out, void *stream);
+/* Y[i] * g[i] in complex128, g = G or sqrt(G) (FDGSC.py:292-294): spectral gain before Transform.istft.
+ * Yin c64 or c128 (n values), G float64, Yout c128 (may alias Yin when it is c128).              */
+int ds_spectral_gain_run(long long n, const void *Yin, int y_is_c128, const double *G, int take_sqrt,
+                         void *Yout, void *stream);
+
 /* replaces McSppBase.compute_omlsa_weight (mcspp_base.py:140-155):
  * G = clip((xi/(1+xi))^p Gmin^(1-p), Gmin, 1), G[:2] = 0 per row of n_bins.       */
 int ds_omlsa_gain_run(int n_rows, int n_bins, const double *xi, const double *p, double Gmin,
@@ -282,7 +290,8 @@ typedef struct ds_omlsa_multi_params {
   int32_t first_frame; /* 1 until the first frame has been seen (host-tracked) omlsa_multi.py:87 */
   int32_t frm_cnt, ell, mcra_L; /* shared by the M MCRA trackers (15)                */
   int32_t cal_weights; /* compute the OMLSA gain G                           :152   */
-  int32_t reserved;
+  int32_t u_const;     /* 1: u is [S][M-1][K], the same reference powers for every frame
+                          (what FDGSC.process(postfilter=True) feeds it, FDGSC.py:285-289) */
   double alpha_d, alpha_s, alpha_xi; /* 0.85, 0.8, 0.921                  :53,70,96 */
   double beta;                       /* 1.47                                   :149  */
   double Gmin, q_min, q_max;         /* 10^-1.2, 1e-6, 0.9999998            :35-50   */
@@ -291,7 +300,7 @@ typedef struct ds_omlsa_multi_params {
 void ds_omlsa_multi_default_params(ds_omlsa_multi_params *p, int n_bins, int n_streams, int n_frames, int n_mics);
 size_t ds_omlsa_multi_state_bytes(const ds_omlsa_multi_params *p);
 /* replaces NsOmlsaMulti.estimation (noise_estimation/omlsa_multi.py:73-156) over T frames.
- *   y [S][T][K] beam-output power, u [S][T][M-1][K] reference powers (float64)
+ *   y [S][T][K] beam-output power, u [S][T][M-1][K] (u_const: [S][M-1][K]) reference powers (float64)
  *   G_out / lambda_out / p_out [S][T][K] or NULL                                  */
 int ds_omlsa_multi_run(const ds_omlsa_multi_params *p, void *state, const double *y, const double *u,
                        double *G_out, double *lambda_out, double *p_out, void *stream);

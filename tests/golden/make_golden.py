@@ -131,6 +131,15 @@ def main():
          x_notched=xin.astype(np.float32), delay_filter=fd.time_alignment.delay_filter,
          W_aic_last=fd.aic_filter.W, W_bm0_last=fd.bm[0].W)
 
+    # ---- a17 with postfilter=True (two calls: the second sees the carried transform / OMLSA state) ----
+    with contextlib.redirect_stdout(io.StringIO()):
+        fdp = FDGSC(mic6, frameLen=256, angle=[60, 0])
+    xa, xb = x6[:256 * 40].astype(np.float64), x6[256 * 40:].astype(np.float64)
+    ya = fdp.process(xa, postfilter=True, dc_notch=True)[0]
+    yb = fdp.process(xb, postfilter=True, dc_notch=True)[0]
+    save("fdgsc_postfilter.npz", n_first=np.array(256 * 40), n_total=np.array(256 * 60), y=np.concatenate([ya, yb]),
+         G_last=fdp.omlsa_multi.G)
+
     # ---- a15: NsOmlsaMulti on the FDGSC outputs, a16: Zelinski postfilter weights -------
     from DistantSpeech.noise_estimation.omlsa_multi import NsOmlsaMulti
     from DistantSpeech.postfilter.postfilter import PostFilter

@@ -375,6 +375,26 @@ def test_fdgsc_golden(cuda, precision):
     assert rel < (1e-3 if precision == "fp32" else 1e-5), rel
 
 
+def test_fdgsc_postfilter_golden(cuda):
+    """postfilter=True reproduces the reference as written (hybrid analysis frames, buffer-wide reference
+    spectra, sqrt(G) gain), over two consecutive calls so the carried Transform / OMLSA state is covered."""
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.FDGSC import FDGSC
+    g, gp = golden("fdgsc.npz"), golden("fdgsc_postfilter.npz")
+    n1 = int(gp["n_first"])
+    mic = MicArray(arrayType="linear", r=0.05, M=6, n_fft=256)
+    fd = FDGSC(mic, frameLen=256, angle=[int(g["angle_deg"][0]), int(g["angle_deg"][1])])
+    ya = fd.process(g["x"][:n1].copy(), postfilter=True, dc_notch=True)[0]
+    yb = fd.process(g["x"][n1:].copy(), postfilter=True, dc_notch=True)[0]
+    err, s = assert_wave_parity(gp["y"], np.concatenate([ya, yb]), "FDGSC postfilter")
+    print("FDGSC postfilter: max-abs %.2e SNR %.1f dB" % (err, s))
+    # batch of two streams == singles; the postfiltered output differs from the plain one
+    xs = np.stack([g["x"][:n1], g["x"][:n1][::-1].copy()])
+    yb2 = FDGSC(mic, frameLen=256, angle=[60, 0]).process(xs.copy(), postfilter=True)[0]
+    assert np.max(np.abs(yb2[0] - ya)) < 1e-6
+    assert np.max(np.abs(ya - g["y"][:n1])) > 1e-3
+
+
 def test_fdgsc_streaming_batch_and_time_alignment(cuda):
     from distantspeech_b200.beamformer.MicArray import MicArray
     from distantspeech_b200.beamformer.FDGSC import FDGSC, TimeAlignment

@@ -19,6 +19,16 @@ def test_fdgsc_golden():
     assert np.allclose(o.aic.W, g["W_aic_last"], rtol=1e-6, atol=1e-9)
 
 
+def test_fdgsc_postfilter_golden():
+    g, gp = golden("fdgsc.npz"), golden("fdgsc_postfilter.npz")
+    n1 = int(gp["n_first"])
+    o = O.FdgscOracle(O.MicGeometry("linear", r=0.05, M=6, n_fft=256), 256, g["angle_deg"] / 180 * np.pi)
+    ya = o.process(g["x"][:n1].astype(np.float64), postfilter=True)[0]
+    yb = o.process(g["x"][n1:].astype(np.float64), postfilter=True)[0]
+    assert np.max(np.abs(np.concatenate([ya, yb]) - gp["y"])) < 1e-9
+    assert np.allclose(o.omlsa_multi.G, gp["G_last"], rtol=1e-9, atol=0)
+
+
 def test_omlsa_multi_golden():
     g = golden("omlsa_multi.npz")
     Y, U = g["Y"].astype(np.float64), g["U"].astype(np.float64)
