@@ -538,6 +538,17 @@ def test_pcm16_ingest_matches_load_audio(cuda):
     back = torch.empty(pcm.shape[0], dtype=torch.int16, device="cuda")
     L.check(L.lib().ds_float_to_pcm16_run(pcm.shape[0], L.ptr(out), L.ptr(back), L.stream_ptr()))
     assert np.array_equal(back.cpu().numpy(), (ref * np.iinfo(np.int16).max).astype(np.int16))   # :193
+    # load_audio / save_audio round trip through a wav file (utils.py:182-196)
+    import os
+    import tempfile
+    from distantspeech_b200.beamformer.utils import load_audio, save_audio
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "rt")
+        save_audio(path, ref[:4000].reshape(2000, 2), fs=16000)
+        got = load_audio(path + ".wav")
+    assert got.dtype == np.float32 and got.shape == (2000, 2)
+    q = (ref[:4000] * 32767).astype(np.int16)
+    assert np.array_equal(got.reshape(-1), q.astype(np.float32) / 32767.0)
     # int16 host buffers through the chain == float path on the dequantised signal
     geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
     xs = O.synth_streams(3, geo, 256 * 40, seed0=77)
