@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(SRP_NT) srp_simt_kernel(const float *__restric
   }
 }
 
-int srp_tc_launch(const float *tau, const float2 *Yhat, float *P, int D, int T, int M, int K, float two_f0, cudaStream_t st);
+int srp_tc_launch(const float *tau, const float2 *Yhat, void *workspace, float *P, int D, int T, int M, int K, float two_f0,
+                  cudaStream_t st);
+size_t srp_tc_workspace_bytes(int T, int M, int K);
 bool srp_tc_supported(int D, int T, int M, int K);
 
 }  // namespace ds
@@ -116,8 +118,13 @@ int ds_phat_run(int n_frames, int n_mics, int n_bins, int phat, const void *X, v
   return DS_OK;
 }
 
+size_t ds_srp_workspace_bytes(int n_frames, int n_mics, int n_bins, int use_tensor_cores) {
+  if (!use_tensor_cores || !srp_tc_supported(1, n_frames, n_mics, n_bins)) return 0;
+  return srp_tc_workspace_bytes(n_frames, n_mics, n_bins);
+}
+
 int ds_srp_run(int n_dirs, int n_frames, int n_mics, int n_bins, double fs, int n_fft, const float *tau, const void *Yhat,
-               float *P, int use_tensor_cores, void *stream) {
+               void *workspace, float *P, int use_tensor_cores, void *stream) {
   DS_CHECK_ARG(tau && Yhat && P, "ds_srp_run: null argument");
   DS_CHECK_ARG(n_dirs >= 1 && n_frames >= 1 && n_bins >= 1 && n_mics >= 1 && n_mics <= SRP_MMAX,
                "ds_srp_run: n_mics must be 1..%d", SRP_MMAX);
@@ -125,10 +132,11 @@ int ds_srp_run(int n_dirs, int n_frames, int n_mics, int n_bins, double fs, int 
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tensor_cores) {
     if (!srp_tc_supported(n_dirs, n_frames, n_mics, n_bins)) {
-      set_error("ds_srp_run: tensor-core path needs n_mics in {8, 16}");
+      set_error("ds_srp_run: tensor-core path needs n_mics in {4, 8, 16}");
       return DS_EUNSUPPORTED;
     }
-    return srp_tc_launch(tau, (const float2 *)Yhat, P, n_dirs, n_frames, n_mics, n_bins, two_f0, st);
+    DS_CHECK_ARG(workspace && (reinterpret_cast<size_t>(workspace) & 127) == 0, "ds_srp_run: the tensor-core path needs a 128-byte aligned workspace");
+    return srp_tc_launch(tau, (const float2 *)Yhat, workspace, P, n_dirs, n_frames, n_mics, n_bins, two_f0, st);
   }
   dim3 grid((n_dirs + SRP_DT - 1) / SRP_DT, (n_frames + SRP_TT - 1) / SRP_TT);
   srp_simt_kernel<<<grid, SRP_NT, 0, st>>>(tau, (const float2 *)Yhat, P, n_dirs, n_frames, n_mics, n_bins, two_f0);

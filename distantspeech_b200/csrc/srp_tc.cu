@@ -11,10 +11,17 @@
 // chip (it is never stored: D x K x M complex would be 4 GB) and the |.| + sum_k
 // epilogue out of tensor memory.  One CTA = 128 directions x 64 frames, looping over
 // all bins:
-//   warps 0-3   epilogue: tcgen05.ld the 128 x 128 fp32 accumulator, |z|, accumulate over bins
-//   warp  4     one elected thread issues tcgen05.mma (kind::tf32, M128 N128 K8, 2M/8 per bin)
-//   warps 5-12  producers: sincospi steering tile + spectrum tile into shared memory in
-//               the canonical no-swizzle K-major core-matrix layout, 3 stages
+//   warps 0-7   epilogue: tcgen05.ld the 128 x 128 fp32 accumulator, |z|, accumulate over bins
+//               (warp w reads TMEM lanes 32 (w % 4) .. +31 and the frame half w / 4; the epilogue is
+//               bound by the special-function unit -- one sqrt per (direction, frame, bin) -- so it
+//               gets two warps per scheduler to keep that unit fed across TMEM-load latency)
+//   warps 8-11  producers: steering tile generated on chip (phasor recurrence) into shared memory
+//               in the canonical no-swizzle K-major core-matrix layout, 3 stages
+//   warp  12    one elected thread issues tcgen05.mma (kind::tf32, M128 N128 K8, 2M/8 per bin)
+//   warp  13    one elected thread streams the spectrum tile of each bin into shared memory with
+//               cp.async.bulk (the tile was laid out and rounded to tf32 once by srp_pack_kernel)
+//   warps 14-15 idle (they complete the fourth warpgroup: setmaxnreg is a warpgroup-wide instruction)
+// Registers are rebalanced with setmaxnreg (launch 64: epilogue 72, producers 88, last warpgroup 24).
 // TMEM: 2 accumulator stages x 128 columns.  Synchronisation: mbarriers
 // (producer -> MMA -> producer, MMA -> epilogue -> MMA) with tcgen05.commit.
 #include "common.cuh"
@@ -25,9 +32,11 @@ namespace tc {
 
 constexpr int TILE_D = 128, TILE_T = 64, UMMA_N = 2 * TILE_T;
 constexpr int STAGES = 3, ACC_STAGES = 2;
-constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
+constexpr int EPI_WARPS = 8, PROD_WARPS = 4;
+constexpr int EPI_COLS = TILE_T / (EPI_WARPS / 4);      // frames per epilogue thread
 constexpr int RESYNC = 32;            // bins between exact re-evaluations of the steering phasors
-constexpr int NTHREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
+constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS, COPY_WARP = MMA_WARP + 1;
+constexpr int NTHREADS = (EPI_WARPS + PROD_WARPS + 4) * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,9 +119,41 @@ template <int ROWS> __device__ __forceinline__ int tile_off(int r, int c) {
   return (c >> 2) * (ROWS * 16) + (r >> 3) * 128 + (r & 7) * 16 + (c & 3) * 4;
 }
 
+// Spectrum tiles for the B operand, built once per call: for bin k and frame tile j the 128 x 2M tile
+//   row r < 64 : [ yr_m ... |  yi_m ... ] of frame 64 j + r          (-> Re Z)
+//   row 64 + r : [ yi_m ... | -yr_m ... ]                            (-> Im Z)
+// rounded to tf32 and stored in the canonical layout, so the contraction kernel moves it with one
+// bulk copy per bin.  One thread per 16-byte chunk.
+template <int MM>
+__global__ void srp_pack_kernel(const float2 *__restrict__ Yhat, unsigned char *__restrict__ Bp, int T, int K, int n_tiles) {
+  constexpr int KD = 2 * MM, CHUNKS = KD / 4;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)K * n_tiles * UMMA_N * CHUNKS;
+  if (g >= total) return;
+  const int q = (int)(g % CHUNKS);
+  const int r = (int)((g / CHUNKS) % UMMA_N);
+  const long long kt = g / ((long long)CHUNKS * UMMA_N);        // k * n_tiles + tile
+  const int tile = (int)(kt % n_tiles);
+  const int k = (int)(kt / n_tiles);
+  const bool im_row = r >= TILE_T;
+  const int t = tile * TILE_T + (im_row ? r - TILE_T : r);
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (t < T) {
+    const float2 *src = Yhat + ((size_t)k * T + t) * MM;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * q + e;
+      const float2 y = src[c < MM ? c : c - MM];
+      const float val = (c < MM) ? (im_row ? y.y : y.x) : (im_row ? -y.x : y.y);
+      v[e] = to_tf32(val);
+    }
+  }
+  *reinterpret_cast<float4 *>(Bp + (size_t)kt * (UMMA_N * KD * 4) + tile_off<UMMA_N>(r, 4 * q)) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 template <int MM>   // microphones
-__global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__restrict__ tau, const float2 *__restrict__ Yhat,
-                                                             float *__restrict__ P, int D, int T, int K, float two_f0) {
+__global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__restrict__ tau, const unsigned char *__restrict__ Bp,
+                                                             float *__restrict__ P, int D, int T, int K, float two_f0, int n_tiles) {
   constexpr int KD = 2 * MM;                      // contraction depth (fp32 / tf32 elements)
   constexpr int A_BYTES = TILE_D * KD * 4, B_BYTES = UMMA_N * KD * 4;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -133,11 +174,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
     tau_s[i] = (d < D) ? tau[(size_t)d * MM + (i % MM)] : 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PROD_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PROD_THREADS + 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == EPI_WARPS) {      // the MMA warp owns the TMEM allocation
+  if (warp == MMA_WARP) {      // the MMA warp owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(ACC_STAGES * UMMA_N));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -148,17 +189,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
 
   if (warp < EPI_WARPS) {
     // ===================== epilogue: |z| and sum over bins ==========================
-    float acc[TILE_T];
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+    float acc[EPI_COLS];
 #pragma unroll
-    for (int j = 0; j < TILE_T; ++j) acc[j] = 0.f;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     for (int k = 0; k < K; ++k) {
       const int as = k % ACC_STAGES;
       mbar_wait(&acc_full[as], (k / ACC_STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tcol = tmem_base + lane_addr + as * UMMA_N;
+      const uint32_t tcol = tmem_base + lane_addr + as * UMMA_N + half * EPI_COLS;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 0; h < EPI_COLS / 16; ++h) {
         uint32_t re[16], im[16];
         tmem_ld16(tcol + h * 16, re);
         tmem_ld16(tcol + TILE_T + h * 16, im);
@@ -166,27 +209,35 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float zr = __uint_as_float(re[j]), zi = __uint_as_float(im[j]);
-          const float zz = fmaf(zr, zr, zi * zi);
-          acc[h * 16 + j] = fmaf(zz, rsqrtf(fmaxf(zz, 1e-30f)), acc[h * 16 + j]);     // |z| = zz * rsqrt(zz)
+#ifdef SRP_DBG_EPI_LIGHT
+          acc[h * 16 + j] += zr + zi;
+#else
+          float mag;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(zr, zr, zi * zi)));
+          acc[h * 16 + j] += mag;
+#endif
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&acc_empty[as]);
     }
-    const int d = d0 + warp * 32 + lane;
+    const int d = d0 + quad * 32 + lane;
     if (d < D) {
-      float *out = P + (size_t)d * T + t0;
-      const bool vec = (t0 + TILE_T <= T) && ((reinterpret_cast<size_t>(out) & 15) == 0);
+      const int tb = t0 + half * EPI_COLS;
+      float *out = P + (size_t)d * T + tb;
+      const bool vec = (tb + EPI_COLS <= T) && ((reinterpret_cast<size_t>(out) & 15) == 0);
       if (vec) {
 #pragma unroll
-        for (int j = 0; j < TILE_T; j += 4) *reinterpret_cast<float4 *>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        for (int j = 0; j < EPI_COLS; j += 4) *reinterpret_cast<float4 *>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       } else {
 #pragma unroll
-        for (int j = 0; j < TILE_T; ++j)
-          if (t0 + j < T) out[j] = acc[j];
+        for (int j = 0; j < EPI_COLS; ++j)
+          if (tb + j < T) out[j] = acc[j];
       }
     }
-  } else if (warp == EPI_WARPS) {
+  } else if (warp >= MMA_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == MMA_WARP) {
     // ===================== MMA issuer ==================================================
     // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UMMA_N >> 3) << 17) | ((uint32_t)(TILE_D >> 4) << 24);
@@ -210,21 +261,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
       }
       __syncwarp();
     }
+    } else if (warp == COPY_WARP && lane == 0) {
+    // ===================== spectrum tiles: one bulk copy per bin ==============================
+      const unsigned char *src = Bp + (size_t)blockIdx.y * B_BYTES;
+      for (int k = 0; k < K; ++k) {
+        const int s = k % STAGES;
+        if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)B_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(tiles + s * STAGE_BYTES + A_BYTES)),
+                     "l"(src + (size_t)k * n_tiles * B_BYTES), "r"((uint32_t)B_BYTES), "r"(bar)
+                     : "memory");
+      }
+    }
   } else {
-    // ===================== producers ====================================================
+    // ===================== producers: steering tile ===========================================
     // Thread pt owns steering row pt (one direction, all MM mics): its phasors advance from bin to
     // bin by one complex rotation exp(-j 2 pi df tau) and are re-evaluated exactly every RESYNC bins.
-    // Threads 0..63 also write the "real" spectrum rows [yr | yi] of frame pt, threads 64..127 the
-    // "imaginary" rows [yi | -yr] of frame pt-64.  All shared-memory traffic is 16-byte vectors.
-    const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;     // 0 .. 127
+    // All shared-memory traffic is 16-byte vectors.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    const int pt = threadIdx.x - PROD_WARP0 * 32;          // 0 .. 127
     float cs[MM], sn[MM], rc[MM], rs[MM];
 #pragma unroll
     for (int m = 0; m < MM; ++m) sincospif(two_f0 * tau_s[pt * MM + m], &rs[m], &rc[m]);   // rotation per bin
     const int a_row = (pt >> 3) * 128 + (pt & 7) * 16;
-    const int tt = pt & (TILE_T - 1);
-    const bool im_row = pt >= TILE_T;
-    const int b_row = ((pt >> 3) * 128) + (pt & 7) * 16;   // row pt of the B tile (rows 64.. are the imaginary rows)
-    const bool t_ok = (t0 + tt) < T;
     for (int k = 0; k < K; ++k) {
       const int s = k % STAGES;
       if ((k % RESYNC) == 0) {
@@ -232,14 +293,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
 #pragma unroll
         for (int m = 0; m < MM; ++m) sincospif(fk2 * tau_s[pt * MM + m], &sn[m], &cs[m]);
       }
-      // spectrum row of this frame (global loads issued before the wait)
-      float4 yv[MM / 2];
-      const float4 *src = reinterpret_cast<const float4 *>(Yhat + ((size_t)k * T + t0 + tt) * MM);
-#pragma unroll
-      for (int i = 0; i < MM / 2; ++i) yv[i] = t_ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1);
       unsigned char *At = tiles + s * STAGE_BYTES;
-      unsigned char *Bt = At + A_BYTES;
       // steering row: [cos_0 .. cos_{M-1} | -sin_0 .. -sin_{M-1}]   (a = cos - j sin)
 #pragma unroll
       for (int q = 0; q < MM / 4; ++q) {
@@ -248,46 +303,39 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
         *reinterpret_cast<float4 *>(At + (MM / 4 + q) * (TILE_D * 16) + a_row) =
             make_float4(-to_tf32(sn[4 * q]), -to_tf32(sn[4 * q + 1]), -to_tf32(sn[4 * q + 2]), -to_tf32(sn[4 * q + 3]));
       }
-      // spectrum row: yv[i] = (re_{2i}, im_{2i}, re_{2i+1}, im_{2i+1})
-#pragma unroll
-      for (int q = 0; q < MM / 4; ++q) {
-        const float4 u = yv[2 * q], v = yv[2 * q + 1];
-        const float4 re4 = make_float4(to_tf32(u.x), to_tf32(u.z), to_tf32(v.x), to_tf32(v.z));
-        const float4 im4 = make_float4(to_tf32(u.y), to_tf32(u.w), to_tf32(v.y), to_tf32(v.w));
-        if (!im_row) {
-          *reinterpret_cast<float4 *>(Bt + q * (UMMA_N * 16) + b_row) = re4;
-          *reinterpret_cast<float4 *>(Bt + (MM / 4 + q) * (UMMA_N * 16) + b_row) = im4;
-        } else {
-          *reinterpret_cast<float4 *>(Bt + q * (UMMA_N * 16) + b_row) = im4;
-          *reinterpret_cast<float4 *>(Bt + (MM / 4 + q) * (UMMA_N * 16) + b_row) = make_float4(-re4.x, -re4.y, -re4.z, -re4.w);
-        }
-      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (tensor core)
       mbar_arrive(&full_bar[s]);
       // advance the phasors to the next bin
+#ifndef SRP_DBG_PROD_LIGHT
 #pragma unroll
       for (int m = 0; m < MM; ++m) {
         const float c = cs[m], sv = sn[m];
         cs[m] = fmaf(c, rc[m], -sv * rs[m]);
         sn[m] = fmaf(sv, rc[m], c * rs[m]);
       }
+#endif
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == EPI_WARPS) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ACC_STAGES * UMMA_N));
   }
 }
 
-template <int MM> static int launch(const float *tau, const float2 *Yhat, float *P, int D, int T, int K, float two_f0, cudaStream_t st) {
+template <int MM> static int launch(const float *tau, const float2 *Yhat, unsigned char *Bp, float *P, int D, int T, int K,
+                                    float two_f0, cudaStream_t st) {
   constexpr int KD = 2 * MM;
+  const int n_tiles = (T + TILE_T - 1) / TILE_T;
+  const long long chunks = (long long)K * n_tiles * UMMA_N * (KD / 4);
+  srp_pack_kernel<MM><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(Yhat, Bp, T, K, n_tiles);
+  DS_LAUNCH_CHECK();
   const size_t smem = (size_t)STAGES * (TILE_D + UMMA_N) * KD * 4 + (2 * STAGES + 2 * ACC_STAGES) * 8 + 16 + (size_t)TILE_D * MM * 4 + 128;
   auto kern = srp_tc_kernel<MM>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((D + TILE_D - 1) / TILE_D, (T + TILE_T - 1) / TILE_T);
-  kern<<<grid, NTHREADS, smem, st>>>(tau, Yhat, P, D, T, K, two_f0);
+  dim3 grid((D + TILE_D - 1) / TILE_D, n_tiles);
+  kern<<<grid, NTHREADS, smem, st>>>(tau, Bp, P, D, T, K, two_f0, n_tiles);
   DS_LAUNCH_CHECK();
   return DS_OK;
 }
@@ -296,11 +344,17 @@ template <int MM> static int launch(const float *tau, const float2 *Yhat, float 
 
 bool srp_tc_supported(int D, int T, int M, int K) { return (M == 4 || M == 8 || M == 16) && D >= 1 && T >= 1 && K >= 1; }
 
-int srp_tc_launch(const float *tau, const float2 *Yhat, float *P, int D, int T, int M, int K, float two_f0, cudaStream_t st) {
+size_t srp_tc_workspace_bytes(int T, int M, int K) {
+  return (size_t)K * ((T + tc::TILE_T - 1) / tc::TILE_T) * tc::UMMA_N * 2 * M * 4;
+}
+
+int srp_tc_launch(const float *tau, const float2 *Yhat, void *workspace, float *P, int D, int T, int M, int K, float two_f0,
+                  cudaStream_t st) {
+  unsigned char *Bp = (unsigned char *)workspace;
   switch (M) {
-    case 4: return tc::launch<4>(tau, Yhat, P, D, T, K, two_f0, st);
-    case 8: return tc::launch<8>(tau, Yhat, P, D, T, K, two_f0, st);
-    case 16: return tc::launch<16>(tau, Yhat, P, D, T, K, two_f0, st);
+    case 4: return tc::launch<4>(tau, Yhat, Bp, P, D, T, K, two_f0, st);
+    case 8: return tc::launch<8>(tau, Yhat, Bp, P, D, T, K, two_f0, st);
+    case 16: return tc::launch<16>(tau, Yhat, Bp, P, D, T, K, two_f0, st);
   }
   set_error("srp tensor-core path: unsupported microphone count %d", M);
   return DS_EUNSUPPORTED;

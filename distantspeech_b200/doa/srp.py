@@ -48,8 +48,10 @@ class srp(object):
         tau_d = t.as_tensor(np.ascontiguousarray(tau, dtype=np.float32)).to("cuda")
         P = t.empty((D, T), dtype=t.float32, device="cuda")
         use_tc = int(self.engine == "tensor" and M in (4, 8, 16))
+        nws = L.lib().ds_srp_workspace_bytes(T, M, K, use_tc)
+        ws = t.empty(max(nws, 1), dtype=t.uint8, device="cuda") if nws else None      # torch allocations are 512-byte aligned
         L.check(L.lib().ds_srp_run(D, T, M, K, float(self.mic_array.fs), int(self.mic_array.n_fft), L.ptr(tau_d),
-                                   L.ptr(Yhat), L.ptr(P), use_tc, L.stream_ptr()), "ds_srp_run")
+                                   L.ptr(Yhat), L.ptr(ws), L.ptr(P), use_tc, L.stream_ptr()), "ds_srp_run")
         return P
 
     def _mcra_p(self, X):

@@ -399,9 +399,12 @@ int ds_phat_run(int n_frames, int n_mics, int n_bins, int phat, const void *X, v
 /* replaces the direction x frame loops of srp.compute_angle_spectrum (srp.py:45-51):
  *   P[d, t] = sum_k | sum_m conj(a[d,k,m]) Yhat[k,t,m] |,  a = exp(-j 2 pi f_k tau[d,m]),  f_k = k fs / n_fft
  *   tau [D][M] float32 (MicArray.compute_tau per direction), P [D][T] float32
- *   use_tensor_cores = 1: tcgen05 (tf32) path, n_mics in {4, 8, 16}; 0: CUDA-core path, n_mics <= 16 */
+ *   use_tensor_cores = 1: tcgen05 (tf32) path, n_mics in {4, 8, 16}; 0: CUDA-core path, n_mics <= 16
+ *   workspace: ds_srp_workspace_bytes() bytes, 128-byte aligned (tensor path: the spectrum re-tiled and
+ *   rounded to tf32 once per call; may be NULL for the CUDA-core path)                              */
+size_t ds_srp_workspace_bytes(int n_frames, int n_mics, int n_bins, int use_tensor_cores);
 int ds_srp_run(int n_dirs, int n_frames, int n_mics, int n_bins, double fs, int n_fft, const float *tau,
-               const void *Yhat, float *P, int use_tensor_cores, void *stream);
+               const void *Yhat, void *workspace, float *P, int use_tensor_cores, void *stream);
 
 /* ---- config-4 chain: STFT -> McSppBase -> MVDR -> OMLSA -> ISTFT ------- */
 typedef struct ds_chain_params {
