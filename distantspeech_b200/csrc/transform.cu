@@ -247,6 +247,81 @@ __global__ void __launch_bounds__(ISTFT_WARPS * 32) istft_kernel(IstftArgs a, co
   }
 }
 
+// hop = N/2 fast path: one warp walks a run of consecutive hop-blocks of one (stream, channel), keeping the
+// second half of the previous frame in shared memory -- every frame is inverse-transformed once (plus one
+// halo frame per run), there is no CTA-wide synchronisation, and output rows are written as they complete.
+// Same arithmetic and float32 accumulation order as istft_kernel: acc = (0 + f[b-1]) + f[b] (+ tail).
+constexpr int ISEQ_WARPS = 8;
+
+template <int N, typename T>
+__global__ void __launch_bounds__(ISEQ_WARPS * 32) istft_seq_kernel(IstftArgs a, const typename V2<T>::type *__restrict__ tw_h_g,
+                                                                   const typename V2<T>::type *__restrict__ tw_n_g, int G, int nseg) {
+  typedef typename V2<T>::type C2;
+  constexpr int H = N / 2, K = H + 1, BE = fft_buf_elems(N), HOP = N / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *wind = reinterpret_cast<double *>(smem_raw);                    // [N]
+  C2 *tw_h = reinterpret_cast<C2 *>(wind + N);                            // [H]
+  C2 *tw_n = tw_h + H;                                                    // [H/2 + 1] (+1 pad)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  C2 *buf = tw_n + H / 2 + 2 + warp * BE;
+  float *prev = reinterpret_cast<float *>(tw_n + H / 2 + 2 + ISEQ_WARPS * BE) + warp * HOP;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) wind[i] = a.window[i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) tw_h[i] = tw_h_g[i];
+  for (int i = threadIdx.x; i <= H / 2; i += blockDim.x) tw_n[i] = tw_n_g[i];
+  __syncthreads();
+  const long long w = (long long)blockIdx.x * ISEQ_WARPS + warp;
+  if (w >= (long long)a.S * a.C * nseg) return;
+  const int sc = (int)(w / nseg), seg = (int)(w % nseg);
+  const int s = sc / a.C, c = sc % a.C;
+  const int nblk = (a.n_out + HOP - 1) / HOP;
+  const int b0 = seg * G, b1 = min(b0 + G, nblk);
+  const T *fb = reinterpret_cast<const T *>(buf);
+  const T inv_n = (T)1 / (T)N;
+  float *ys = a.y + (long long)sc * a.n_out;
+  const bool streaming = a.mode == DS_STFT_STREAMING;
+
+  auto inverse = [&](int t) {          // frame t -> buf holds irfft * N
+    const long long ibase = (((long long)s * a.T + t) * a.C + c) * K;
+    if (a.in_c128) {
+      const double2 *in = reinterpret_cast<const double2 *>(a.Y) + ibase;
+      for (int k = lane; k < K; k += 32) { const double2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
+    } else {
+      const float2 *in = reinterpret_cast<const float2 *>(a.Y) + ibase;
+      for (int k = lane; k < K; k += 32) { const float2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
+    }
+    __syncwarp();
+    warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
+  };
+  auto sample = [&](int n) -> float {  // windowed sample n of the frame in buf      (:368)
+    const T v = fb[2 * FPAD<T>(n >> 1) + (n & 1)] * inv_n;
+    return (float)((double)v * wind[n]);
+  };
+
+  if (b0 >= 1) {                       // halo: second half of frame b0-1
+    inverse(b0 - 1);
+    for (int j = lane; j < HOP; j += 32) prev[j] = sample(HOP + j);
+    __syncwarp();
+  }
+  for (int b = b0; b < b1; ++b) {
+    if (b < a.T) inverse(b);
+    for (int j = lane; j < HOP; j += 32) {
+      const int g = b * HOP + j;
+      float acc = 0.0f;
+      if (b >= 1) acc = acc + prev[j];
+      if (b < a.T) { acc = acc + sample(j); prev[j] = sample(HOP + j); }
+      if (g < a.n_out) {
+        if (streaming) {
+          if (b == 0) acc = acc + a.tail[(long long)sc * HOP + j];           // x[:overlap] += previous_output (:476)
+          ys[g] = (float)((double)acc * a.scale);                           // :479
+        } else {
+          ys[g] = acc;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int N, typename T>
 static int launch_istft(const IstftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
   const int R = (N + a.hop - 1) / a.hop;
@@ -256,10 +331,29 @@ static int launch_istft(const IstftArgs &a, const TwiddleSet &tw, cudaStream_t s
   auto kern = istft_kernel<N, T>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = (a.n_out + a.hop - 1) / a.hop;
-  dim3 grid((nblk + ISTFT_TILE - 1) / ISTFT_TILE, a.S * a.C);
-  if (grid.x > 0 && grid.y > 0) {
-    kern<<<grid, ISTFT_WARPS * 32, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw), R, 0);
+  if (a.hop * 2 == N && (a.mode != DS_STFT_STREAMING || a.tail)) {
+    // one warp per run of G hop-blocks; enough runs to fill the machine twice over
+    typedef typename V2<T>::type C2;
+    const long long seqs = (long long)a.S * a.C;
+    long long nseg = (2LL * 148 * 32 + seqs - 1) / seqs;
+    const long long max_seg = (nblk + 7) / 8;
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+    const int G = (int)((nblk + nseg - 1) / nseg);
+    nseg = (nblk + G - 1) / G;
+    const size_t smem2 = (size_t)N * sizeof(double) + (size_t)(N / 2 + N / 4 + 2) * sizeof(C2) +
+                         (size_t)ISEQ_WARPS * (fft_buf_elems(N) * sizeof(C2) + (N / 2) * sizeof(float));
+    auto kseq = istft_seq_kernel<N, T>;
+    DS_CUDA(cudaFuncSetAttribute(kseq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const long long warps = seqs * nseg;
+    kseq<<<(unsigned)((warps + ISEQ_WARPS - 1) / ISEQ_WARPS), ISEQ_WARPS * 32, smem2, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw), G, (int)nseg);
     DS_LAUNCH_CHECK();
+  } else {
+    dim3 grid((nblk + ISTFT_TILE - 1) / ISTFT_TILE, a.S * a.C);
+    if (grid.x > 0 && grid.y > 0) {
+      kern<<<grid, ISTFT_WARPS * 32, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw), R, 0);
+      DS_LAUNCH_CHECK();
+    }
   }
   if (a.mode == DS_STFT_STREAMING && a.tail && N > a.hop) {
     dim3 g2(1, a.S * a.C);
