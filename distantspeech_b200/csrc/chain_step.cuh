@@ -118,22 +118,29 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
     const double den = (den4[0] + den4[1]) + (den4[2] + den4[3]);
     double Yr = 0.0, Yi = 0.0, Yr2 = 0.0, Yi2 = 0.0;   // numerator (A a)^H y = a^H u, accumulated below from u = A y
 
-    // ---- P4: Phi_yy update, Xr = Re(Phi_yy - Phi_vv), xi = tr(A Xr), real half of gamma   :84-90,274-284
+    // ---- P4: u = A y, Phi_yy update, Xr = Re(Phi_yy - Phi_vv), xi = tr(A Xr), gamma = Re(u^H Xr u)   :84-90,274-284
+    // gamma runs on the packed triangle as sum_ij Xr_ij Z_ij with Z_ij = Re(conj(u_i) u_j): one product
+    // pair per element instead of one quadratic form per real / imaginary half.
     const double alpha = a.alpha, one_m_alpha = 1.0 - a.alpha;
     double trd[2] = {0.0, 0.0}, tro[4] = {0.0, 0.0, 0.0, 0.0}, gmd[2] = {0.0, 0.0}, gmo[4] = {0.0, 0.0, 0.0, 0.0};
     {
-      double ur[M];
+      double ur[M], ui[M];
 #pragma unroll
       for (int i = 0; i < M; ++i) {
-        double sr = 0.0, sr2 = 0.0;
+        double sr = 0.0, sr2 = 0.0, si = 0.0, si2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < M; ++j) { if (j & 1) sr2 = fma(AS(i, j), yr[j], sr2); else sr = fma(AS(i, j), yr[j], sr); }
+        for (int j = 0; j < M; ++j) {
+          if (j & 1) { sr2 = fma(AS(i, j), yr[j], sr2); si2 = fma(AS(i, j), yi[j], si2); }
+          else { sr = fma(AS(i, j), yr[j], sr); si = fma(AS(i, j), yi[j], si); }
+        }
         ur[i] = sr + sr2;
+        ui[i] = si + si2;
       }
 #pragma unroll
-      for (int m = 0; m < M; ++m) {          // conj(a) * u, real half of u
-        Yr = fma(ld_f64_once(a0 + 2 * m * K), ur[m], Yr);
-        Yi = fma(-ld_f64_once(a0 + 2 * m * K + 1), ur[m], Yi);
+      for (int m = 0; m < M; ++m) {          // numerator a^H u
+        const double ar = ld_f64_once(a0 + 2 * m * K), ai = ld_f64_once(a0 + 2 * m * K + 1);
+        Yr = fma(ar, ur[m], Yr);   Yi = fma(-ai, ur[m], Yi);
+        Yr2 = fma(ai, ui[m], Yr2); Yi2 = fma(ar, ui[m], Yi2);
       }
       // every product chain starts at the shared-memory operand, so nothing can be
       // pre-computed (and spilled) ahead of the loads by the instruction scheduler
@@ -146,34 +153,9 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
           const double pyy = fma(tr_i, yr[j], fma(ti_i, yi[j], alpha * smy[e * NT]));
           smy[e * NT] = pyy;
           const double x = pyy - smv[e * NT];
-          if (i == j) { trd[i & 1] = fma(A[e], x, trd[i & 1]); gmd[i & 1] = fma(x * ur[i], ur[j], gmd[i & 1]); }
-          else { tro[e & 3] = fma(A[e], x, tro[e & 3]); gmo[e & 3] = fma(x * ur[i], ur[j], gmo[e & 3]); }
-        }
-      }
-    }
-    // ---- P5: imaginary half of gamma = Re(u^H Xr u), u = A y
-    {
-      double ui[M];
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        double si = 0.0, si2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) { if (j & 1) si2 = fma(AS(i, j), yi[j], si2); else si = fma(AS(i, j), yi[j], si); }
-        ui[i] = si + si2;
-      }
-#pragma unroll
-      for (int m = 0; m < M; ++m) {          // conj(a) * u, imaginary half of u
-        Yr2 = fma(ld_f64_once(a0 + 2 * m * K + 1), ui[m], Yr2);
-        Yi2 = fma(ld_f64_once(a0 + 2 * m * K), ui[m], Yi2);
-      }
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-#pragma unroll
-        for (int j = i; j < M; ++j) {
-          const int e = pidx<M>(i, j);
-          const double x = smy[e * NT] - smv[e * NT];
-          if (i == j) gmd[i & 1] = fma(x * ui[i], ui[j], gmd[i & 1]);
-          else gmo[e & 3] = fma(x * ui[i], ui[j], gmo[e & 3]);
+          const double z = fma(ui[i], ui[j], ur[i] * ur[j]);
+          if (i == j) { trd[i & 1] = fma(A[e], x, trd[i & 1]); gmd[i & 1] = fma(x, z, gmd[i & 1]); }
+          else { tro[e & 3] = fma(A[e], x, tro[e & 3]); gmo[e & 3] = fma(x, z, gmo[e & 3]); }
         }
       }
     }
