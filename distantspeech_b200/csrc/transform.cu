@@ -559,6 +559,176 @@ __global__ void __launch_bounds__(FBF_WARPS * 32, 3) fixedbf_kernel(FixedBfArgs 
   }
 }
 
+// hop = N/2, up to 3 beams: one warp owns a run of consecutive frames of one stream and does everything
+// for them -- M analysis FFTs whose real-FFT split feeds the weight sums held in registers (each lane owns
+// the bin pairs (k, H-k), k = lane + 32 i), one inverse FFT per beam, overlap-add against the previous
+// half-frame kept in shared memory.  No CTA-wide synchronisation, the spectrum exists only in registers.
+// Same arithmetic as fixedbf_kernel.
+constexpr int FSEQ_WARPS = 8;
+
+template <int N, int NB>
+__global__ void __launch_bounds__(FSEQ_WARPS * 32, NB == 1 ? 4 : 2) fixedbf_seq_kernel(FixedBfArgs a, const float2 *__restrict__ tw_h_g,
+                                                                     const float2 *__restrict__ tw_n_g, int G, int nseg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = N / 2, K = H + 1, HOP = N / 2, BE = fft_buf_elems(N);
+  constexpr int NPAIR = (H / 2) / 32 + 1;        // pair slots per lane: kk = lane + 32 i <= H/2
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  float *win = reinterpret_cast<float *>(smem_raw);                 // [N]
+  float2 *tw_h = reinterpret_cast<float2 *>(win + N);               // [H]
+  float2 *tw_n = tw_h + H;                                          // [H/2 + 1] (+1 pad)
+  float2 *buf = tw_n + H / 2 + 2 + (size_t)warp * BE;
+  float *prev = reinterpret_cast<float *>(tw_n + H / 2 + 2 + (size_t)FSEQ_WARPS * BE) + (size_t)warp * NB * HOP;
+  float2 *Ws = reinterpret_cast<float2 *>(reinterpret_cast<float *>(tw_n + H / 2 + 2 + (size_t)FSEQ_WARPS * BE) +
+                                          (size_t)FSEQ_WARPS * NB * HOP);       // [NB][M][K]: weights, bin index innermost
+  for (int i = tid; i < H; i += blockDim.x) tw_h[i] = tw_h_g[i];
+  for (int i = tid; i <= H / 2; i += blockDim.x) tw_n[i] = tw_n_g[i];
+  for (int n = tid; n < N; n += blockDim.x) win[n] = (float)a.window[n];
+  for (int i = tid; i < NB * K * a.M; i += blockDim.x) {              // a.W is [NB][K][M]
+    const int m = i % a.M, k = (i / a.M) % K, b = i / (a.M * K);
+    Ws[((size_t)b * a.M + m) * K + k] = a.W[i];
+  }
+  __syncthreads();
+  const long long w = (long long)blockIdx.x * FSEQ_WARPS + warp;
+  if (w >= (long long)a.S * nseg) return;
+  const int s = (int)(w / nseg), seg = (int)(w % nseg);
+  const int t0 = seg * G, t1 = min(a.T, t0 + G);
+  const int parity = *reinterpret_cast<const int *>(a.state);
+  const size_t half = fbf_half_bytes(a.S, a.M, a.B, HOP);
+  const float *hist_in = reinterpret_cast<const float *>(a.state + 16 + (size_t)parity * half);
+  const float *tail_in = hist_in + (size_t)a.S * a.M * HOP;
+  float *hist_out = reinterpret_cast<float *>(a.state + 16 + (size_t)(1 - parity) * half);
+  float *tail_out = hist_out + (size_t)a.S * a.M * HOP;
+  const float inv_n = 1.0f / (float)N;
+  float *fb = reinterpret_cast<float *>(buf);
+
+  if (t0 == 0) {
+    for (int i = lane; i < NB * HOP; i += 32) prev[i] = tail_in[(long long)s * NB * HOP + i];   // x[:overlap] += previous_output
+    __syncwarp();
+  }
+  for (int t = (t0 > 0 ? t0 - 1 : 0); t < t1; ++t) {
+    float2 y1[NB][NPAIR], y2[NB][NPAIR];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int i = 0; i < NPAIR; ++i) { y1[b][i] = make_float2(0.f, 0.f); y2[b][i] = make_float2(0.f, 0.f); }
+    const int g0 = t * HOP - HOP;
+    for (int m = 0; m < a.M; ++m) {
+      const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
+      if (g0 >= 0 && ((reinterpret_cast<size_t>(xs + g0) & 7) == 0)) {
+        typedef FftFirst<H, float> F1;
+        float2 v[F1::PER][F1::R];
+        const float2 *src = reinterpret_cast<const float2 *>(xs + g0);
+        const float2 *w2 = reinterpret_cast<const float2 *>(win);
+#pragma unroll
+        for (int i = 0; i < F1::PER; ++i) {
+          const int j = lane + 32 * i;
+          if (F1::NB % 32 == 0 || j < F1::NB) {
+#pragma unroll
+            for (int r = 0; r < F1::R; ++r) {
+              const int e = j + r * F1::NB;
+              const float2 xv = __ldg(src + e);
+              const float2 wv = w2[e];
+              v[i][r] = make_float2(mul_rn(xv.x, wv.x), mul_rn(xv.y, wv.y));
+            }
+          }
+        }
+        F1::run(v, buf, tw_h, lane);
+      } else {
+        const float *hs = hist_in + ((long long)s * a.M + m) * HOP;
+        for (int n = lane; n < N; n += 32) {
+          const int g = g0 + n;
+          const float v = (g < 0) ? hs[HOP + g] : xs[g];
+          fb[2 * FPAD<float>(n >> 1) + (n & 1)] = v * win[n];
+        }
+        __syncwarp();
+        warp_cfft<H, float>(buf, tw_h, lane);
+      }
+      // real-FFT split fused with the weight sums: Y_b[k] += conj(W[b,k,m]) X_m[k]
+#pragma unroll
+      for (int i = 0; i < NPAIR; ++i) {
+        const int kk = lane + 32 * i;
+        if (kk <= H / 2) {
+          const float2 za = buf[FPAD<float>(kk)];
+          const float2 zb = buf[FPAD<float>((H - kk) & (H - 1))];
+          float x1r, x1i, x2r, x2i;
+          if (kk == 0) {
+            x1r = za.x + za.y; x1i = 0.f; x2r = za.x - za.y; x2i = 0.f;
+          } else {
+            const float2 wn = tw_n[kk];
+            const float sx = 0.5f * (za.x + zb.x), sy = 0.5f * (za.y - zb.y);
+            const float dx = 0.5f * (za.x - zb.x), dy = 0.5f * (za.y + zb.y);
+            const float px = wn.x * dx - wn.y * dy, py = wn.x * dy + wn.y * dx;
+            x1r = sx + py; x1i = sy - px;          // s/2 - e, e = (-py, px)
+            x2r = sx - py; x2i = -(sy + px);       // conj(s/2 + e)
+          }
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const float2 wa = Ws[((size_t)b * a.M + m) * K + kk];
+            const float2 wb = Ws[((size_t)b * a.M + m) * K + (H - kk)];
+            y1[b][i].x += wa.x * x1r + wa.y * x1i; y1[b][i].y += wa.x * x1i - wa.y * x1r;
+            y2[b][i].x += wb.x * x2r + wb.y * x2i; y2[b][i].y += wb.x * x2i - wb.y * x2r;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // synthesis of every beam, overlap-add with the previous half-frame
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+      for (int i = 0; i < NPAIR; ++i) {
+        const int kk = lane + 32 * i;
+        if (kk <= H / 2) { buf[FPAD<float>(kk)] = y1[b][i]; buf[FPAD<float>(H - kk)] = y2[b][i]; }
+      }
+      __syncwarp();
+      warp_irfft_unscaled<N, float>(buf, tw_h, tw_n, lane);
+      float *pv = prev + b * HOP;
+      float *ys = a.y + ((long long)s * NB + b) * a.Ns;
+      for (int j = lane; j < HOP; j += 32) {
+        const float c0 = fb[2 * FPAD<float>(j >> 1) + (j & 1)] * inv_n * win[j];
+        const float c1 = fb[2 * FPAD<float>((HOP + j) >> 1) + (j & 1)] * inv_n * win[HOP + j];
+        if (t >= t0) {
+          const float v = (t > 0) ? pv[j] + c0 : c0 + pv[j];      // (0 + f[t-1]) + f[t];  t = 0: f[0] + previous_output
+          ys[(long long)t * HOP + j] = (float)((double)v * a.scale);
+        }
+        pv[j] = c1;
+      }
+      __syncwarp();
+    }
+  }
+  // ---- new state (last run of each stream) ----------------------------------------
+  if (t1 == a.T) {
+    for (int i = lane; i < NB * HOP; i += 32) tail_out[(long long)s * NB * HOP + i] = prev[i];
+    for (int i = lane; i < a.M * HOP; i += 32) {
+      const int m = i / HOP, j = i - m * HOP;
+      const int g = a.Ns + j;  // index into concat(history, x)
+      const float *hs = hist_in + ((long long)s * a.M + m) * HOP;
+      const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
+      hist_out[((long long)s * a.M + m) * HOP + j] = (g < HOP) ? hs[g] : xs[g - HOP];
+    }
+  }
+}
+
+template <int N, int NB>
+static int launch_fixedbf_seq(const FixedBfArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+  long long nseg = (2LL * 148 * 24 + a.S - 1) / a.S;
+  const long long max_seg = a.T / 16 > 0 ? a.T / 16 : 1;
+  if (nseg > max_seg) nseg = max_seg;
+  if (nseg < 1) nseg = 1;
+  const int G = (int)((a.T + nseg - 1) / nseg);
+  nseg = (a.T + G - 1) / G;
+  const size_t smem = (size_t)N * sizeof(float) + (size_t)(N / 2 + N / 4 + 2) * sizeof(float2) +
+                      (size_t)FSEQ_WARPS * (fft_buf_elems(N) * sizeof(float2) + (size_t)NB * (N / 2) * sizeof(float)) +
+                      (size_t)NB * a.M * (N / 2 + 1) * sizeof(float2);
+  if (smem > 227 * 1024) return DS_EUNSUPPORTED;
+  auto kern = fixedbf_seq_kernel<N, NB>;
+  DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long warps = (long long)a.S * nseg;
+  kern<<<(unsigned)((warps + FSEQ_WARPS - 1) / FSEQ_WARPS), FSEQ_WARPS * 32, smem, st>>>(a, tw.h32, tw.n32, G, (int)nseg);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
 __global__ void flip_parity_kernel(unsigned char *state) {
   int *p = reinterpret_cast<int *>(state);
   *p = 1 - *p;
@@ -567,6 +737,17 @@ __global__ void flip_parity_kernel(unsigned char *state) {
 template <int N>
 static int launch_fixedbf(const FixedBfArgs &a0, const TwiddleSet &tw, cudaStream_t st) {
   FixedBfArgs a = a0;
+  if constexpr (N <= 512) {
+    if (a.hop * 2 == N && a.B <= 3) {
+      int rc = a.B == 1 ? launch_fixedbf_seq<N, 1>(a, tw, st) : a.B == 2 ? launch_fixedbf_seq<N, 2>(a, tw, st) : launch_fixedbf_seq<N, 3>(a, tw, st);
+      if (rc == DS_OK) {
+        flip_parity_kernel<<<1, 1, 0, st>>>(a.state);
+        DS_LAUNCH_CHECK();
+        return DS_OK;
+      }
+      if (rc != DS_EUNSUPPORTED) return rc;        // too many microphones for the weight tile: CTA-pipelined kernel below
+    }
+  }
   constexpr int BE = fft_buf_elems(N);
   const size_t smem = ((size_t)a.M + a.B) * BE * sizeof(float2) + (size_t)a.B * N * sizeof(float) + (size_t)N * sizeof(float) +
                       (size_t)(N / 2 + N / 4 + 2) * sizeof(float2);
