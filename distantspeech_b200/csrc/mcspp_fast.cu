@@ -13,8 +13,20 @@
 
 namespace ds {
 
+#ifndef DS_FAST_MINB
+#define DS_FAST_MINB 4
+#define DS_FAST_USE_C 1
+#endif
+
+#ifdef DS_FAST_MAXNREG
+#define DS_FAST_BOUNDS __maxnreg__(DS_FAST_MAXNREG)
+#else
+#define DS_FAST_BOUNDS __launch_bounds__(NT, MINB)
+#endif
+
 template <int M, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
+__global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
+  constexpr bool USE_C = DS_FAST_USE_C != 0;
   constexpr int NP = M * (M + 1) / 2;
   constexpr int NE = mcspp_state_elems<M>();
   constexpr int OFF_YR = 0, OFF_VR = NP, OFF_MC = 2 * NP;
@@ -35,7 +47,7 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
   double mS = blob[(long long)(OFF_MC + 0) * K], mSmin = blob[(long long)(OFF_MC + 1) * K], mStmp = blob[(long long)(OFF_MC + 2) * K],
          mp = blob[(long long)(OFF_MC + 3) * K], mlam = blob[(long long)(OFF_MC + 4) * K];
 
-  {
+  if constexpr (USE_C) {
     double ar[M], ai[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) { const double2 v = a.a0[(long long)m * K + k]; ar[m] = v.x; ai[m] = v.y; }
@@ -72,7 +84,7 @@ __global__ void __launch_bounds__(NT, MINB) mcspp_fast_kernel(McsppArgs a) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(Xp + (long long)(DS_X_PREFETCH - 1) * M * K + m * K));
     }
     const bool reset = (frm > 0) && (ell % a.mc.L == 0);
-    *Yp = chain_bin_step<M, NT, true>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a);
+    *Yp = chain_bin_step<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a);
     if (reset) ell = 0;
     ++ell; ++frm;
     if (a.k_first == 2 && k == 2) { Yp[-1] = make_float2(0.f, 0.f); Yp[-2] = make_float2(0.f, 0.f); }
@@ -90,8 +102,8 @@ template <int M>
 static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
   constexpr int NT = 64;
   constexpr int NP = M * (M + 1) / 2;
-  constexpr int MINB = 4;            // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
-  const size_t smem = (size_t)3 * NP * NT * sizeof(double);
+  constexpr int MINB = DS_FAST_MINB; // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
+  const size_t smem = (size_t)(DS_FAST_USE_C ? 3 : 2) * NP * NT * sizeof(double);
   auto kern = mcspp_fast_kernel<M, NT, MINB>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)a.S * (a.K - a.k_first);

@@ -559,3 +559,25 @@ def test_pcm16_ingest_matches_load_audio(cuda):
     xf = xi.astype(np.float32) / 32767.0
     ref0 = O.mvdr_mcspp_chain(xf[0].T.astype(np.float64), geo, (30, 0), 512, 256)
     assert_wave_parity(ref0, y_pcm[0], "pcm16 chain")
+
+
+# ---------------------------------------------------------------- the boundary from plain C
+def test_capi_from_plain_c(cuda, tmp_path):
+    """tests/capi/host_roundtrip.c: dlopen + cudaMalloc + POD structs, no torch -- STFT/ISTFT round trip and
+    the error path through the C ABI."""
+    import os
+    import shutil
+    import subprocess
+    from distantspeech_b200 import _build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda_home, "include", "cuda_runtime_api.h")):
+        pytest.skip("no C toolchain / CUDA headers on this box")
+    exe = str(tmp_path / "host_roundtrip")
+    subprocess.run(["gcc", "-O1", os.path.join(root, "tests", "capi", "host_roundtrip.c"), "-I", os.path.join(root, "include"),
+                    "-I", os.path.join(cuda_home, "include"), "-L", os.path.join(cuda_home, "lib64"), "-lcudart", "-ldl", "-lm",
+                    "-o", exe], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(cuda_home, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe, _build.LIB], capture_output=True, text=True, env=env, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout
