@@ -168,7 +168,7 @@ def _declare(lib):
     lib.ds_srp_run.argtypes = [i32, i32, i32, i32, dbl, i32, vp, vp, vp, vp, i32, vp]
     lib.ds_srp_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.ds_srp_workspace_bytes.restype = C.c_size_t
-    lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_power_run.restype = C.c_int
     lib.ds_spectral_gain_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_spectral_gain_run.restype = C.c_int
@@ -273,3 +273,14 @@ def device_window(window: np.ndarray, n_fft: int):
             _window_cache.clear()
         _window_cache[key] = t.as_tensor(w).to("cuda")
     return _window_cache[key]
+
+
+def spectral_power(Xd, via_abs=False):
+    """|X|^2 of a complex64/complex128 CUDA tensor on the device (ds_power_run) -> float64 tensor of the same shape."""
+    t = require_cuda()
+    Xd = Xd.contiguous()
+    out = t.empty(Xd.shape, dtype=t.float64, device=Xd.device)
+    if Xd.numel():
+        check(lib().ds_power_run(Xd.numel(), ptr(Xd), int(Xd.dtype == t.complex128), int(bool(via_abs)), ptr(out), stream_ptr()),
+              "ds_power_run")
+    return out

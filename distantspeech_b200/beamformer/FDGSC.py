@@ -136,10 +136,8 @@ class FDGSC(object):
         hist = pf["bm_hist"].clone()
         U0 = stft_device(bm_out[:, :M - 1, :Lf].contiguous(), 2 * Lf, Lf, win, L.DS_STFT_STREAMING, history=hist)
         pf["bm_hist"] = bm_out[:, :M - 1, Nb - Lf:Nb].contiguous()
-        Ypow = t.empty((S, nblk, K), dtype=t.float64, device="cuda")
-        Upow = t.empty((S, M - 1, K), dtype=t.float64, device="cuda")
-        L.check(L.lib().ds_power_run(Ypow.numel(), L.ptr(Y), 0, L.ptr(Ypow), L.stream_ptr()), "ds_power_run")
-        L.check(L.lib().ds_power_run(Upow.numel(), L.ptr(U0), 0, L.ptr(Upow), L.stream_ptr()), "ds_power_run")
+        Ypow = L.spectral_power(Y).view(S, nblk, K)                       # np.real(Y * conj(Y))   (:288)
+        Upow = L.spectral_power(U0).view(S, M - 1, K)
         G, _, _ = pf["omlsa"]._run(Ypow, Upow, u_const=True)
         Yg = t.empty((S, nblk, 1, K), dtype=t.complex128, device="cuda")
         L.check(L.lib().ds_spectral_gain_run(Ypow.numel(), L.ptr(Y), 0, L.ptr(G), 1, L.ptr(Yg), L.stream_ptr()),

@@ -144,11 +144,16 @@ extern "C" int ds_omlsa_gain_run(int n_rows, int n_bins, const double *xi, const
 // ---- spectral power / gain (FDGSC.py:288-294) -------------------------------------------
 namespace ds {
 template <typename C2>
-__global__ void power_kernel(long long n, const C2 *__restrict__ X, double *__restrict__ out) {
+__global__ void power_kernel(long long n, const C2 *__restrict__ X, int via_abs, double *__restrict__ out) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
   const C2 v = X[g];
-  out[g] = power_c((double)v.x, (double)v.y);
+  if (via_abs) {                       // np.abs(X) ** 2: hypot, then squared (mcra.py:29-30)
+    const double h = hypot((double)v.x, (double)v.y);
+    out[g] = __dmul_rn(h, h);
+  } else {                             // np.real(X * np.conj(X))
+    out[g] = power_c((double)v.x, (double)v.y);
+  }
 }
 template <typename C2>
 __global__ void spectral_gain_kernel(long long n, const C2 *__restrict__ Yin, const double *__restrict__ G, int take_sqrt,
@@ -161,11 +166,11 @@ __global__ void spectral_gain_kernel(long long n, const C2 *__restrict__ Yin, co
 }
 }  // namespace ds
 
-extern "C" int ds_power_run(long long n, const void *X, int x_is_c128, double *out, void *stream) {
+extern "C" int ds_power_run(long long n, const void *X, int x_is_c128, int via_abs, double *out, void *stream) {
   DS_CHECK_ARG(X && out && n >= 1, "ds_power_run: bad argument");
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  if (x_is_c128) ds::power_kernel<double2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const double2 *)X, out);
-  else ds::power_kernel<float2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const float2 *)X, out);
+  if (x_is_c128) ds::power_kernel<double2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const double2 *)X, via_abs, out);
+  else ds::power_kernel<float2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const float2 *)X, via_abs, out);
   DS_LAUNCH_CHECK();
   return DS_OK;
 }

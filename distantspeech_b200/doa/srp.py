@@ -57,8 +57,7 @@ class srp(object):
     def _mcra_p(self, X):
         """MCRA speech presence on channel 0 (srp.py:38-40; returned, not used by the map)."""
         t = L.require_cuda()
-        x0 = X[:, 0, :].to(t.complex128)
-        pw = (x0.real * x0.real + x0.imag * x0.imag).contiguous()             # [T, K]
+        pw = L.spectral_power(X[:, 0, :].to(t.complex128), via_abs=True)     # [T, K]; complex input -> np.abs(y) ** 2
         _, p = self.spp.estimation_frames(pw, return_p=True)
         return p                                                              # [T, K]
 

@@ -79,11 +79,11 @@ class NoiseEstimationMCRA(NoiseEstimationBase):
         if isinstance(Y, t.Tensor):
             Yd = Y.to("cuda")
             if Yd.dtype == t.complex128:
-                Yd = Yd.real * Yd.real + Yd.imag * Yd.imag
+                return L.spectral_power(Yd, via_abs=True)
             return Yd.to(t.float64)
         Y = np.asarray(Y)
-        if Y.dtype == 'complex':                 # complex128 only, like the reference (:29-30)
-            Y = np.abs(Y) ** 2
+        if Y.dtype == 'complex':                 # complex128 only, like the reference (:29-30): np.abs(Y) ** 2
+            return L.spectral_power(t.as_tensor(np.ascontiguousarray(Y)).to("cuda"), via_abs=True)
         return t.as_tensor(np.ascontiguousarray(Y, dtype=np.float64)).to("cuda")
 
     def estimation(self, Y):

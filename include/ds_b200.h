@@ -147,9 +147,11 @@ int ds_pmwf_weight_run(int n_bins, int n_mics, const double *xi, const void *Rxx
 int ds_apply_weights_run(int n_streams, int n_frames, int n_mics, int n_bins, const void *X,
                          int x_is_c128, const void *W, void *Y, void *stream);
 
-/* |X|^2 the way the reference writes it, np.real(X * np.conj(X)) (FDGSC.py:288, GSC.py:286):
- * re*re + im*im with each product rounded.  X: n complex values, c64 or c128; out: n float64.    */
-int ds_power_run(long long n, const void *X, int x_is_c128, double *out, void *stream);
+/* |X|^2 the two ways the reference writes it.  via_abs = 0: np.real(X * np.conj(X)) (FDGSC.py:288,
+ * GSC.py:286), re*re + im*im with each product rounded; via_abs = 1: np.abs(X) ** 2 (mcra.py:29-30,
+ * what NoiseEstimationMCRA does to complex input), hypot then squared.
+ * X: n complex values, c64 or c128; out: n float64.                                              */
+int ds_power_run(long long n, const void *X, int x_is_c128, int via_abs, double *out, void *stream);
 /* Y[i] * g[i] in complex128, g = G or sqrt(G) (FDGSC.py:292-294): spectral gain before Transform.istft.
  * Yin c64 or c128 (n values), G float64, Yout c128 (may alias Yin when it is c128).              */
 int ds_spectral_gain_run(long long n, const void *Yin, int y_is_c128, const double *G, int take_sqrt,
