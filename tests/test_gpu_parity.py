@@ -581,3 +581,25 @@ def test_capi_from_plain_c(cuda, tmp_path):
     r = subprocess.run([exe, _build.LIB], capture_output=True, text=True, env=env, timeout=120)
     print(r.stdout, r.stderr)
     assert r.returncode == 0 and "PASS" in r.stdout
+
+
+def test_transform_ragged_chunks_match_the_reference_quirk(cuda):
+    """Quirk 4 (transform.py:441,451): a chunk that is not a multiple of hop loses its trailing samples but the
+    history still takes the last `overlap` samples -- the device Transform must misalign exactly like the oracle;
+    a chunk shorter than one hop raises (the reference fails inside util.frame)."""
+    from distantspeech_b200.transform.transform import Transform
+    rng = np.random.default_rng(17)
+    x = (rng.standard_normal((4000, 2)) * 0.2).astype(np.float32)
+    tf, ref = Transform(n_fft=512, hop_length=256, channel=2), O.Transform(channel=2, n_fft=512, hop_length=256)
+    tfo, refo = Transform(n_fft=512, hop_length=256, channel=2), O.Transform(channel=2, n_fft=512, hop_length=256)
+    pos = 0
+    for n in (300, 1000, 256, 777, 1667):
+        Y, Yr = tf.stft(x[pos:pos + n]), ref.stft(x[pos:pos + n].astype(np.float64))
+        assert Y.shape == Yr.shape == (257, n // 256, 2)
+        assert np.max(np.abs(Y - Yr)) <= 3e-6 * np.max(np.abs(Yr))
+        assert np.array_equal(tf.previous_input, ref.previous_input)
+        y, yr = tfo.istft(Yr), refo.istft(Yr)
+        assert y.shape == yr.shape and np.max(np.abs(y - yr)) < 2e-6
+        pos += n
+    with pytest.raises(ValueError):
+        Transform(n_fft=512, hop_length=256, channel=2).stft(x[:100])
