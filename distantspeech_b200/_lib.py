@@ -168,6 +168,8 @@ def _declare(lib):
     lib.ds_srp_run.argtypes = [i32, i32, i32, i32, dbl, i32, vp, vp, vp, vp, i32, vp]
     lib.ds_srp_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.ds_srp_workspace_bytes.restype = C.c_size_t
+    lib.ds_fdgsc_notch_run.argtypes = [C.POINTER(FdgscParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.ds_fdgsc_notch_run.restype = C.c_int
     lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_power_run.restype = C.c_int
     lib.ds_spectral_gain_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -89,6 +89,7 @@ class FDGSC(object):
         self.phi, self.psi = None, None          # ccafbounds: computed by the reference ctor but never used
         self._state = None
         self._pf = None
+        self._diag = None
         self._S = None
         self.bm = None
         self.aic_filter = None
@@ -105,6 +106,7 @@ class FDGSC(object):
     def reset(self):
         self._state = None
         self._pf = None
+        self._diag = None
         self.spp.frm_cnt, self.spp.ell = 0, 1
 
     def _postfilter(self, y_aic, fix_out, bm_out):
@@ -146,10 +148,38 @@ class FDGSC(object):
                            fft_fp64=self.precision == "fp64")
         return out[:, 0, :]
 
-    def process(self, x, postfilter=False, dc_notch=True):
+    def _alignment_diagnostics(self, x_notched, fix_out):
+        """fix_output_delayed, aligned_output, aligned_output_delayed of the return tuple (FDGSC.py:256,267,299-302).
+        The fused kernel keeps them on chip; here they are rebuilt from its inputs/outputs with the streaming FIR
+        (ds_fir_run, float64 like the reference) and two carried delay lines (frameLen and frameLen/2 samples).
+        x_notched [S, M, Nb] float32, fix_out [S, Nb] float32 -> three float64 CUDA tensors."""
+        t = L.require_cuda()
+        S, M, Nb = x_notched.shape
+        Lf, FL = self.frameLen, self.time_alignment.delay_filter_len
+        d = self._diag
+        if d is None or d["S"] != S:
+            d = self._diag = dict(S=S, cache=t.zeros((S, M, FL - 1), dtype=t.float64, device="cuda"),
+                                  al=t.zeros((S, M, Lf // 2), dtype=t.float64, device="cuda"),
+                                  fix=t.zeros((S, Lf), dtype=t.float64, device="cuda"))
+        h = t.as_tensor(np.ascontiguousarray(self.time_alignment.delay_filter.T)).to("cuda")
+        xin = x_notched.double().contiguous()
+        aligned = t.empty_like(xin)
+        scratch = t.empty_like(xin)
+        L.check(L.lib().ds_fir_run(S, M, Nb, FL, L.ptr(h), L.ptr(d["cache"]), L.ptr(xin), L.ptr(aligned), L.ptr(scratch),
+                                   L.stream_ptr()), "ds_fir_run")
+        al_d = t.cat([d["al"], aligned[:, :, :Nb - Lf // 2]], dim=2)
+        d["al"] = aligned[:, :, Nb - Lf // 2:].clone()
+        fx = fix_out.double()
+        fix_d = t.cat([d["fix"], fx[:, :Nb - Lf]], dim=1)
+        d["fix"] = fx[:, Nb - Lf:].clone()
+        return fix_d, aligned.permute(0, 2, 1), al_d.permute(0, 2, 1)
+
+    def process(self, x, postfilter=False, dc_notch=True, diagnostics=None):
         """x [n_samples, n_chs] (or [S, n_samples, n_chs]) -> (output, p, fix_output, fix_output_delayed,
         bm_output, aligned_output, aligned_output_delayed, bm, aic_filter) like FDGSC.py:307-317.
-        ``aligned_output`` / the delayed copies are diagnostics the kernel does not materialise (None)."""
+        ``diagnostics``: materialise fix_output_delayed / aligned_output / aligned_output_delayed (default: yes
+        for the reference's single-stream call, no -- None in the tuple -- for the batched extension, where they
+        would cost three float64 copies of the input)."""
         t = L.require_cuda()
         L.ensure_init()
         as_torch = isinstance(x, t.Tensor)
@@ -188,14 +218,20 @@ class FDGSC(object):
                 y = yrun
         if Nb != N:
             y[:, :Nb] = yrun
-        # quirk 11: the caller's array now holds the DC-notched signal
+        # quirk 11: the caller's array now holds the DC-notched signal -- all of it, also the samples beyond the
+        # last full block, whose only other effect is on the notch memories the next call starts from
         if dc_notch:
             notched = xrun.permute(0, 2, 1)
+            if Nb != N:
+                tail = xs[:, :, Nb:].contiguous()
+                L.check(L.lib().ds_fdgsc_notch_run(C.byref(prm), L.ptr(self._state), L.ptr(tail), N - Nb, L.stream_ptr()),
+                        "ds_fdgsc_notch_run")
+                notched = t.cat([notched, tail.permute(0, 2, 1)], dim=1)
             if as_torch:
-                (x if batched else x[None])[:, :Nb, :] = notched.to(x.dtype)
+                (x if batched else x[None])[:, :, :] = notched.to(x.dtype)
             elif isinstance(x, np.ndarray) and x.flags.writeable:
                 xv = x if batched else x[None]
-                xv[:, :Nb, :] = notched.cpu().numpy().astype(x.dtype)
+                xv[:, :, :] = notched.cpu().numpy().astype(x.dtype)
         # filter views from the state blob
         K = 257
         st = self._state.view(t.float64).view(S, -1)
@@ -206,7 +242,11 @@ class FDGSC(object):
         self.aic_filter = _FilterView(Waic[0].T)
         p = p_out.permute(0, 2, 1)
         self.spp.p = p[0, :, -1].cpu().numpy()
-        outs = [y, p, fix_out, None, bm_out.permute(0, 2, 1), None, None]
+        diag = [None, None, None]
+        if (not batched) if diagnostics is None else diagnostics:
+            pad = (lambda v: v if Nb == N else t.nn.functional.pad(v, (0, 0, 0, N - Nb) if v.dim() == 3 else (0, N - Nb)))
+            diag = [pad(v) for v in self._alignment_diagnostics(xrun, fix_out)]
+        outs = [y, p, fix_out, diag[0], bm_out.permute(0, 2, 1), diag[1], diag[2]]
         if not batched:
             outs = [o[0] if o is not None else None for o in outs]
         if not as_torch:

@@ -554,4 +554,14 @@ int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const dou
   return p->fp64 ? launch_fdgsc<double>(a, tw, st) : launch_fdgsc<float>(a, tw, st);
 }
 
+int ds_fdgsc_notch_run(const ds_fdgsc_params *p, void *state, float *x, int n_samples, void *stream) {
+  DS_CHECK_ARG(p && state && x && n_samples >= 1, "ds_fdgsc_notch_run: bad argument");
+  const double r = p->notch_radius;
+  const double den2 = r * r + 0.7 * (1 - r) * (1 - r);
+  const int items = p->n_streams * p->n_mics;
+  dcnotch_kernel<<<(items + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, (double *)state, p->n_streams, p->n_mics, n_samples, r, den2);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
 }  // extern "C"

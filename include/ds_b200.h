@@ -382,6 +382,11 @@ int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const dou
                  void *state, float *x, float *y, float *bm_out, float *fix_out, double *p_out,
                  void *stream);
 
+/* The DC notch of FDGSC.process on its own (FDGSC.py:211-213, feature.py:37-49), in place on
+ * x [S][M][n_samples] with the notch memories of `state`: the reference filters the WHOLE input,
+ * also the trailing samples beyond the last full block that ds_fdgsc_run does not consume.       */
+int ds_fdgsc_notch_run(const ds_fdgsc_params *p, void *state, float *x, int n_samples, void *stream);
+
 /* replaces TimeAlignment.process / fir_filter (fixedbeamformer.py:13-93): streaming per-channel
  * FIR y[n] = sum_k h[k] x[n-k] with a (filter_len-1)-sample cache.  All float64:
  *   h [C][filter_len]   cache [S][C][filter_len-1] in/out   x, y, scratch [S][C][N]   */

@@ -412,6 +412,17 @@ def test_fdgsc_streaming_batch_and_time_alignment(cuda):
     ya = fd2.process(x_nm[:, :256 * 20].copy())[0]
     yb = fd2.process(x_nm[:, 256 * 20:].copy())[0]
     assert np.max(np.abs(np.concatenate([ya, yb], axis=1) - y)) < 1e-6
+    # the whole 9-tuple of the single-stream call, over two chunks (ragged tail: 100 samples beyond a block)
+    orc = O.FdgscOracle(geo, 256, ang)
+    fd3 = FDGSC(mic, frameLen=256, angle=[75, 0])
+    for lo, hi in ((0, 256 * 12 + 100), (256 * 12 + 100, 256 * 30 + 100)):
+        res = fd3.process(x_nm[0, lo:hi].copy())
+        ref = orc.process(x_nm[0, lo:hi].astype(np.float64))
+        assert len(res) == 9 and res[3].shape == ref[0].shape and res[5].shape == (hi - lo, 4)
+        assert np.max(np.abs(res[3] - orc.diag["fix_output_delayed"])) < 2e-6
+        assert np.max(np.abs(res[5] - orc.diag["aligned_output"])) < 1e-6
+        assert np.max(np.abs(res[6] - orc.diag["aligned_output_delayed"])) < 1e-6
+    assert fd.process(x_nm.copy())[5] is None and fd.process(x_nm.copy(), diagnostics=True)[5].shape == (3, 256 * 50, 4)
     # TimeAlignment.process == oracle FIR, streaming in two blocks
     ta = TimeAlignment(mic, angle=[75, 0])
     h = O.alignment_filters(geo, ang)
