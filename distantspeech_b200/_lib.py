@@ -79,6 +79,18 @@ class McsppCdrTaps(C.Structure):
                 ("w", C.c_void_p)]
 
 
+class GscParams(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_frames", C.c_int32),
+                ("frm_cnt", C.c_int32), ("method", C.c_int32), ("init_frames", C.c_int32), ("reserved", C.c_int32),
+                ("alpha", C.c_double), ("alpha_d", C.c_double), ("diag_eps", C.c_double), ("psi_0", C.c_double),
+                ("q_min", C.c_double), ("q_max", C.c_double), ("p_min", C.c_double), ("p_max", C.c_double),
+                ("snr_min", C.c_double), ("snr_max", C.c_double), ("Gmin", C.c_double), ("mu", C.c_double)]
+
+
+class GscTaps(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("G", C.c_void_p), ("xi", C.c_void_p), ("gamma", C.c_void_p), ("q", C.c_void_p)]
+
+
 class AmvdrParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_frames", C.c_int32),
                 ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32), ("method", C.c_int32),
@@ -170,6 +182,13 @@ def _declare(lib):
     lib.ds_srp_workspace_bytes.restype = C.c_size_t
     lib.ds_fdgsc_notch_run.argtypes = [C.POINTER(FdgscParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.ds_fdgsc_notch_run.restype = C.c_int
+    lib.ds_gsc_default_params.argtypes = [C.POINTER(GscParams), C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ds_gsc_default_params.restype = None
+    lib.ds_gsc_state_bytes.argtypes = [C.POINTER(GscParams)]
+    lib.ds_gsc_state_bytes.restype = C.c_size_t
+    lib.ds_gsc_run.argtypes = [C.POINTER(GscParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                               C.POINTER(GscTaps), C.c_void_p]
+    lib.ds_gsc_run.restype = C.c_int
     lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_power_run.restype = C.c_int
     lib.ds_spectral_gain_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -285,6 +285,39 @@ int ds_mcspp_cdr_run(const ds_mcspp_cdr_params *p, void *state, void *workspace,
  * Re Pxij[6] Im Pxij[6]; 7 [S][6][K] MCRA S Smin Stmp p lambda_d, posterior p      */
 int ds_mcspp_cdr_export(const ds_mcspp_cdr_params *p, const void *state, int field, void *out, void *stream);
 
+/* ---- McMcra + frequency-domain GSC (noise_estimation/mc_mcra.py, beamformer/GSC.py) -------- */
+typedef struct ds_gsc_params {
+  int32_t n_fft;
+  int32_t n_streams;
+  int32_t n_mics;      /* 2..8                                                              */
+  int32_t n_frames;
+  int32_t frm_cnt;     /* frames already processed (McMcra.frm_cnt, host-tracked)           */
+  int32_t method;      /* GSC.process `method`: 0 = pass channel 0 through (GSC.py:242), else GSC */
+  int32_t init_frames; /* 5: Phi_vv = Phi_yy                              mc_mcra.py:186-187 */
+  int32_t reserved;
+  double alpha, alpha_d;            /* .92 .95                             mc_mcra.py:34-36  */
+  double diag_eps;                  /* 1e-6                                :191              */
+  double psi_0;                     /* 100 (psi_0 = psi_tilde_0)           :62-63            */
+  double q_min, q_max, p_min, p_max;/* .01 .99 .01 .99                     :89, :218         */
+  double snr_min, snr_max;          /* 1e-6 1e6                            :194, :199        */
+  double Gmin;                      /* 0.0631                              :152              */
+  double mu;                        /* 0.01 NLMS step                      GSC.py:207        */
+} ds_gsc_params;
+void ds_gsc_default_params(ds_gsc_params *p, int n_fft, int n_streams, int n_mics, int n_frames);
+/* state [S][NE][K] float64, zero = reset: Phi_yy, Phi_vv (packed real upper triangles, M(M+1)/2 each),
+ * Re G[M-1], Im G[M-1] (noise-canceller weights), then p q xi gamma G of the last frame               */
+size_t ds_gsc_state_bytes(const ds_gsc_params *p);
+typedef struct ds_gsc_taps { /* optional per-frame outputs [S][T][K], any may be NULL */
+  double *p, *G, *xi, *gamma, *q;
+} ds_gsc_taps;
+/* replaces, per frame, McMcra.estimation (mc_mcra.py:179-221) and -- when `a` and `Yout` are given -- the
+ * per-bin loop of GSC.process (GSC.py:231-286): fixed beam a/(a^H a), Griffiths-Jim blocking matrix, NLMS
+ * noise canceller gated by 1 - p, McMcra gain as postfilter.
+ *   a    [M][K] c128 propagation vectors exp(-j w_k tau_m) (or NULL: estimator only)
+ *   X    [S][T][M][K] c64 / c128     Yout [S][T][K] c64 (or NULL)                                        */
+int ds_gsc_run(const ds_gsc_params *p, void *state, const void *a, const void *X, int x_is_c128, void *Yout,
+               const ds_gsc_taps *taps, void *stream);
+
 /* ---- postfilter gains ------------------------------------------------------ */
 typedef struct ds_omlsa_multi_params {
   int32_t n_bins, n_streams, n_frames;

@@ -156,3 +156,19 @@ def make_adaptive_mvdr(mic, frameLen, hop, nfft):
     orig = obj.transformer.istft
     obj.transformer.istft = lambda Y: orig(Y[..., None] if Y.ndim == 2 else Y)
     return obj
+
+
+def make_gsc(mic, frameLen=256, angle=None):
+    """Construct the reference frequency-domain ``GSC`` (beamformer/GSC.py) with the same patch (iii):
+    ``GSC.process`` hands its 2-D ``[K, T]`` spectrum to ``Transform.istft`` (:289), which reads 2-D as one
+    frame x channels (transform.py:463-464) and asserts."""
+    install()
+    import contextlib
+    import io
+    from DistantSpeech.beamformer.GSC import GSC
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        obj = GSC(mic, frameLen=frameLen) if angle is None else GSC(mic, frameLen=frameLen, angle=angle)
+    orig = obj.transformer.istft
+    obj.transformer.istft = lambda Y: orig(Y[..., None] if Y.ndim == 2 else Y)
+    return obj

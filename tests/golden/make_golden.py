@@ -159,6 +159,20 @@ def main():
     Ws = np.array([pf.getweights(Z8[:, :, n]).squeeze() for n in range(40)])
     save("zelinski.npz", Z=Z8.astype(np.complex64), W=Ws, Pxii=pf.Pxii, Pxij=pf.Pxij)
 
+    # ---- f1: frequency-domain GSC with the McMcra postfilter (GSC.py:174-294), 4 mics, two calls ----
+    from DistantSpeech.beamformer.MicArray import MicArray as RefMic
+    geo_g = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    xg = O.synth_streams(1, geo_g, 128 * 160, seed0=0x65C)[0]                                   # [4, N] float32
+    gsc = H.make_gsc(RefMic(arrayType="circular", r=0.032, M=4), 256)
+    ang = np.array([30, 0]) / 180 * np.pi
+    n1 = 128 * 100
+    ps, Gs, ys = [], [], []
+    for lo, hi in ((0, n1), (n1, xg.shape[1])):
+        ys.append(gsc.process(xg[:, lo:hi].astype(np.float64), ang, method=2)["data"])
+    save("gsc.npz", x=xg, angle_rad=ang, n_first=np.array(n1), y=np.concatenate(ys), p_last=gsc.spp.p, q_last=gsc.spp.q,
+         xi_last=gsc.spp.xi, gamma_last=gsc.spp.gamma, Gpost_last=gsc.spp.G, Gw_last=gsc.G, Phi_yy_last=gsc.spp.Phi_yy,
+         Phi_vv_last=gsc.spp.Phi_vv)
+
     # ---- a14: McSpp (CDR-driven prior, complex inverse with SNR-dependent loading), 4 mics ----
     from DistantSpeech.noise_estimation.mcspp import McSpp
     geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=512)

@@ -614,3 +614,56 @@ def test_transform_ragged_chunks_match_the_reference_quirk(cuda):
         pos += n
     with pytest.raises(ValueError):
         Transform(n_fft=512, hop_length=256, channel=2).stft(x[:100])
+
+
+# ---------------------------------------------------------------- f1: frequency-domain GSC + McMcra
+def test_gsc_mcmcra_golden(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.GSC import GSC
+    from distantspeech_b200.noise_estimation.mc_mcra import McMcra
+    g = golden("gsc.npz")
+    n1 = int(g["n_first"])
+    mic = MicArray(arrayType="circular", r=0.032, M=4)
+    gsc = GSC(mic, 256)
+    ya = gsc.process(g["x"][:, :n1], g["angle_rad"], method=2)
+    yb = gsc.process(g["x"][:, n1:], g["angle_rad"], method=2)
+    assert set(ya.keys()) == {"data", "WNG", "DI", "beampattern"}
+    err, snr = assert_wave_parity(g["y"], np.concatenate([ya["data"], yb["data"]]), "GSC")
+    print("GSC: max-abs %.2e SNR %.1f dB" % (err, snr))
+    assert np.max(np.abs(gsc.spp.p - g["p_last"])) < 1e-4 and np.max(np.abs(gsc.spp.G - g["Gpost_last"])) < 1e-4
+    assert np.linalg.norm(gsc.G - g["Gw_last"]) <= 1e-4 * np.linalg.norm(g["Gw_last"])
+    assert np.linalg.norm(gsc.spp.Phi_vv - g["Phi_vv_last"]) <= 1e-5 * np.linalg.norm(g["Phi_vv_last"])
+    # McMcra on its own, fed the oracle's spectrum: per-frame p / q / xi / gamma / G against the oracle
+    geo = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    D = O.Transform(channel=4, n_fft=256, hop_length=128).stft(g["x"].astype(np.float64).T)[:, :60]
+    ref, taps = O.McMcra(nfft=256, channels=4), {k: [] for k in ("p", "q", "xi", "gamma", "G")}
+    for n in range(D.shape[1]):
+        ref.estimation(D[:, n, :])
+        for k in taps:
+            taps[k].append(getattr(ref, k).copy())
+    est = McMcra(nfft=256, channels=4)
+    res = est.estimation_frames(D)
+    for k in taps:
+        assert np.allclose(res[k], np.array(taps[k]).T, rtol=1e-8, atol=1e-12), k
+    assert np.allclose(est.Phi_yy, ref.Phi_yy, rtol=1e-10, atol=1e-18) and est.Phi_vv.shape == (4, 4, 129)
+    e2 = McMcra(nfft=256, channels=4)
+    for n in range(8):
+        e2.estimation(D[:, n, :])
+    assert np.array_equal(e2.p, res["p"][:, 7])                                # frame by frame == many frames per call
+    # method 0 passes channel 0 through (GSC.py:242); batch of streams == singles
+    y0 = GSC(mic, 256).process(g["x"][:, :n1], g["angle_rad"], method=0)["data"]
+    assert np.max(np.abs(y0[128:] - g["x"][0, :n1 - 128])) < 2e-6
+    yb2 = GSC(mic, 256).process(np.stack([g["x"][:, :n1], g["x"][::-1, :n1]]), g["angle_rad"], method=2)["data"]
+    assert np.max(np.abs(yb2[0] - ya["data"])) < 1e-6
+
+
+@pytest.mark.parametrize("M", [2, 6, 8])
+def test_gsc_other_mic_counts(cuda, M):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.GSC import GSC
+    geo = O.MicGeometry("circular", r=0.04, M=M, n_fft=256)
+    x = O.synth_streams(1, geo, 128 * 90, seed0=40 + M)[0]
+    ang = np.array([75, 0]) / 180 * np.pi
+    ref = O.GscOracle(geo, 256).process(x.astype(np.float64), ang, method=2)
+    y = GSC(MicArray(arrayType="circular", r=0.04, M=M), 256).process(x, ang, method=2)["data"]
+    assert_wave_parity(ref, y, "GSC M=%d" % M)

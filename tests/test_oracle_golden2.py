@@ -64,3 +64,17 @@ def test_mcspp_cdr_golden():
     assert np.array_equal(est.mccdr.mcra.p, g["mcra_p_last"])
     with pytest.raises(ValueError):
         O.McSpp(nfft=512, channels=6)                     # the reference raises IndexError above 4 channels
+
+
+def test_gsc_mcmcra_golden():
+    """f1: frequency-domain GSC with the McMcra postfilter, two consecutive calls (streaming state)."""
+    g = golden("gsc.npz")
+    geo = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    o = O.GscOracle(geo, 256)
+    n1 = int(g["n_first"])
+    x = g["x"].astype(np.float64)
+    y = np.concatenate([o.process(x[:, :n1], g["angle_rad"], method=2), o.process(x[:, n1:], g["angle_rad"], method=2)])
+    assert np.max(np.abs(y - g["y"])) < 1e-12
+    assert np.array_equal(o.spp.p, g["p_last"]) and np.array_equal(o.spp.q, g["q_last"])
+    assert np.allclose(o.spp.G, g["Gpost_last"], rtol=1e-13, atol=0) and np.allclose(o.Gw, g["Gw_last"], rtol=1e-12, atol=1e-15)
+    assert np.allclose(o.spp.Phi_vv, g["Phi_vv_last"], rtol=1e-13, atol=1e-18)

@@ -121,6 +121,18 @@ def main():
         D, T, K = tau.shape[0], X.shape[0], X.shape[2]
         out.append({"config": 5, "what": "SRP-PHAT 16-mic 48 kHz n_fft 1024, %d dirs x %d frames (%s engine)" % (D, T, eng),
                     "ms": ms, "audio_s_per_s": (N5 / 48000) / (ms / 1e3), "tflops_algorithmic": 8.0 * D * 16 * K * T / (ms / 1e3) / 1e12})
+    # ---- f1: frequency-domain GSC with the McMcra postfilter, 8 mics, n_fft 256 / hop 128 ----
+    from distantspeech_b200.beamformer.GSC import GSC
+    Sg = 128 if small else 1024
+    mic8g = MicArray(arrayType="circular", r=0.05, M=8)
+    xg = torch.randn((Sg, 8, N), device="cuda") * 0.1
+    gsc = GSC(mic8g, 256)
+    ms = timed(lambda: gsc.process(xg, ang, method=2), warm=1, reps=2)
+    geo8 = O.MicGeometry("circular", r=0.05, M=8, n_fft=256)
+    xh = xg[0, :, :16000].cpu().numpy().astype(np.float64)
+    t0 = time.perf_counter(); O.GscOracle(geo8, 256).process(xh, ang, method=2); cpu = 1.0 / (time.perf_counter() - t0)
+    out.append({"config": "f1", "what": "frequency-domain GSC + McMcra postfilter 8-mic, %d streams x 10 s (incl. API hand-off)" % Sg,
+                "ms": ms, "audio_s_per_s": Sg * N / FS / (ms / 1e3), "cpu_oracle_1core_audio_s_per_s": cpu})
     for o in out:
         print(json.dumps(o))
 
