@@ -91,6 +91,12 @@ class GscTaps(C.Structure):
     _fields_ = [("p", C.c_void_p), ("G", C.c_void_p), ("xi", C.c_void_p), ("gamma", C.c_void_p), ("q", C.c_void_p)]
 
 
+class SubbandNlmsParams(C.Structure):
+    _fields_ = [("n_bins", C.c_int32), ("n_streams", C.c_int32), ("n_filters", C.c_int32), ("n_frames", C.c_int32),
+                ("n_ch", C.c_int32), ("filter_len", C.c_int32), ("one_minus_p", C.c_int32), ("reserved", C.c_int32),
+                ("mu", C.c_double), ("alpha", C.c_double), ("eps", C.c_double)]
+
+
 class AmvdrParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_frames", C.c_int32),
                 ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32), ("method", C.c_int32),
@@ -189,6 +195,15 @@ def _declare(lib):
     lib.ds_gsc_run.argtypes = [C.POINTER(GscParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                C.POINTER(GscTaps), C.c_void_p]
     lib.ds_gsc_run.restype = C.c_int
+    lib.ds_subband_nlms_state_bytes.argtypes = [C.POINTER(SubbandNlmsParams)]
+    lib.ds_subband_nlms_state_bytes.restype = C.c_size_t
+    lib.ds_subband_nlms_run.argtypes = [C.POINTER(SubbandNlmsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    lib.ds_subband_nlms_run.restype = C.c_int
+    lib.ds_dcnotch_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ds_dcnotch_run.restype = C.c_int
+    lib.ds_channel_mean_run.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ds_channel_mean_run.restype = C.c_int
     lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_power_run.restype = C.c_int
     lib.ds_spectral_gain_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -318,6 +318,35 @@ typedef struct ds_gsc_taps { /* optional per-frame outputs [S][T][K], any may be
 int ds_gsc_run(const ds_gsc_params *p, void *state, const void *a, const void *X, int x_is_c128, void *Yout,
                const ds_gsc_taps *taps, void *stream);
 
+/* ---- STFT-domain NLMS filters (adaptivefilter/SubbandLMS.py, SubbandLmsMc.py) and SubbandGSC helpers -- */
+typedef struct ds_subband_nlms_params {
+  int32_t n_bins;      /* K = num_bands / 2 + 1                                                   */
+  int32_t n_streams;   /* S                                                                       */
+  int32_t n_filters;   /* F independent filters per stream that share the input X (SubbandGSC: the M
+                          blocking filters all take the fixed beam as input, SubbandGSC.py:220-226) */
+  int32_t n_frames;    /* T                                                                       */
+  int32_t n_ch;        /* C input channels per filter (SubbandLMS: 1, SubbandLmsMc: channel)      */
+  int32_t filter_len;  /* frame taps per bin (2 in SubbandGSC)                                    */
+  int32_t one_minus_p; /* 1: gate with 1 - p (the canceller, SubbandGSC.py:236)                   */
+  int32_t reserved;
+  double mu;    /* step: W += 2 mu p grad                            SubbandAF.py:84-87           */
+  double alpha; /* power smoothing (0.9 default, 0.8 canceller)      SubbandLMS.py:70-74          */
+  double eps;   /* 1e-4 regulariser (the `alpha` argument of update) SubbandLMS.py:75            */
+} ds_subband_nlms_params;
+size_t ds_subband_nlms_state_bytes(const ds_subband_nlms_params *p);   /* zero = fresh filters    */
+/* replaces SubbandLMS.update (SubbandLMS.py:28-84) / SubbandLmsMc.update (SubbandLmsMc.py:144-191) over T frames,
+ * spectra in, error spectra out (the Transform analysis / synthesis around them are ds_stft_run / ds_istft_run):
+ *   X [S][T][C][K] c64 input spectra   D [S][T][F][K] c64 desired spectra   prob [S][T][K] float64 or NULL (p = 1)
+ *   Err [S][T][F][K] c128                                                                               */
+int ds_subband_nlms_run(const ds_subband_nlms_params *p, void *state, const void *X, const void *D, const double *prob,
+                        void *Err, void *stream);
+/* FilterDcNotch16.filter_dc_notch16 (adaptivefilter/feature.py:37-49) in place on x [S][C][n_samples] float32,
+ * memories mem [S][C][2] float64 in/out (zero = fresh filter).                                            */
+int ds_dcnotch_run(int n_streams, int n_ch, int n_samples, double radius, double *mem, float *x, void *stream);
+/* np.mean(x, axis=channel) (the fixed beamformer of the GSC pipelines, SubbandGSC.py:143, FDGSC.py:138):
+ * x [S][C][n_samples] float64 -> out [S][n_samples] float64.                                              */
+int ds_channel_mean_run(int n_streams, int n_ch, long long n_samples, const double *x, double *out, void *stream);
+
 /* ---- postfilter gains ------------------------------------------------------ */
 typedef struct ds_omlsa_multi_params {
   int32_t n_bins, n_streams, n_frames;

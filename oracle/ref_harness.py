@@ -172,3 +172,21 @@ def make_gsc(mic, frameLen=256, angle=None):
     orig = obj.transformer.istft
     obj.transformer.istft = lambda Y: orig(Y[..., None] if Y.ndim == 2 else Y)
     return obj
+
+
+def make_subband_gsc(mic, frameLen=256, angle=None):
+    """Construct the reference ``SubbandGSC`` (beamformer/SubbandGSC.py).  Patch (iv): the module cannot be
+    imported as it stands -- it does ``from DistantSpeech.beamformer.FDGSC import FDGSC, DelayObj`` (:23) and
+    FDGSC.py defines no ``DelayObj`` (SubbandGSC.py defines its own right below, :43) -- so the missing name is
+    injected as a placeholder before the import.  Nothing else is touched."""
+    install()
+    import contextlib
+    import io
+    import DistantSpeech.beamformer.FDGSC as _fdgsc_mod
+
+    if not hasattr(_fdgsc_mod, "DelayObj"):
+        _fdgsc_mod.DelayObj = object
+    from DistantSpeech.beamformer.SubbandGSC import SubbandGSC
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        return SubbandGSC(mic, frameLen=frameLen) if angle is None else SubbandGSC(mic, frameLen=frameLen, angle=angle)

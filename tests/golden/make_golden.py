@@ -173,6 +173,20 @@ def main():
          xi_last=gsc.spp.xi, gamma_last=gsc.spp.gamma, Gpost_last=gsc.spp.G, Gw_last=gsc.G, Phi_yy_last=gsc.spp.Phi_yy,
          Phi_vv_last=gsc.spp.Phi_vv)
 
+    # ---- f1: SubbandGSC (STFT-domain NLMS blocking filters + canceller, McSpp gate), 4 mics, two calls ----
+    xs4 = O.synth_streams(1, geo_g, 256 * 70 + 77, seed0=0x5B6)[0]                              # [4, N] float32
+    sgsc = H.make_subband_gsc(RefMic(arrayType="circular", r=0.032, M=4), 256, angle=[30, 0])
+    n1s = 256 * 40 + 77
+    outs = []
+    for lo, hi in ((0, n1s), (n1s, xs4.shape[1])):
+        with contextlib.redirect_stdout(io.StringIO()):
+            outs.append(sgsc.process(xs4[:, lo:hi].astype(np.float64)))
+    save("subband_gsc.npz", x=xs4, n_first=np.array(n1s), y=np.concatenate([o[0] for o in outs]),
+         fix_output=np.concatenate([o[1] for o in outs]).astype(np.float32),
+         bm_output=np.concatenate([o[2] for o in outs]).astype(np.float32),
+         p=np.concatenate([o[3] for o in outs], axis=1).astype(np.float32),
+         W_aic_last=sgsc.aic_filter.W, W_bm0_last=sgsc.bm[0].W)
+
     # ---- a14: McSpp (CDR-driven prior, complex inverse with SNR-dependent loading), 4 mics ----
     from DistantSpeech.noise_estimation.mcspp import McSpp
     geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=512)

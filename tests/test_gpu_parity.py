@@ -667,3 +667,47 @@ def test_gsc_other_mic_counts(cuda, M):
     ref = O.GscOracle(geo, 256).process(x.astype(np.float64), ang, method=2)
     y = GSC(MicArray(arrayType="circular", r=0.04, M=M), 256).process(x, ang, method=2)["data"]
     assert_wave_parity(ref, y, "GSC M=%d" % M)
+
+
+def test_subband_gsc_golden(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.SubbandGSC import SubbandGSC
+    g = golden("subband_gsc.npz")
+    n1 = int(g["n_first"])
+    sg = SubbandGSC(MicArray(arrayType="circular", r=0.032, M=4), 256, angle=[30, 0])
+    xa, xb = g["x"][:, :n1].copy(), g["x"][:, n1:].copy()
+    ra, rb = sg.process(xa), sg.process(xb)
+    assert len(ra) == 5 and ra[2].shape == (n1, 4) and ra[3].shape[0] == 257
+    err, snr = assert_wave_parity(g["y"], np.concatenate([ra[0], rb[0]]), "SubbandGSC")
+    print("SubbandGSC: max-abs %.2e SNR %.1f dB" % (err, snr))
+    assert np.max(np.abs(np.concatenate([ra[1], rb[1]]) - g["fix_output"])) < 2e-6
+    assert np.max(np.abs(np.concatenate([ra[2], rb[2]]) - g["bm_output"])) < 1e-4
+    assert np.mean(np.abs(np.concatenate([ra[3], rb[3]], axis=1) - g["p"]) > 1e-3) < 0.01
+    rel = np.linalg.norm(sg.aic_filter.W - g["W_aic_last"]) / np.linalg.norm(g["W_aic_last"])
+    assert rel < 1e-3, rel
+    assert np.linalg.norm(sg._bm_W(0) - g["W_bm0_last"]) < 1e-3 * np.linalg.norm(g["W_bm0_last"])
+    assert not np.array_equal(xa, g["x"][:, :n1])                       # the caller's array was DC-notched in place
+    # batch of two streams == singles
+    rb2 = SubbandGSC(MicArray(arrayType="circular", r=0.032, M=4), 256, angle=[30, 0]).process(
+        np.stack([g["x"][:, :n1], g["x"][::-1, :n1]]).copy())
+    assert np.max(np.abs(rb2[0][0] - ra[0])) < 1e-6
+
+
+def test_subband_lms_classes(cuda):
+    """SubbandLMS / SubbandLmsMc block by block (time-domain in and out) against the oracle's filters."""
+    from distantspeech_b200.adaptivefilter.SubbandLMS import SubbandLMS
+    from distantspeech_b200.adaptivefilter.SubbandLmsMc import SubbandLmsMc
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((256 * 12, 3)) * 0.2
+    d = 0.6 * np.roll(x[:, 0], 7) + 0.1 * rng.standard_normal(256 * 12)
+    p = rng.uniform(0.1, 1.0, 257)
+    f1, o1 = SubbandLMS(filter_len=2, num_bands=512, mu=0.1), O.SubbandNlms(2, 512, 1, mu=0.1)
+    f3, o3 = SubbandLmsMc(filter_len=2, num_bands=512, channel=3, mu=0.01, alpha=0.8), O.SubbandNlms(2, 512, 3, mu=0.01, alpha=0.8)
+    for n in range(12):
+        sl = slice(256 * n, 256 * (n + 1))
+        e1, W1 = f1.update(x[sl, 0], d[sl], p=p)
+        e3, W3 = f3.update(x[sl], d[sl], p=p[:, None])
+        r1, r3 = o1.update(x[sl, 0], d[sl], p), o3.update(x[sl], d[sl], p)
+        assert np.max(np.abs(e1 - r1)) < 5e-6 and np.max(np.abs(e3 - r3)) < 5e-6
+    assert W1.shape == (257, 2) and W3.shape == (257, 2, 3)
+    assert np.linalg.norm(W1 - o1.W[:, :, 0]) < 1e-4 * np.linalg.norm(o1.W) and np.linalg.norm(W3 - o3.W) < 1e-4 * np.linalg.norm(o3.W)

@@ -78,3 +78,15 @@ def test_gsc_mcmcra_golden():
     assert np.array_equal(o.spp.p, g["p_last"]) and np.array_equal(o.spp.q, g["q_last"])
     assert np.allclose(o.spp.G, g["Gpost_last"], rtol=1e-13, atol=0) and np.allclose(o.Gw, g["Gw_last"], rtol=1e-12, atol=1e-15)
     assert np.allclose(o.spp.Phi_vv, g["Phi_vv_last"], rtol=1e-13, atol=1e-18)
+
+
+def test_subband_gsc_golden():
+    """f1: SubbandGSC (STFT-domain NLMS blocking filters + canceller gated by McSpp), two calls with a ragged tail."""
+    g = golden("subband_gsc.npz")
+    o = O.SubbandGscOracle(O.MicGeometry("circular", r=0.032, M=4, n_fft=256), 256, np.array([30, 0]) / 180 * np.pi)
+    n1 = int(g["n_first"])
+    x = g["x"].astype(np.float64)
+    a, b = o.process(x[:, :n1]), o.process(x[:, n1:])
+    assert np.max(np.abs(np.concatenate([a[0], b[0]]) - g["y"])) < 1e-12
+    assert np.max(np.abs(np.concatenate([a[2], b[2]]) - g["bm_output"])) < 1e-6
+    assert np.allclose(o.aic.W, g["W_aic_last"], rtol=1e-9, atol=1e-14) and np.allclose(o.bm[0].W[:, :, 0], g["W_bm0_last"], rtol=1e-9, atol=1e-14)

@@ -133,6 +133,17 @@ def main():
     t0 = time.perf_counter(); O.GscOracle(geo8, 256).process(xh, ang, method=2); cpu = 1.0 / (time.perf_counter() - t0)
     out.append({"config": "f1", "what": "frequency-domain GSC + McMcra postfilter 8-mic, %d streams x 10 s (incl. API hand-off)" % Sg,
                 "ms": ms, "audio_s_per_s": Sg * N / FS / (ms / 1e3), "cpu_oracle_1core_audio_s_per_s": cpu})
+    # ---- f1: SubbandGSC (STFT-domain NLMS blocking filters + canceller gated by McSpp), 4 mics ----------------
+    from distantspeech_b200.beamformer.SubbandGSC import SubbandGSC
+    Ss = 128 if small else 1024
+    xs4 = torch.randn((Ss, 4, N), device="cuda") * 0.1
+    sg = SubbandGSC(mic4, 256, angle=[30, 0])
+    ms = timed(lambda: sg.process(xs4), warm=1, reps=2)
+    geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    xh = xs4[0, :, :16000].cpu().numpy().astype(np.float64)
+    t0 = time.perf_counter(); O.SubbandGscOracle(geo4, 256, ang).process(xh); cpu = 1.0 / (time.perf_counter() - t0)
+    out.append({"config": "f1", "what": "SubbandGSC 4-mic, %d streams x 10 s (incl. API hand-off + diagnostics outputs)" % Ss,
+                "ms": ms, "audio_s_per_s": Ss * N / FS / (ms / 1e3), "cpu_oracle_1core_audio_s_per_s": cpu})
     for o in out:
         print(json.dumps(o))
 
