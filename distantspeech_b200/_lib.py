@@ -204,6 +204,11 @@ def _declare(lib):
     lib.ds_dcnotch_run.restype = C.c_int
     lib.ds_channel_mean_run.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ds_channel_mean_run.restype = C.c_int
+    lib.ds_subband_rls_state_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.ds_subband_rls_state_bytes.restype = C.c_size_t
+    lib.ds_subband_rls_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ds_subband_rls_run.restype = C.c_int
     lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_power_run.restype = C.c_int
     lib.ds_spectral_gain_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

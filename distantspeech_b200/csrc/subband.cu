@@ -79,6 +79,115 @@ __global__ void subband_nlms_kernel(NlmsArgs a) {
   blob[(long long)(4 * LC) * K] = P;
 }
 
+// SubbandRLS.update (adaptivefilter/SubbandRLS.py:44-71): per-bin RLS, L frame taps, one input channel.
+//   err = D - conj(W) buf;  k = P buf / (lambda + buf^H P buf);  P = (P - k buf^H P) / lambda;  W += 2 mu conj(err) k
+// state per (stream, bin): W re/im [L], buf re/im [L], P re/im [L*L] (row major); P(0) = I / 1e-3 is written by the
+// host when the state is created.
+struct RlsArgs {
+  double *state;            // [S][NE][K]
+  const float2 *X;          // [S][T][K]
+  const float2 *D;          // [S][T][K]
+  double2 *Err;             // [S][T][K]
+  int S, K, T;
+  double mu, lambda;
+};
+
+template <int L>
+__global__ void subband_rls_kernel(RlsArgs a) {
+  constexpr int NE = 4 * L + 2 * L * L;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)a.S * a.K) return;
+  const int k = (int)(g % a.K), s = (int)(g / a.K), K = a.K;
+  double *blob = a.state + ((long long)s * NE) * K + k;
+  double wr[L], wi[L], br[L], bi[L], Pr[L][L], Pi[L][L];
+#pragma unroll
+  for (int e = 0; e < L; ++e) {
+    wr[e] = blob[(long long)e * K]; wi[e] = blob[(long long)(L + e) * K];
+    br[e] = blob[(long long)(2 * L + e) * K]; bi[e] = blob[(long long)(3 * L + e) * K];
+  }
+#pragma unroll
+  for (int i = 0; i < L; ++i)
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      Pr[i][j] = blob[(long long)(4 * L + i * L + j) * K];
+      Pi[i][j] = blob[(long long)(4 * L + L * L + i * L + j) * K];
+    }
+  const double inv_lambda = 1.0 / a.lambda;
+  for (int t = 0; t < a.T; ++t) {
+#pragma unroll
+    for (int e = L - 1; e >= 1; --e) { br[e] = br[e - 1]; bi[e] = bi[e - 1]; }
+    const long long o = ((long long)s * a.T + t) * K + k;
+    { const float2 v = a.X[o]; br[0] = (double)v.x; bi[0] = (double)v.y; }
+    const float2 dv = a.D[o];
+    double outr = 0.0, outi = 0.0;
+#pragma unroll
+    for (int e = 0; e < L; ++e) {
+      outr = fma(wr[e], br[e], fma(wi[e], bi[e], outr));
+      outi = fma(wr[e], bi[e], fma(-wi[e], br[e], outi));
+    }
+    const double er = (double)dv.x - outr, ei = (double)dv.y - outi;
+    // num = P buf;  den = lambda + buf^H num (complex);  k = num / den
+    double nr[L], ni[L], denr = a.lambda, deni = 0.0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      double sr = 0.0, si = 0.0;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        sr = fma(Pr[i][j], br[j], fma(-Pi[i][j], bi[j], sr));
+        si = fma(Pr[i][j], bi[j], fma(Pi[i][j], br[j], si));
+      }
+      nr[i] = sr; ni[i] = si;
+      denr = fma(br[i], sr, fma(bi[i], si, denr));        // conj(buf_i) num_i
+      deni = fma(br[i], si, fma(-bi[i], sr, deni));
+    }
+    const double d2 = 1.0 / fma(denr, denr, deni * deni);
+    double kr[L], ki[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {                          // num / den
+      kr[i] = fma(nr[i], denr, ni[i] * deni) * d2;
+      ki[i] = fma(ni[i], denr, -nr[i] * deni) * d2;
+    }
+    // v = buf^H P (row vector);  P = (P - k v) / lambda
+    double vr[L], vi[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      double sr = 0.0, si = 0.0;
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        sr = fma(br[i], Pr[i][j], fma(bi[i], Pi[i][j], sr));
+        si = fma(br[i], Pi[i][j], fma(-bi[i], Pr[i][j], si));
+      }
+      vr[j] = sr; vi[j] = si;
+    }
+#pragma unroll
+    for (int i = 0; i < L; ++i)
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        Pr[i][j] = (Pr[i][j] - fma(kr[i], vr[j], -ki[i] * vi[j])) * inv_lambda;
+        Pi[i][j] = (Pi[i][j] - fma(kr[i], vi[j], ki[i] * vr[j])) * inv_lambda;
+      }
+    const double two_mu = 2.0 * a.mu;
+#pragma unroll
+    for (int e = 0; e < L; ++e) {                          // W += 2 mu conj(err) k
+      wr[e] = fma(two_mu, fma(er, kr[e], ei * ki[e]), wr[e]);
+      wi[e] = fma(two_mu, fma(er, ki[e], -ei * kr[e]), wi[e]);
+    }
+    a.Err[o] = make_double2(er, ei);
+  }
+#pragma unroll
+  for (int e = 0; e < L; ++e) {
+    blob[(long long)e * K] = wr[e]; blob[(long long)(L + e) * K] = wi[e];
+    blob[(long long)(2 * L + e) * K] = br[e]; blob[(long long)(3 * L + e) * K] = bi[e];
+  }
+#pragma unroll
+  for (int i = 0; i < L; ++i)
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      blob[(long long)(4 * L + i * L + j) * K] = Pr[i][j];
+      blob[(long long)(4 * L + L * L + i * L + j) * K] = Pi[i][j];
+    }
+}
+
 // FilterDcNotch16.filter_dc_notch16 (adaptivefilter/feature.py:37-49), in place, one thread per (stream, channel);
 // same operation order as dcnotch_kernel in fdgsc.cu, memories in a caller-owned [S][C][2] float64 array.
 __global__ void dcnotch_generic_kernel(float *x, double *mem_all, int SC, int Ns, double radius, double den2) {
@@ -140,6 +249,31 @@ int ds_subband_nlms_run(const ds_subband_nlms_params *p, void *state, const void
     set_error("ds_subband_nlms_run: filter_len %d x n_ch %d is not in the compiled set (taps 1..4 x {1,2,3,4} channels, 1..2 x {6,8})",
               a.L, a.C);
     return DS_EUNSUPPORTED;
+  }
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
+size_t ds_subband_rls_state_bytes(int n_streams, int n_bins, int filter_len) {
+  return (size_t)n_streams * (4 * filter_len + 2 * filter_len * filter_len) * n_bins * sizeof(double);
+}
+
+int ds_subband_rls_run(int n_streams, int n_bins, int n_frames, int filter_len, double mu, double forgetting_factor, void *state,
+                       const void *X, const void *D, void *Err, void *stream) {
+  DS_CHECK_ARG(state && X && D && Err, "ds_subband_rls_run: null argument");
+  DS_CHECK_ARG(n_streams >= 1 && n_bins >= 1 && n_frames >= 1 && forgetting_factor > 0.0, "ds_subband_rls_run: bad shape");
+  RlsArgs a;
+  a.state = (double *)state; a.X = (const float2 *)X; a.D = (const float2 *)D; a.Err = (double2 *)Err;
+  a.S = n_streams; a.K = n_bins; a.T = n_frames; a.mu = mu; a.lambda = forgetting_factor;
+  const long long items = (long long)a.S * a.K;
+  const unsigned blocks = (unsigned)((items + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (filter_len) {
+    case 1: subband_rls_kernel<1><<<blocks, 128, 0, st>>>(a); break;
+    case 2: subband_rls_kernel<2><<<blocks, 128, 0, st>>>(a); break;
+    case 3: subband_rls_kernel<3><<<blocks, 128, 0, st>>>(a); break;
+    case 4: subband_rls_kernel<4><<<blocks, 128, 0, st>>>(a); break;
+    default: set_error("ds_subband_rls_run: filter_len %d outside the compiled range 1..4", filter_len); return DS_EUNSUPPORTED;
   }
   DS_LAUNCH_CHECK();
   return DS_OK;

@@ -340,6 +340,12 @@ size_t ds_subband_nlms_state_bytes(const ds_subband_nlms_params *p);   /* zero =
  *   Err [S][T][F][K] c128                                                                               */
 int ds_subband_nlms_run(const ds_subband_nlms_params *p, void *state, const void *X, const void *D, const double *prob,
                         void *Err, void *stream);
+/* replaces SubbandRLS.update (adaptivefilter/SubbandRLS.py:44-71) over T frames: per-bin RLS, filter_len (1..4) frame
+ * taps, one input channel.  state [S][NE][K] float64: Re W[L] Im W[L] Re buf[L] Im buf[L] Re P[L][L] Im P[L][L]; the caller
+ * initialises P = I / 1e-3 (:38-40), everything else zero.  X, D [S][T][K] c64, Err [S][T][K] c128.                     */
+size_t ds_subband_rls_state_bytes(int n_streams, int n_bins, int filter_len);
+int ds_subband_rls_run(int n_streams, int n_bins, int n_frames, int filter_len, double mu, double forgetting_factor,
+                       void *state, const void *X, const void *D, void *Err, void *stream);
 /* FilterDcNotch16.filter_dc_notch16 (adaptivefilter/feature.py:37-49) in place on x [S][C][n_samples] float32,
  * memories mem [S][C][2] float64 in/out (zero = fresh filter).                                            */
 int ds_dcnotch_run(int n_streams, int n_ch, int n_samples, double radius, double *mem, float *x, void *stream);

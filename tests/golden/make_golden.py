@@ -187,6 +187,16 @@ def main():
          p=np.concatenate([o[3] for o in outs], axis=1).astype(np.float32),
          W_aic_last=sgsc.aic_filter.W, W_bm0_last=sgsc.bm[0].W)
 
+    # ---- f1: SubbandRLS, 2 taps, 14 blocks -------------------------------------------------------------------
+    from DistantSpeech.adaptivefilter.SubbandRLS import SubbandRLS
+    rng = np.random.default_rng(0x715)
+    xr = (rng.standard_normal(256 * 14) * 0.2).astype(np.float32)
+    dr = (0.5 * np.roll(xr, 5) + 0.05 * rng.standard_normal(256 * 14)).astype(np.float32)
+    rls = SubbandRLS(filter_len=2, num_bands=512)
+    errs = [rls.update(xr[256 * n:256 * (n + 1)].astype(np.float64), dr[256 * n:256 * (n + 1)].astype(np.float64))[0]
+            for n in range(14)]
+    save("subband_rls.npz", x=xr, d=dr, err=np.concatenate(errs), W_last=rls.W, P_last=rls.P)
+
     # ---- a14: McSpp (CDR-driven prior, complex inverse with SNR-dependent loading), 4 mics ----
     from DistantSpeech.noise_estimation.mcspp import McSpp
     geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=512)

@@ -711,3 +711,15 @@ def test_subband_lms_classes(cuda):
         assert np.max(np.abs(e1 - r1)) < 5e-6 and np.max(np.abs(e3 - r3)) < 5e-6
     assert W1.shape == (257, 2) and W3.shape == (257, 2, 3)
     assert np.linalg.norm(W1 - o1.W[:, :, 0]) < 1e-4 * np.linalg.norm(o1.W) and np.linalg.norm(W3 - o3.W) < 1e-4 * np.linalg.norm(o3.W)
+
+
+def test_subband_rls_golden(cuda):
+    from distantspeech_b200.adaptivefilter.SubbandRLS import SubbandRLS
+    g = golden("subband_rls.npz")
+    f = SubbandRLS(filter_len=2, num_bands=512)
+    errs = [f.update(g["x"][256 * n:256 * (n + 1)], g["d"][256 * n:256 * (n + 1)])[0] for n in range(14)]
+    assert_wave_parity(g["err"], np.concatenate(errs), "SubbandRLS")
+    assert np.linalg.norm(f.W - g["W_last"]) < 1e-4 * np.linalg.norm(g["W_last"])
+    assert np.linalg.norm(f.P - g["P_last"]) < 1e-4 * np.linalg.norm(g["P_last"])
+    with pytest.raises(ValueError):
+        SubbandRLS(filter_len=5)

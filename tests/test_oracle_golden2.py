@@ -90,3 +90,11 @@ def test_subband_gsc_golden():
     assert np.max(np.abs(np.concatenate([a[0], b[0]]) - g["y"])) < 1e-12
     assert np.max(np.abs(np.concatenate([a[2], b[2]]) - g["bm_output"])) < 1e-6
     assert np.allclose(o.aic.W, g["W_aic_last"], rtol=1e-9, atol=1e-14) and np.allclose(o.bm[0].W[:, :, 0], g["W_bm0_last"], rtol=1e-9, atol=1e-14)
+
+
+def test_subband_rls_golden():
+    g = golden("subband_rls.npz")
+    o = O.SubbandRls(2, 512)
+    x, d = g["x"].astype(np.float64), g["d"].astype(np.float64)
+    err = np.concatenate([o.update(x[256 * n:256 * (n + 1)], d[256 * n:256 * (n + 1)]) for n in range(14)])
+    assert np.array_equal(err, g["err"]) and np.array_equal(o.W, g["W_last"]) and np.array_equal(o.P, g["P_last"])
