@@ -97,6 +97,12 @@ class SubbandNlmsParams(C.Structure):
                 ("mu", C.c_double), ("alpha", C.c_double), ("eps", C.c_double)]
 
 
+class FdafParams(C.Structure):
+    _fields_ = [("frame_len", C.c_int32), ("n_streams", C.c_int32), ("n_ch", C.c_int32), ("n_samples", C.c_int32),
+                ("fir_truncate", C.c_int32), ("non_causal", C.c_int32), ("one_minus_p", C.c_int32), ("reserved", C.c_int32),
+                ("mu", C.c_double), ("alpha", C.c_double)]
+
+
 class AmvdrParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("n_streams", C.c_int32), ("n_mics", C.c_int32), ("n_frames", C.c_int32),
                 ("frm_cnt", C.c_int32), ("ell", C.c_int32), ("mcra_L", C.c_int32), ("method", C.c_int32),
@@ -209,6 +215,12 @@ def _declare(lib):
     lib.ds_subband_rls_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ds_subband_rls_run.restype = C.c_int
+    lib.ds_fdaf_state_bytes.argtypes = [C.c_int, C.c_int]
+    lib.ds_fdaf_state_bytes.restype = C.c_size_t
+    lib.ds_fdaf_run.argtypes = [C.POINTER(FdafParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ds_fdaf_run.restype = C.c_int
+    lib.ds_adjacent_diff_run.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ds_adjacent_diff_run.restype = C.c_int
     lib.ds_power_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_power_run.restype = C.c_int
     lib.ds_spectral_gain_run.argtypes = [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

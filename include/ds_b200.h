@@ -353,6 +353,30 @@ int ds_dcnotch_run(int n_streams, int n_ch, int n_samples, double radius, double
  * x [S][C][n_samples] float64 -> out [S][n_samples] float64.                                              */
 int ds_channel_mean_run(int n_streams, int n_ch, long long n_samples, const double *x, double *out, void *stream);
 
+/* ---- constrained frequency-domain adaptive filter (adaptivefilter/FastFreqLms.py) and TDGSC helpers ---- */
+typedef struct ds_fdaf_params {
+  int32_t frame_len;    /* filter_len = hop_len; compiled for 256 (n_fft 512)           FastFreqLms.py:62-68 */
+  int32_t n_streams;
+  int32_t n_ch;         /* input channels, 1..7 (TDGSC: M - 1)                                               */
+  int32_t n_samples;    /* multiple of frame_len                                                             */
+  int32_t fir_truncate; /* taps zeroed at both ends after each update (:238-243); < 0 = None                 */
+  int32_t non_causal;   /* 1: desired signal delayed by frame_len / 2 (:80-81, :156-157)                     */
+  int32_t one_minus_p;  /* 1: the gate is 1 - prob (TDGSC.py:157)                                            */
+  int32_t reserved;
+  double mu;            /* 0.01                                                                   :55        */
+  double alpha;         /* 0.9 power smoothing                                                    :58        */
+} ds_fdaf_params;
+size_t ds_fdaf_state_bytes(int n_streams, int n_ch);          /* float32 state, zero = fresh filter */
+/* replaces FastFreqLms.update (FastFreqLms.py:203-245, base class: gradient constraint, factor 2, optional tap
+ * truncation) over all blocks of a call:
+ *   x [S][C][N] float32 inputs, d [S][N] float32 desired, prob [S][N/frame_len][257] float64 per-bin gate or NULL (1),
+ *   e [S][N] float32 error output                                                                             */
+int ds_fdaf_run(const ds_fdaf_params *p, void *state, const float *x, const float *d, const double *prob, float *e,
+                void *stream);
+/* the fixed blocking matrix of TDGSC (TDGSC.py:77-81): out[c] = x[c] - x[c + 1];
+ * x [S][C][n_samples] float64 -> out [S][C-1][n_samples] float32                                              */
+int ds_adjacent_diff_run(int n_streams, int n_ch, long long n_samples, const double *x, float *out, void *stream);
+
 /* ---- postfilter gains ------------------------------------------------------ */
 typedef struct ds_omlsa_multi_params {
   int32_t n_bins, n_streams, n_frames;

@@ -197,6 +197,20 @@ def main():
             for n in range(14)]
     save("subband_rls.npz", x=xr, d=dr, err=np.concatenate(errs), W_last=rls.W, P_last=rls.P)
 
+    # ---- f1: TDGSC (fixed blocking matrix + constrained FDAF canceller), 4 mics, two calls with a ragged tail ----
+    from DistantSpeech.beamformer.TDGSC import TDGSC
+    xt4 = np.ascontiguousarray(O.synth_streams(1, geo_g, 256 * 70 + 50, seed0=0x7D6)[0].T)       # [N, 4] float32
+    with contextlib.redirect_stdout(io.StringIO()):
+        td = TDGSC(RefMic(arrayType="circular", r=0.032, M=4), frameLen=256, angle=[30, 0])
+    n1t = 256 * 40 + 50
+    touts = []
+    for lo, hi in ((0, n1t), (n1t, xt4.shape[0])):
+        with contextlib.redirect_stdout(io.StringIO()):
+            touts.append(td.process(xt4[lo:hi].astype(np.float64)))
+    save("tdgsc.npz", x=xt4, n_first=np.array(n1t), y=np.concatenate([o[0] for o in touts]),
+         p=np.concatenate([o[1] for o in touts], axis=1).astype(np.float32),
+         bm_output=np.concatenate([o[2] for o in touts]).astype(np.float32), W_last=td.aic_filter.W)
+
     # ---- a14: McSpp (CDR-driven prior, complex inverse with SNR-dependent loading), 4 mics ----
     from DistantSpeech.noise_estimation.mcspp import McSpp
     geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=512)

@@ -723,3 +723,25 @@ def test_subband_rls_golden(cuda):
     assert np.linalg.norm(f.P - g["P_last"]) < 1e-4 * np.linalg.norm(g["P_last"])
     with pytest.raises(ValueError):
         SubbandRLS(filter_len=5)
+
+
+def test_tdgsc_golden(cuda):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.TDGSC import TDGSC
+    g = golden("tdgsc.npz")
+    n1 = int(g["n_first"])
+    td = TDGSC(MicArray(arrayType="circular", r=0.032, M=4), frameLen=256, angle=[30, 0])
+    ra, rb = td.process(g["x"][:n1].copy()), td.process(g["x"][n1:].copy())
+    assert len(ra) == 3 and ra[2].shape == (n1, 3) and ra[1].shape[0] == 257
+    err, snr = assert_wave_parity(g["y"], np.concatenate([ra[0], rb[0]]), "TDGSC")
+    print("TDGSC: max-abs %.2e SNR %.1f dB" % (err, snr))
+    assert np.max(np.abs(np.concatenate([ra[2], rb[2]]) - g["bm_output"])) < 2e-6
+    assert np.mean(np.abs(np.concatenate([ra[1], rb[1]], axis=1) - g["p"]) > 1e-6) < 0.01
+    assert np.linalg.norm(td.aic_filter.W - g["W_last"]) < 1e-3 * np.linalg.norm(g["W_last"])
+    # other microphone counts against the oracle; batch == singles
+    geo = O.MicGeometry("linear", r=0.04, M=6, n_fft=256)
+    x6 = np.ascontiguousarray(O.synth_streams(2, geo, 256 * 40, look_deg=(75.0, 0.0), seed0=61).transpose(0, 2, 1))
+    ang = np.array([75, 0]) / 180 * np.pi
+    yb = TDGSC(MicArray(arrayType="linear", r=0.04, M=6), frameLen=256, angle=[75, 0]).process(x6.copy())[0]
+    for s in range(2):
+        assert_wave_parity(O.TdgscOracle(geo, 256, ang).process(x6[s].astype(np.float64))[0], yb[s], "TDGSC 6 mics stream %d" % s)

@@ -98,3 +98,13 @@ def test_subband_rls_golden():
     x, d = g["x"].astype(np.float64), g["d"].astype(np.float64)
     err = np.concatenate([o.update(x[256 * n:256 * (n + 1)], d[256 * n:256 * (n + 1)]) for n in range(14)])
     assert np.array_equal(err, g["err"]) and np.array_equal(o.W, g["W_last"]) and np.array_equal(o.P, g["P_last"])
+
+
+def test_tdgsc_golden():
+    g = golden("tdgsc.npz")
+    o = O.TdgscOracle(O.MicGeometry("circular", r=0.032, M=4, n_fft=256), 256, np.array([30, 0]) / 180 * np.pi)
+    n1 = int(g["n_first"])
+    x = g["x"].astype(np.float64)
+    a, b = o.process(x[:n1]), o.process(x[n1:])
+    assert np.max(np.abs(np.concatenate([a[0], b[0]]) - g["y"])) < 1e-12
+    assert np.allclose(o.W, g["W_last"], rtol=1e-9, atol=1e-14)

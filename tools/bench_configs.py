@@ -144,6 +144,15 @@ def main():
     t0 = time.perf_counter(); O.SubbandGscOracle(geo4, 256, ang).process(xh); cpu = 1.0 / (time.perf_counter() - t0)
     out.append({"config": "f1", "what": "SubbandGSC 4-mic, %d streams x 10 s (incl. API hand-off + diagnostics outputs)" % Ss,
                 "ms": ms, "audio_s_per_s": Ss * N / FS / (ms / 1e3), "cpu_oracle_1core_audio_s_per_s": cpu})
+    # ---- f1: TDGSC (fixed blocking matrix + constrained FDAF canceller), 4 mics -----------------------------------
+    from distantspeech_b200.beamformer.TDGSC import TDGSC
+    xt = torch.randn((Ss, N, 4), device="cuda") * 0.1
+    td = TDGSC(mic4, frameLen=256, angle=[30, 0])
+    ms = timed(lambda: td.process(xt), warm=1, reps=2)
+    xh = xt[0, :16000].cpu().numpy().astype(np.float64)
+    t0 = time.perf_counter(); O.TdgscOracle(geo4, 256, ang).process(xh); cpu = 1.0 / (time.perf_counter() - t0)
+    out.append({"config": "f1", "what": "TDGSC 4-mic, %d streams x 10 s (incl. API hand-off + diagnostics outputs)" % Ss,
+                "ms": ms, "audio_s_per_s": Ss * N / FS / (ms / 1e3), "cpu_oracle_1core_audio_s_per_s": cpu})
     for o in out:
         print(json.dumps(o))
 
