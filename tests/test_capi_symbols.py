@@ -56,3 +56,41 @@ def test_no_cpu_fallback():
     from distantspeech_b200.transform.transform import Transform
     with pytest.raises(_lib.DsError):
         Transform(n_fft=256, hop_length=128).stft(np.zeros(1024))
+
+
+def test_argument_validation_precedes_any_device_work():
+    """Every *_run rejects null pointers / unsupported shapes with DS_EINVAL / DS_EUNSUPPORTED and a message before it
+    touches the device -- so this runs without a GPU."""
+    from distantspeech_b200 import _lib
+    lib = _lib.lib()
+    lib.ds_last_error.restype = ctypes.c_char_p
+    null = ctypes.c_void_p(0)
+    dummy = (ctypes.c_double * 4)()
+    one = ctypes.cast(dummy, ctypes.c_void_p)
+    EINVAL, EUNSUP = -1, -2
+
+    sp = _lib.StftParams(512, 256, 1, 1, 4096, _lib.DS_STFT_STREAMING, 0, 0)
+    assert lib.ds_stft_run(ctypes.byref(sp), null, null, null, null, null) == EINVAL and b"null" in lib.ds_last_error()
+    sp.hop = 1024                                                            # hop > n_fft
+    assert lib.ds_stft_run(ctypes.byref(sp), one, one, one, one, null) == EINVAL and b"hop" in lib.ds_last_error()
+    sp.hop, sp.n_fft = 250, 500                                              # not a power of two
+    assert lib.ds_stft_run(ctypes.byref(sp), one, one, one, one, null) == EUNSUP and b"n_fft" in lib.ds_last_error()
+    ip = _lib.IstftParams(512, 256, 1, 1, 4, 1, 0, 0, 1.0)                   # DS_STFT_CENTER is not a synthesis mode
+    assert lib.ds_istft_run(ctypes.byref(ip), one, one, one, one, null) == EINVAL
+
+    mp = _lib.McsppParams()
+    lib.ds_mcspp_default_params(ctypes.byref(mp), 512, 1, 9, 4)              # 9 microphones: outside 2..8
+    assert lib.ds_mcspp_run(ctypes.byref(mp), one, null, one, 0, null, 0, None, null) == EUNSUP
+    cp = _lib.McsppCdrParams()
+    lib.ds_mcspp_cdr_default_params(ctypes.byref(cp), 512, 1, 8, 4)          # McSpp needs 4 channels
+    assert lib.ds_mcspp_cdr_run(ctypes.byref(cp), one, one, one, one, 0, null, None, null) == EUNSUP
+    assert b"n_mics must be 4" in lib.ds_last_error()
+    gp = _lib.GscParams()
+    lib.ds_gsc_default_params(ctypes.byref(gp), 256, 1, 4, 4)
+    assert lib.ds_gsc_run(ctypes.byref(gp), one, null, one, 0, one, None, null) == EINVAL     # output without propagation vectors
+    fp = _lib.FdafParams(128, 1, 3, 1024, 30, 1, 1, 0, 0.01, 0.9)            # frame_len 128 is not compiled
+    assert lib.ds_fdaf_run(ctypes.byref(fp), one, one, one, null, one, null) == EUNSUP
+    np_ = _lib.SubbandNlmsParams(257, 1, 1, 4, 5, 4, 0, 0, 0.1, 0.9, 1e-4)   # 4 taps x 5 channels: not compiled
+    assert lib.ds_subband_nlms_run(ctypes.byref(np_), one, one, one, null, one, null) == EUNSUP
+    assert lib.ds_srp_run(10, 4, 5, 513, 48000.0, 1024, one, one, null, one, 1, null) == EUNSUP   # tensor path: 4, 8, 16 mics
+    assert lib.ds_srp_workspace_bytes(937, 16, 513, 1) == 513 * 15 * 128 * 32 * 4 and lib.ds_srp_workspace_bytes(937, 16, 513, 0) == 0
