@@ -1,0 +1,1 @@
+"""Device-backed counterparts of DistantSpeech/transform (see DESIGN.md for the reference file:line map)."""
