@@ -6,8 +6,9 @@ ISTFT all run on the device.  ``process(x [M, N], angle_rad, method)`` returns `
 
 Notes on the reference: ``GSC.process`` ends with ``self.transformer.istft(Y)`` on a 2-D ``[K, T]`` array (:289),
 which ``Transform.istft`` reads as one frame x channels and rejects -- the call only works with the array lifted
-to ``[K, T, 1]`` (what the oracle harness does); this class implements that intended behaviour.  The time-domain
-``process1`` (FastFreqLms path) and WNG / DI (``calcWNG`` / ``calcDI`` do not exist in the reference) are not built.
+to ``[K, T, 1]`` (what the oracle harness does); this class implements that intended behaviour.  ``process1`` is the
+time-domain variant (alignment, mean beam, pairwise-difference blocking matrix, constrained FDAF canceller,
+GSC.py:151-172).  WNG / DI are not built (``calcWNG`` / ``calcDI`` do not exist in the reference either).
 Extension: a leading stream axis ``x [S, M, N]``.
 """
 import numpy as np
@@ -35,6 +36,15 @@ class GSC(beamformer):
         self.BM = np.zeros((self.M, self.M - 1, self.half_bin), dtype=complex)
         self._hist = None
         self._tail = None
+
+    def process1(self, x):
+        """Time-domain GSC (GSC.py:151-172): x [samples, chs] (or [S, samples, chs]) -> output [samples]; the input is
+        DC-notched in place.  Same chain as TDGSC without the MCRA gate and without the non-causal delay."""
+        from .TDGSC import TDGSC
+        if getattr(self, "_td", None) is None:
+            self._td = TDGSC(self.mic_array, frameLen=self.frameLen, angle=self.angle)
+            self._td._gated, self._td._non_causal = False, False
+        return self._td.process(x)[0]
 
     @property
     def G(self):

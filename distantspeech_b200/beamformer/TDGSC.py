@@ -51,6 +51,7 @@ class TDGSC(beamformer):
         self.mcra.L = 65
         self.spp = self.mcra
         self.mu, self.alpha, self.fir_truncate = 0.01, 0.9, 30
+        self._gated, self._non_causal = True, True        # GSC.process1 runs the same chain ungated and causal
         self._st = None
         self.aic_filter = _CancellerView(self)
 
@@ -125,17 +126,22 @@ class TDGSC(beamformer):
             bm = t.empty((S, M - 1, Nb), dtype=t.float32, device="cuda")
             L.check(lib.ds_adjacent_diff_run(S, M, Nb, L.ptr(aligned), L.ptr(bm), sp), "ds_adjacent_diff_run")
             fbf32 = fbf.float()
-            win = L.device_window(_sqrt_hann(2 * Lf), 2 * Lf)
-            D = stft_device(fbf32[:, None, :].contiguous(), 2 * Lf, Lf, win, L.DS_STFT_STREAMING, history=st["h_fbf"])   # [S, T, 1, K]
-            pw = L.spectral_power(D[:, :, 0, :].to(t.complex128), via_abs=True)                                           # [S, T, K]
-            _, p = self.mcra._run(pw, want_p=True)                                                                                     # [S, T, K]
+            p = None
+            if self._gated:
+                win = L.device_window(_sqrt_hann(2 * Lf), 2 * Lf)
+                D = stft_device(fbf32[:, None, :].contiguous(), 2 * Lf, Lf, win, L.DS_STFT_STREAMING, history=st["h_fbf"])   # [S, T, 1, K]
+                pw = L.spectral_power(D[:, :, 0, :].to(t.complex128), via_abs=True)                                       # [S, T, K]
+                _, p = self.mcra._run(pw, want_p=True)                                                                    # [S, T, K]
+                p = p.contiguous()
             e = t.empty((S, Nb), dtype=t.float32, device="cuda")
-            prm = L.FdafParams(Lf, S, M - 1, Nb, int(self.fir_truncate), 1, 1, 0, float(self.mu), float(self.alpha))
-            L.check(lib.ds_fdaf_run(C.byref(prm), L.ptr(st["fdaf"]), L.ptr(bm), L.ptr(fbf32.contiguous()), L.ptr(p.contiguous()),
-                                    L.ptr(e), sp), "ds_fdaf_run")
+            prm = L.FdafParams(Lf, S, M - 1, Nb, int(self.fir_truncate), int(self._non_causal), int(self._gated), 0,
+                               float(self.mu), float(self.alpha))
+            L.check(lib.ds_fdaf_run(C.byref(prm), L.ptr(st["fdaf"]), L.ptr(bm), L.ptr(fbf32.contiguous()), L.ptr(p), L.ptr(e), sp),
+                    "ds_fdaf_run")
             out[:, :Nb] = e.double()
             out_bm[:, :Nb] = bm.permute(0, 2, 1).double()
-            p_out = p.permute(0, 2, 1)
+            if p is not None:
+                p_out = p.permute(0, 2, 1)
         outs = [out, p_out, out_bm]
         if not batched:
             outs = [o[0] for o in outs]

@@ -738,6 +738,14 @@ def test_tdgsc_golden(cuda):
     assert np.max(np.abs(np.concatenate([ra[2], rb[2]]) - g["bm_output"])) < 2e-6
     assert np.mean(np.abs(np.concatenate([ra[1], rb[1]], axis=1) - g["p"]) > 1e-6) < 0.01
     assert np.linalg.norm(td.aic_filter.W - g["W_last"]) < 1e-3 * np.linalg.norm(g["W_last"])
+    # GSC.process1: the same chain ungated and causal (GSC.py:151-172)
+    from distantspeech_b200.beamformer.GSC import GSC
+    geo4 = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    o1 = O.TdgscOracle(geo4, 256, np.array([30, 0]) / 180 * np.pi, gated=False, non_causal=False)
+    g1 = GSC(MicArray(arrayType="circular", r=0.032, M=4), 256, angle=[30, 0])
+    y1 = np.concatenate([g1.process1(g["x"][:n1].copy()), g1.process1(g["x"][n1:].copy())])
+    r1 = np.concatenate([o1.process(g["x"][:n1].astype(np.float64))[0], o1.process(g["x"][n1:].astype(np.float64))[0]])
+    assert_wave_parity(r1, y1, "GSC.process1")
     # other microphone counts against the oracle; batch == singles
     geo = O.MicGeometry("linear", r=0.04, M=6, n_fft=256)
     x6 = np.ascontiguousarray(O.synth_streams(2, geo, 256 * 40, look_deg=(75.0, 0.0), seed0=61).transpose(0, 2, 1))
