@@ -93,7 +93,7 @@ class GscTaps(C.Structure):
 
 class SubbandNlmsParams(C.Structure):
     _fields_ = [("n_bins", C.c_int32), ("n_streams", C.c_int32), ("n_filters", C.c_int32), ("n_frames", C.c_int32),
-                ("n_ch", C.c_int32), ("filter_len", C.c_int32), ("one_minus_p", C.c_int32), ("reserved", C.c_int32),
+                ("n_ch", C.c_int32), ("filter_len", C.c_int32), ("one_minus_p", C.c_int32), ("plain_lms", C.c_int32),
                 ("mu", C.c_double), ("alpha", C.c_double), ("eps", C.c_double)]
 
 

@@ -12,8 +12,6 @@ from ..transform.transform import _sqrt_hann, stft_device, istft_device
 class SubbandAF(object):
     def __init__(self, filter_len=2, num_bands=512, mu=0.1, normalization=True, alpha=0.9, m=2, hop_length=None,
                  input_td=False, channel=1):
-        if not normalization:
-            raise NotImplementedError("normalization=False (plain LMS, SubbandLMS.py:77) is not built")
         self.filter_len = filter_len
         self.num_bands = num_bands
         self.half_band = int(num_bands / 2) + 1
@@ -30,7 +28,7 @@ class SubbandAF(object):
 
     # ---- device state: [S][F=1][NE][K] float64 ---------------------------------------------
     def _params(self, S, T, one_minus_p=0, eps=1e-4):
-        p = L.SubbandNlmsParams(self.half_band, S, 1, T, self.M, self.filter_len, int(one_minus_p), 0,
+        p = L.SubbandNlmsParams(self.half_band, S, 1, T, self.M, self.filter_len, int(one_minus_p), int(not self.norm),
                                 float(self.mu_value), float(self.alpha), float(eps))
         return p
 

@@ -18,7 +18,7 @@ struct NlmsArgs {
   const float2 *D;          // [S][T][F][K]
   const double *p;          // [S][T][K] or null (p = 1)
   double2 *Err;             // [S][T][F][K]
-  int S, F, K, T, C, L, one_minus_p;
+  int S, F, K, T, C, L, one_minus_p, plain_lms;
   double mu, alpha, eps;
 };
 // state per (stream, filter, bin): W re/im [L*C], buf re/im [L*C] (newest tap first), P
@@ -62,8 +62,11 @@ __global__ void subband_nlms_kernel(NlmsArgs a) {
       pw = fma(br[e], br[e], fma(bi[e], bi[e], pw));
     }
     const double er = (double)dv.x - outr * pk, ei = (double)dv.y - outi * pk;
-    P = a.alpha * P + om_alpha * pw / (double)C;
-    const double step = 2.0 * a.mu * pk / (P + a.eps);
+    double step = 2.0 * a.mu * pk;
+    if (!a.plain_lms) {                               // normalization=True (default)          SubbandLMS.py:69-75
+      P = a.alpha * P + om_alpha * pw / (double)C;
+      step /= (P + a.eps);
+    }
 #pragma unroll
     for (int e = 0; e < LC; ++e) {                    // W += step * buf * conj(err)
       wr[e] = fma(step, fma(br[e], er, bi[e] * ei), wr[e]);
@@ -235,7 +238,7 @@ int ds_subband_nlms_run(const ds_subband_nlms_params *p, void *state, const void
   NlmsArgs a;
   a.state = (double *)state; a.X = (const float2 *)X; a.D = (const float2 *)D; a.p = prob; a.Err = (double2 *)Err;
   a.S = p->n_streams; a.F = p->n_filters; a.K = p->n_bins; a.T = p->n_frames; a.C = p->n_ch; a.L = p->filter_len;
-  a.one_minus_p = p->one_minus_p; a.mu = p->mu; a.alpha = p->alpha; a.eps = p->eps;
+  a.one_minus_p = p->one_minus_p; a.plain_lms = p->plain_lms; a.mu = p->mu; a.alpha = p->alpha; a.eps = p->eps;
   const long long items = (long long)a.S * a.F * a.K;
   const unsigned blocks = (unsigned)((items + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;

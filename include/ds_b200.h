@@ -328,7 +328,7 @@ typedef struct ds_subband_nlms_params {
   int32_t n_ch;        /* C input channels per filter (SubbandLMS: 1, SubbandLmsMc: channel)      */
   int32_t filter_len;  /* frame taps per bin (2 in SubbandGSC)                                    */
   int32_t one_minus_p; /* 1: gate with 1 - p (the canceller, SubbandGSC.py:236)                   */
-  int32_t reserved;
+  int32_t plain_lms;   /* 1: normalization=False, grad = buf conj(err) without the power term (:77) */
   double mu;    /* step: W += 2 mu p grad                            SubbandAF.py:84-87           */
   double alpha; /* power smoothing (0.9 default, 0.8 canceller)      SubbandLMS.py:70-74          */
   double eps;   /* 1e-4 regulariser (the `alpha` argument of update) SubbandLMS.py:75            */

@@ -709,6 +709,10 @@ def test_subband_lms_classes(cuda):
         e3, W3 = f3.update(x[sl], d[sl], p=p[:, None])
         r1, r3 = o1.update(x[sl, 0], d[sl], p), o3.update(x[sl], d[sl], p)
         assert np.max(np.abs(e1 - r1)) < 5e-6 and np.max(np.abs(e3 - r3)) < 5e-6
+    fl, ol = SubbandLMS(filter_len=3, num_bands=512, mu=0.002, normalization=False), O.SubbandNlms(3, 512, 1, mu=0.002, normalization=False)
+    for n in range(12):
+        sl = slice(256 * n, 256 * (n + 1))
+        assert np.max(np.abs(fl.update(x[sl, 0], d[sl])[0] - ol.update(x[sl, 0], d[sl], np.ones(257)))) < 5e-6
     assert W1.shape == (257, 2) and W3.shape == (257, 2, 3)
     assert np.linalg.norm(W1 - o1.W[:, :, 0]) < 1e-4 * np.linalg.norm(o1.W) and np.linalg.norm(W3 - o3.W) < 1e-4 * np.linalg.norm(o3.W)
 
