@@ -1,0 +1,101 @@
+"""LIVE pinning of the oracle: the NumPy restatement (oracle/np_oracle.py) against the UNMODIFIED reference imported from
+/root/reference through oracle/ref_harness.py, on fresh random inputs (the committed fixtures in tests/golden were made the
+same way).  Runs only where the reference tree exists (the build container); skipped on the GPU box."""
+import contextlib
+import io
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+from oracle import ref_harness as H
+
+pytestmark = [pytest.mark.skipif(not H.reference_available(), reason="reference tree not present"),
+              pytest.mark.filterwarnings("ignore")]
+warnings.filterwarnings("ignore")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    H.install()
+    return H
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def test_transform_and_mcra_live(ref):
+    from DistantSpeech.transform.transform import Transform, stft, istft
+    from DistantSpeech.noise_estimation.mcra import NoiseEstimationMCRA
+    rng = np.random.default_rng(101)
+    x = rng.standard_normal((256 * 20, 3)) * 0.2
+    tr, to = Transform(n_fft=512, hop_length=256, channel=3), O.Transform(channel=3, n_fft=512, hop_length=256)
+    for lo, hi in ((0, 256 * 7), (256 * 7, 256 * 20)):
+        Yr, Yo = tr.stft(x[lo:hi]), to.stft(x[lo:hi])
+        assert np.array_equal(Yr, Yo)
+        assert np.array_equal(tr.istft(Yr), to.istft(Yo))
+    w = O.sqrt_hann(512)
+    D = stft(x[:, 0], n_fft=512, hop_length=128, window=w, center=True)
+    assert np.array_equal(D, O.stft(x[:, 0], n_fft=512, hop_length=128, window=w, center=True))
+    assert np.array_equal(istft(D, hop_length=128, window=w, center=True, length=4000),
+                          O.istft(D, hop_length=128, window=w, center=True, length=4000))
+    mr, mo = NoiseEstimationMCRA(nfft=512), O.Mcra(nfft=512)
+    P = np.abs(Yr[:, :, 0]) ** 2
+    for n in range(P.shape[1]):
+        assert np.array_equal(mr.estimation(P[:, n]), mo.estimation(P[:, n])) and np.array_equal(mr.p, mo.p)
+
+
+def test_chain_b_and_mcspp_live(ref):
+    from DistantSpeech.transform.transform import Transform
+    from DistantSpeech.noise_estimation.mcspp_base import McSppBase
+    from DistantSpeech.noise_estimation.mcspp import McSpp
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    x = O.synth_streams(1, geo, 256 * 40, seed0=202)[0].T.astype(np.float64)
+    D = Transform(n_fft=512, hop_length=256, channel=8).stft(x)
+    er, eo = McSppBase(nfft=512, channels=8), O.McSppBase(nfft=512, channels=8)
+    for n in range(D.shape[1]):
+        pr, po = er.estimation(D[:, n, :]), eo.estimation(D[:, n, :])
+        assert np.allclose(pr, po, rtol=1e-9, atol=1e-12)
+    assert np.allclose(er.Phi_vv, eo.Phi_vv, rtol=1e-9, atol=1e-15)
+    with _quiet():
+        cr = McSpp(nfft=512, channels=4)
+    co = O.McSpp(nfft=512, channels=4)
+    for n in range(D.shape[1]):
+        assert np.array_equal(cr.estimation(D[:, n, :4]), co.estimation(D[:, n, :4]))
+    assert np.array_equal(cr.w, co.w)
+
+
+def test_gsc_family_live(ref):
+    from DistantSpeech.beamformer.MicArray import MicArray
+    from DistantSpeech.beamformer.TDGSC import TDGSC
+    geo = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    mic = MicArray(arrayType="circular", r=0.032, M=4)
+    ang = np.array([30, 0]) / 180 * np.pi
+    x = O.synth_streams(1, geo, 256 * 24 + 33, seed0=303)[0].astype(np.float64)          # [M, N]
+    g = H.make_gsc(mic, 256)
+    assert np.max(np.abs(g.process(x.copy(), ang, method=2)["data"] - O.GscOracle(geo, 256).process(x, ang, method=2))) < 1e-12
+    sg = H.make_subband_gsc(mic, 256, angle=[30, 0])
+    with _quiet():
+        r = sg.process(x.copy())
+    o = O.SubbandGscOracle(geo, 256, ang).process(x)
+    assert np.max(np.abs(r[0] - o[0])) < 1e-12 and np.max(np.abs(r[2] - o[2])) < 1e-12
+    with _quiet():
+        td = TDGSC(mic, frameLen=256, angle=[30, 0])
+        rt = td.process(x.T.copy())
+    ot = O.TdgscOracle(geo, 256, ang).process(x.T)
+    assert np.max(np.abs(rt[0] - ot[0])) < 1e-12
+
+
+def test_fdgsc_live(ref):
+    from DistantSpeech.beamformer.MicArray import MicArray
+    from DistantSpeech.beamformer.FDGSC import FDGSC
+    geo = O.MicGeometry("linear", r=0.05, M=6, n_fft=256)
+    x = O.synth_streams(1, geo, 256 * 20, look_deg=(60.0, 0.0), seed0=404)[0].T.astype(np.float64)
+    for post in (False, True):
+        with _quiet():
+            fd = FDGSC(MicArray(arrayType="linear", r=0.05, M=6), frameLen=256, angle=[60, 0])
+            r = fd.process(x.copy(), postfilter=post, dc_notch=True)
+        o = O.FdgscOracle(geo, 256, np.array([60, 0]) / 180 * np.pi).process(x, postfilter=post)
+        assert np.max(np.abs(r[0] - o[0])) < 1e-9
