@@ -188,12 +188,14 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     val, cores, sample = cpu_baseline(args.cpu_streams_per_core, args.cpu_seconds, repeats=max(1, min(args.steps, 3)))
+    step_audio = cores * args.cpu_streams_per_core * (int(args.cpu_seconds * FS) // HOP * HOP) / FS
     line = {
         "impl": "reference", "metric": "audio-s/s (x realtime) for 8-mic MVDR+postfilter chain", "value": val,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": step_audio / val * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "configs[3]: MVDR + McSppBase + OMLSA chain, 8-mic circular r=0.05 16 kHz, n_fft 512 hop 256",
+                   "step": "one bounded sample of the workload: %s (best of up to 3 repeats)" % sample,
                    "note": "reference CPU path = numpy oracle port (the reference is Python and cannot travel to the GPU box)"},
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
