@@ -236,6 +236,13 @@ def _declare(lib):
     lib.ds_mcspp_cdr_run.restype = C.c_int
     lib.ds_mcspp_cdr_export.argtypes = [C.POINTER(McsppCdrParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.ds_mcspp_cdr_export.restype = C.c_int
+    lib.ds_masked_cov_run.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, dbl, vp, vp, vp]
+    lib.ds_steering_run.argtypes = [C.c_longlong, i32, vp, vp, vp]
+    lib.ds_gev_run.argtypes = [C.c_longlong, i32, vp, vp, vp, vp]
+    lib.ds_phase_correction_run.argtypes = [i32, i32, i32, vp, vp]
+    lib.ds_ban_run.argtypes = [C.c_longlong, i32, vp, vp, dbl, vp, vp]
+    lib.ds_mvdr_from_cov_run.argtypes = [C.c_longlong, i32, vp, vp, vp, vp]
+    lib.ds_apply_stream_weights_run.argtypes = [i32, i32, i32, i32, vp, i32, vp, vp, vp]
     lib.ds_chain_state_bytes.argtypes = [C.POINTER(ChainParams)]
     lib.ds_chain_state_bytes.restype = C.c_size_t
     lib.ds_chain_workspace_bytes.argtypes = [C.POINTER(ChainParams)]

@@ -1,6 +1,7 @@
 """Beamformer base class and weight helpers -- drop-in for
 ``DistantSpeech/beamformer/beamformer.py`` (compute_mvdr_weight :133,
-compute_pmwf_weight :100, update_psd :158, update_csd :182, class beamformer :218).
+compute_pmwf_weight :100, update_psd :158, update_csd :182, class beamformer :218;
+steering :10, blind_analytic_normalization :34, phase_correction :64, get_gev_vector :77).
 
 Geometry, steering vectors, the one-off fixed-weight design and the plotting
 diagnostics are host-side NumPy precompute;
@@ -93,6 +94,115 @@ def update_csd(Z, Pxij, alpha=0.8):
             Pxij[:, t] = alpha * Pxij[:, t] + (1 - alpha) * (Z[:, i] * Z[:, j].conj())
             t = t + 1
     return Pxij
+
+
+# ---------------------------------------------------------------------------
+# data-driven steering, GEV weights (example/mvdr.ipynb cells 2-8)
+# ---------------------------------------------------------------------------
+def steering(XXs):
+    """Steering vector (rank 1) = principal eigenvector of the spatial correlation matrix, phase
+    referenced to sensor 0 (beamformer.py:10-31).  XXs [bins, M, M] (any leading axes) -> [bins, M].
+    Like ``np.linalg.eigh`` only the lower triangle is read."""
+    t = L.require_cuda()
+    as_torch = isinstance(XXs, t.Tensor)
+    X = _c128_dev(XXs)
+    M = X.shape[-1]
+    if X.dim() < 2 or X.shape[-2] != M:
+        raise ValueError("steering: expected [..., M, M], got %s" % (tuple(X.shape),))
+    lead = X.shape[:-2]
+    X2 = X.reshape(-1, M, M)
+    out = t.empty((X2.shape[0], M), dtype=t.complex128, device="cuda")
+    L.check(L.lib().ds_steering_run(X2.shape[0], M, L.ptr(X2), L.ptr(out), L.stream_ptr()), "ds_steering_run")
+    out = out.reshape(*lead, M)
+    return out if as_torch else out.cpu().numpy()
+
+
+def get_gev_vector(target_psd_matrix, noise_psd_matrix):
+    """GEV beamforming vectors (beamformer.py:77-97): last generalised eigenvector of
+    (target, noise) per bin, scipy.linalg.eigh normalisation (w^H noise w = 1).  [bins, M, M] x2
+    (any leading axes) -> [bins, M].  The phase LAPACK leaves open is fixed here (see
+    include/ds_b200.h, ds_gev_run): equal to the reference up to a sign per bin."""
+    t = L.require_cuda()
+    as_torch = isinstance(target_psd_matrix, t.Tensor)
+    A = _c128_dev(target_psd_matrix)
+    B = _c128_dev(noise_psd_matrix)
+    if A.shape != B.shape or A.dim() < 2 or A.shape[-1] != A.shape[-2]:
+        raise ValueError("get_gev_vector: shapes %s / %s" % (tuple(A.shape), tuple(B.shape)))
+    M = A.shape[-1]
+    lead = A.shape[:-2]
+    A2, B2 = A.reshape(-1, M, M), B.reshape(-1, M, M)
+    out = t.empty((A2.shape[0], M), dtype=t.complex128, device="cuda")
+    L.check(L.lib().ds_gev_run(A2.shape[0], M, L.ptr(A2), L.ptr(B2), L.ptr(out), L.stream_ptr()), "ds_gev_run")
+    out = out.reshape(*lead, M)
+    return out if as_torch else out.cpu().numpy()
+
+
+def phase_correction(vector):
+    """Rotate each bin's beamforming vector onto the previous (already corrected) one
+    (beamformer.py:64-74).  vector [bins, M] (extension: [S, bins, M]); returns a copy."""
+    t = L.require_cuda()
+    as_torch = isinstance(vector, t.Tensor)
+    w = _c128_dev(vector).clone()
+    if w.dim() not in (2, 3):
+        raise ValueError("phase_correction: expected [bins, M] or [S, bins, M]")
+    S = 1 if w.dim() == 2 else w.shape[0]
+    F, D = w.shape[-2], w.shape[-1]
+    L.check(L.lib().ds_phase_correction_run(S, F, D, L.ptr(w), L.stream_ptr()), "ds_phase_correction_run")
+    return w if as_torch else w.cpu().numpy()
+
+
+def blind_analytic_normalization(vector, noise_psd_matrix, eps=0):
+    """BAN post-scaling of a beamforming vector (beamformer.py:34-61):
+    vector * |sqrt(v^H N N v)| / (|v^H N v| + eps).  vector [..., M], noise [..., M, M]."""
+    t = L.require_cuda()
+    as_torch = isinstance(vector, t.Tensor)
+    v = _c128_dev(vector)
+    N = _c128_dev(noise_psd_matrix)
+    M = v.shape[-1]
+    if N.shape[-2:] != (M, M) or N.shape[:-2] != v.shape[:-1]:
+        raise ValueError("blind_analytic_normalization: shapes %s / %s" % (tuple(v.shape), tuple(N.shape)))
+    lead = v.shape[:-1]
+    v2, N2 = v.reshape(-1, M), N.reshape(-1, M, M)
+    out = t.empty_like(v2)
+    L.check(L.lib().ds_ban_run(v2.shape[0], M, L.ptr(v2), L.ptr(N2), float(eps), L.ptr(out), L.stream_ptr()), "ds_ban_run")
+    out = out.reshape(*lead, M)
+    return out if as_torch else out.cpu().numpy()
+
+
+def masked_covariances(D, p=None, frames=None, scale=1.0):
+    """Mask-weighted spatial covariances of example/mvdr.ipynb cell 6 (and the frame-range averages
+    of cell 2): Phi_xx = scale * sum_n p[:, n] y_n y_n^H, Phi_vv = scale * sum_n (1 - p[:, n]) y_n y_n^H.
+    D [K, T, M] (or [S, K, T, M]) complex, p [K, T] (or [S, K, T]) or None (then only Phi_xx, weight 1),
+    frames = (start, stop) restricts the sum.  Returns (Phi_xx, Phi_vv) [K, M, M] (Phi_vv None without p)."""
+    t = L.require_cuda()
+    as_torch = isinstance(D, t.Tensor)
+    Dd = D.to("cuda") if as_torch else t.as_tensor(np.ascontiguousarray(D)).to("cuda")
+    if Dd.dtype not in (t.complex64, t.complex128):
+        Dd = Dd.to(t.complex128)
+    batched = Dd.dim() == 4
+    if not batched:
+        Dd = Dd[None]
+    Xd = Dd.permute(0, 2, 3, 1).contiguous()                                  # [S, T, M, K]
+    pd = None
+    if p is not None:
+        pd = L.to_device(p, t.float64)
+        pd = (pd if batched else pd[None]).permute(0, 2, 1).contiguous()      # [S, T, K]
+    out = masked_covariances_device(Xd, pd, frames=frames, scale=scale)
+    res = [None if o is None else (o if batched else o[0]) for o in out]
+    return tuple(res) if as_torch else tuple(None if o is None else o.cpu().numpy() for o in res)
+
+
+def masked_covariances_device(Xd, pd=None, frames=None, scale=1.0):
+    """Device-layout variant: Xd [S, T, M, K] complex64/complex128 CUDA, pd [S, T, K] float64 CUDA or None
+    -> (Phi_xx, Phi_vv) [S, K, M, M] complex128 CUDA."""
+    t = L.require_cuda()
+    S, T, M, K = Xd.shape
+    t0, t1 = (0, T) if frames is None else (int(frames[0]), int(frames[1]))
+    Pxx = t.zeros((S, K, M, M), dtype=t.complex128, device="cuda")
+    Pvv = t.zeros((S, K, M, M), dtype=t.complex128, device="cuda") if pd is not None else None
+    L.check(L.lib().ds_masked_cov_run(S, T, M, K, t0, t1, L.ptr(Xd), int(Xd.dtype == t.complex128), L.ptr(pd),
+                                      float(scale), L.ptr(Pxx), L.ptr(Pvv), L.stream_ptr()), "ds_masked_cov_run")
+    return Pxx, Pvv
 
 
 class beamformer(object):

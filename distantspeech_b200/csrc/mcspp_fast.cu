@@ -57,7 +57,8 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
       for (int j = i; j < M; ++j)
         smc[pidx<M>(i, j) * NT] = ((i == j) ? 1.0 : 2.0) * fma(ai[i], ai[j], ar[i] * ar[j]);
   }
-  int frm = a.frm_cnt, ell = a.ell;
+  // ell % L without a division per frame: r follows ell modulo L (mcra.py:52-56 resets ell inside the frame loop)
+  int frm = a.frm_cnt, ell = a.ell, ell_mod = a.ell % a.mc.L;
   const float2 *Xp = reinterpret_cast<const float2 *>(a.X) + (long long)s * a.T * M * K + k;
   float2 *Yp = a.Yout + (long long)s * a.T * K + k;
   const double *a0 = reinterpret_cast<const double *>(a.a0 + k);     // (re, im) pairs, mic stride 2K doubles
@@ -83,10 +84,11 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
       for (int m = 0; m < M; ++m)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(Xp + (long long)(DS_X_PREFETCH - 1) * M * K + m * K));
     }
-    const bool reset = (frm > 0) && (ell % a.mc.L == 0);
+    const bool reset = (frm > 0) && (ell_mod == 0);
     *Yp = chain_bin_step<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a);
     if (reset) ell = 0;
     ++ell; ++frm;
+    ell_mod = (ell_mod + 1 == a.mc.L) ? 0 : ell_mod + 1;
     if (a.k_first == 2 && k == 2) { Yp[-1] = make_float2(0.f, 0.f); Yp[-2] = make_float2(0.f, 0.f); }
     Yp += K;
   }

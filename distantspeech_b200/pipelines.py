@@ -179,3 +179,96 @@ class MvdrMcsppChain(object):
 
     def reset_counters(self):
         self.frm_cnt, self.ell = 0, 1
+
+
+class MaskBeamformer(object):
+    """Whole-utterance mask-based MVDR / GEV beamformer, batched over streams -- the compositions of
+    example/mvdr.ipynb cell 6 ("mvdr") and cell 8 ("gev"), for which the reference has no function:
+
+        D = Transform(n_fft, hop, channel=M).stft(x)
+        p[:, n] = estimator.estimation(D[:, n, :])                     (cell 4; here McSppBase, any M <= 8,
+                                                                        or a mask handed in by the caller)
+        Phi_xx = sum_n p y y^H ; Phi_vv = sum_n (1 - p) y y^H          (cell 6)
+        mvdr: w = compute_mvdr_weight(steering(Phi_xx), inv(Phi_vv))   (cell 6)
+        gev:  w = blind_analytic_normalization(phase_correction(get_gev_vector(Phi_xx, Phi_vv)), Phi_vv)   (cell 8)
+        Y = einsum('inj,ij->in', D, w.conj()) ; y = Transform(channel=1).istft(Y)
+
+    Every stage is a CUDA kernel (transform.cu, mcspp.cu, eig.cu); ``w`` [S, K, M] and ``p`` [S, T, K] of the
+    last call stay on the device as attributes.  Each call is one utterance (no state is carried over)."""
+
+    def __init__(self, n_mics, n_fft=512, hop=256, method="mvdr", fft_precision="fp32", ban_eps=0.0):
+        if method not in ("mvdr", "gev"):
+            raise ValueError("method must be 'mvdr' or 'gev'")
+        self.M, self.n_fft, self.hop, self.method = int(n_mics), int(n_fft), int(hop), method
+        self.K = self.n_fft // 2 + 1
+        self.fft_fp64 = fft_precision == "fp64"
+        self.ban_eps = float(ban_eps)
+        self.window = _sqrt_hann(self.n_fft)
+        self.W0 = float(np.sum(self.window ** 2))
+        self.w = None
+        self.p = None
+        self.Phi_xx = None
+        self.Phi_vv = None
+
+    def weights_device(self, Pxx, Pvv):
+        """Phi_xx, Phi_vv [S, K, M, M] complex128 CUDA -> w [S, K, M] complex128 CUDA."""
+        from .beamformer import beamformer as B
+        t = L.require_cuda()
+        S, K, M, _ = Pxx.shape
+        if self.method == "mvdr":
+            a = B.steering(Pxx)
+            w = t.empty((S, K, M), dtype=t.complex128, device="cuda")
+            L.check(L.lib().ds_mvdr_from_cov_run(S * K, M, L.ptr(a), L.ptr(Pvv), L.ptr(w), L.stream_ptr()),
+                    "ds_mvdr_from_cov_run")
+            return w
+        w = B.get_gev_vector(Pxx, Pvv)
+        w = B.phase_correction(w)
+        return B.blind_analytic_normalization(w, Pvv, eps=self.ban_eps)
+
+    def process_device(self, x_dev, p_dev=None):
+        """x_dev [S, M, N] float32 CUDA (N a multiple of hop), p_dev [S, T, K] float64 CUDA or None
+        -> y [S, N] float32 CUDA."""
+        from .beamformer import beamformer as B
+        from .noise_estimation.mcspp_base import McSppBase
+        from .transform.transform import stft_device, istft_device
+        t = L.require_cuda()
+        S, M, N = x_dev.shape
+        if M != self.M or N % self.hop != 0 or N < self.hop:
+            raise ValueError("expected [S, %d, N] with N a positive multiple of hop=%d" % (self.M, self.hop))
+        wdev = L.device_window(self.window, self.n_fft)
+        hist = t.zeros((S, M, self.n_fft - self.hop), dtype=t.float32, device="cuda")
+        X = stft_device(x_dev.contiguous(), self.n_fft, self.hop, wdev, L.DS_STFT_STREAMING, history=hist,
+                        fft_fp64=self.fft_fp64)                                   # [S, T, M, K] complex64
+        T = X.shape[1]
+        if p_dev is None:
+            est = McSppBase(nfft=self.n_fft, channels=M)
+            p_dev = est._run(X, keep_prev_vv=False)["p"]                          # [S, T, K]
+        elif tuple(p_dev.shape) != (S, T, self.K):
+            raise ValueError("mask must be [S, T, K] = %s, got %s" % ((S, T, self.K), tuple(p_dev.shape)))
+        self.p = p_dev
+        self.Phi_xx, self.Phi_vv = B.masked_covariances_device(X, p_dev.contiguous())
+        self.w = self.weights_device(self.Phi_xx, self.Phi_vv)
+        Y = t.empty((S, T, self.K), dtype=t.complex128, device="cuda")
+        L.check(L.lib().ds_apply_stream_weights_run(S, T, M, self.K, L.ptr(X), 0, L.ptr(self.w), L.ptr(Y), L.stream_ptr()),
+                "ds_apply_stream_weights_run")
+        tail = t.zeros((S, 1, self.n_fft - self.hop), dtype=t.float32, device="cuda")
+        y = istft_device(Y[:, :, None, :], self.n_fft, self.hop, wdev, L.DS_STFT_STREAMING, tail=tail,
+                         scale=self.hop / self.W0, fft_fp64=self.fft_fp64)        # [S, 1, N]
+        return y[:, 0, :]
+
+    def process(self, x, p=None):
+        """Reference-shaped call: x [N, M] (or [S, N, M]), optional mask p [K, T] (or [S, K, T]) -> y [N] (or [S, N])."""
+        t = L.require_cuda()
+        as_torch = isinstance(x, t.Tensor)
+        xd = L.to_device(x, t.float32)
+        batched = xd.dim() == 3
+        if not batched:
+            xd = xd[None]
+        pd = None
+        if p is not None:
+            pd = L.to_device(p, t.float64)
+            pd = (pd if batched else pd[None]).permute(0, 2, 1).contiguous()
+        y = self.process_device(xd.permute(0, 2, 1).contiguous(), pd)
+        if not batched:
+            y = y[0]
+        return y if as_torch else y.double().cpu().numpy()

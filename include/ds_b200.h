@@ -505,6 +505,43 @@ size_t ds_srp_workspace_bytes(int n_frames, int n_mics, int n_bins, int use_tens
 int ds_srp_run(int n_dirs, int n_frames, int n_mics, int n_bins, double fs, int n_fft, const float *tau,
                const void *Yhat, void *workspace, float *P, int use_tensor_cores, void *stream);
 
+/* ---- data-driven steering, mask-based MVDR and GEV weights ---- */
+/* replaces the covariance accumulations of example/mvdr.ipynb cell 6 (mask-based MVDR) and the
+ * frame-range averages of cell 2:
+ *   Phi_xx[s,k] += scale * sum_{t in [t0,t1)} p[s,t,k]       * y y^H
+ *   Phi_vv[s,k] += scale * sum_{t in [t0,t1)} (1 - p[s,t,k]) * y y^H        y = X[s,t,:,k]
+ *   X [S][T][M][K] c64 or c128   p [S][T][K] float64 or NULL (= 1)   Phi_* [S][K][M][M] c128
+ *   Phi_vv may be NULL (it must be when p is NULL).  The caller zero-fills before the first call.   */
+int ds_masked_cov_run(int n_streams, int n_frames, int n_mics, int n_bins, int t0, int t1, const void *X,
+                      int x_is_c128, const double *p, double scale, void *Phi_xx, void *Phi_vv, void *stream);
+/* replaces steering() (beamformer/beamformer.py:10-31): principal eigenvector of each Hermitian
+ * matrix (lower triangle read, like numpy.linalg.eigh), unit norm, phase referenced to sensor 0.
+ *   XXs [n][M][M] c128 -> out [n][M] c128,  1 <= M <= 8                                            */
+int ds_steering_run(long long n, int n_mics, const void *XXs, void *out, void *stream);
+/* replaces get_gev_vector() (beamformer.py:77-97): last generalised eigenvector of (target, noise)
+ * per matrix pair, normalised to w^H noise w = 1 like scipy.linalg.eigh.  LAPACK leaves the phase of
+ * that vector to its tridiagonal solver (component 0 of the standard-form vector real, either sign);
+ * here that component is real and NON-NEGATIVE, so results equal the reference's up to a sign per
+ * matrix -- which phase_correction() removes for every bin but the first.  A noise matrix that is not
+ * positive definite gives the reference's fallback ones * M / trace(noise).
+ *   target, noise [n][M][M] c128 -> out [n][M] c128                                               */
+int ds_gev_run(long long n, int n_mics, const void *target, const void *noise, void *out, void *stream);
+/* replaces phase_correction() (beamformer.py:64-74), in place: W [S][K][M] c128                    */
+int ds_phase_correction_run(int n_streams, int n_bins, int n_mics, void *W, void *stream);
+/* replaces blind_analytic_normalization() (beamformer.py:34-61):
+ *   out = vector * |sqrt(v^H N N v)| / (|v^H N v| + eps);  vector [n][M], noise [n][M][M], out [n][M] c128 */
+int ds_ban_run(long long n, int n_mics, const void *vector, const void *noise, double eps, void *out, void *stream);
+
+/* replaces compute_mvdr_weight(steer, np.linalg.inv(Phi_vv)) of mvdr.ipynb cell 6 (beamformer.py:133-155
+ * fed with a fresh inverse): w = R^-1 a / (a^H R^-1 a) by Cholesky and two triangular solves.
+ *   steer [n][M], Rvv [n][M][M] (Hermitian, lower triangle read) -> w_out [n][M], all c128; NaN where Rvv
+ *   is not positive definite                                                                         */
+int ds_mvdr_from_cov_run(long long n, int n_mics, const void *steer, const void *Rvv, void *w_out, void *stream);
+/* einsum('inj,ij->in', D, w.conj()) with one weight set per stream (mvdr.ipynb cells 6, 8):
+ *   X [S][T][M][K] c64 or c128   W [S][K][M] c128   Y [S][T][K] c128                                 */
+int ds_apply_stream_weights_run(int n_streams, int n_frames, int n_mics, int n_bins, const void *X, int x_is_c128,
+                                const void *W, void *Y, void *stream);
+
 /* ---- config-4 chain: STFT -> McSppBase -> MVDR -> OMLSA -> ISTFT ------- */
 typedef struct ds_chain_params {
   ds_mcspp_params est; /* n_frames is derived: n_samples / hop                    */

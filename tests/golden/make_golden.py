@@ -227,6 +227,51 @@ def main():
          Phi_vv_last=est.Phi_vv, Phi_vv_inv_last=est.Phi_vv_inv, Phi_xx_last=est.Phi_xx,
          mcra_p_last=est.mccdr.mcra.p, Pxii_last=est.mccdr.Gamma_estimator.Pxii, Pxij_last=est.mccdr.Gamma_estimator.Pxij)
 
+    mask_beamformers()
+
+
+def mask_beamformers():
+    """8f.3: mask-based MVDR (mvdr.ipynb cell 6) and GEV (cell 8) on a 6-mic array like the notebook's, with the
+    mask from the reference's McSppBase (the notebook's McSpp raises above 4 microphones)."""
+    H.install()
+    from DistantSpeech.transform.transform import Transform
+    from DistantSpeech.beamformer.beamformer import (steering, compute_mvdr_weight, get_gev_vector, phase_correction,
+                                                     blind_analytic_normalization)
+    from DistantSpeech.noise_estimation.mcspp_base import McSppBase
+    geo6 = O.MicGeometry("circular", r=0.05, M=6, n_fft=512)
+    x6 = np.ascontiguousarray(O.synth_streams(1, geo6, 256 * 100, seed0=0x6E7)[0].T)           # [N, 6] float32
+    tf = Transform(n_fft=512, hop_length=256, channel=6)
+    D = tf.stft(x6.astype(np.float64))                                                         # [257, 100, 6]
+    K, nT, M = D.shape
+    est = McSppBase(nfft=512, channels=6)
+    p = np.zeros((K, nT))
+    Pxx = np.zeros((K, M, M), dtype=complex)
+    Pvv = np.zeros((K, M, M), dtype=complex)
+    for n in range(nT):
+        est.estimation(D[:, n, :])
+        p[:, n] = est.p
+    for n in range(nT):                                                                       # cell 6
+        y = D[:, n, :]
+        Pxx = Pxx + np.einsum('ij,il->ijl', y, y.conj()) * p[:, n:n + 1, None]
+        Pvv = Pvv + np.einsum('ij,il->ijl', y, y.conj()) * (1 - p[:, n:n + 1, None])
+    steer = steering(Pxx)
+    w_mvdr = compute_mvdr_weight(steer, np.linalg.inv(Pvv))
+    y_mvdr = Transform(n_fft=512, hop_length=256, channel=1).istft(np.einsum('inj,ij->in', D, w_mvdr.conj())[:, :, None])
+    w_gev_raw = get_gev_vector(Pxx, Pvv)                                                       # cell 8
+    w_gev_pc = phase_correction(w_gev_raw)
+    w_gev = blind_analytic_normalization(w_gev_pc, Pvv)
+    y_gev = Transform(n_fft=512, hop_length=256, channel=1).istft(np.einsum('inj,ij->in', D, w_gev.conj())[:, :, None])
+    # the frame-range averages + GEVD-flavoured steering of cell 2 (steering() on a non-Hermitian product)
+    Rvv = sum(np.einsum('ij,il->ijl', D[:, n, :], D[:, n, :].conj()) for n in range(10)) / 10
+    Ryy = sum(np.einsum('ij,il->ijl', D[:, n, :], D[:, n, :].conj()) for n in range(30, 80)) / 50
+    steer_pca = steering(Ryy - Rvv)
+    save("mask_beamformers.npz", x=x6, p=p, Pxx=Pxx, Pvv=Pvv, steer=steer, w_mvdr=w_mvdr,
+         y_mvdr=y_mvdr, w_gev_raw=w_gev_raw, w_gev_pc=w_gev_pc, w_gev=w_gev, y_gev=y_gev, Rvv=Rvv, Ryy=Ryy,
+         steer_pca=steer_pca)
+
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "mask":
+        mask_beamformers()
+    else:
+        main()

@@ -99,3 +99,30 @@ def test_fdgsc_live(ref):
             r = fd.process(x.copy(), postfilter=post, dc_notch=True)
         o = O.FdgscOracle(geo, 256, np.array([60, 0]) / 180 * np.pi).process(x, postfilter=post)
         assert np.max(np.abs(r[0] - o[0])) < 1e-9
+
+
+def test_steering_gev_mask_live(ref):
+    """8f.3: steering / get_gev_vector / phase_correction / blind_analytic_normalization and the cell-6 accumulation"""
+    from DistantSpeech.beamformer.beamformer import (steering, get_gev_vector, phase_correction,
+                                                     blind_analytic_normalization, compute_mvdr_weight)
+    rng = np.random.default_rng(77)
+    K, T, M = 33, 40, 5
+    D = rng.standard_normal((K, T, M)) + 1j * rng.standard_normal((K, T, M))
+    p = rng.uniform(0.01, 0.99, (K, T))
+    Pxx_r = np.zeros((K, M, M), dtype=complex)
+    Pvv_r = np.zeros((K, M, M), dtype=complex)
+    for n in range(T):                                               # example/mvdr.ipynb cell 6, verbatim arithmetic
+        y = D[:, n, :]
+        Pxx_r = Pxx_r + np.einsum('ij,il->ijl', y, y.conj()) * p[:, n:n + 1, None]
+        Pvv_r = Pvv_r + np.einsum('ij,il->ijl', y, y.conj()) * (1 - p[:, n:n + 1, None])
+    Pxx, Pvv = O.masked_covariances(D, p)
+    assert np.array_equal(Pxx, Pxx_r) and np.array_equal(Pvv, Pvv_r)
+    assert np.array_equal(O.steering_pca(Pxx), steering(Pxx))
+    raw = get_gev_vector(Pxx, Pvv)
+    assert np.array_equal(O.gev_vector(Pxx, Pvv), raw)
+    assert np.array_equal(O.phase_correction(raw), phase_correction(raw))
+    assert np.array_equal(O.blind_analytic_normalization(raw, Pvv), blind_analytic_normalization(raw, Pvv))
+    assert np.array_equal(O.mask_beamformer_weights(Pxx, Pvv, "mvdr"), compute_mvdr_weight(steering(Pxx), np.linalg.inv(Pvv)))
+    # noise matrix that is not positive definite: the reference's fallback branch
+    with _quiet():
+        assert np.array_equal(O.gev_vector(Pxx[:2], -Pvv[:2]), get_gev_vector(Pxx[:2], -Pvv[:2]))
