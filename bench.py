@@ -279,18 +279,21 @@ def main():
     dom = int(np.argmax(phase))
     names = ["stft_kernel", "mcspp_fast_kernel" if not args.full_state else "mcspp_kernel", "istft_kernel"]
     traffic = None
+    flop_bf, pipe_pct = 1928.0, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         per_stream = tj.get(names[dom], {}).get("dram_bytes_per_stream_10s")
+        flop_bf = float(tj.get("mcspp_fast_kernel", {}).get("fp64_flop_per_bin_frame", flop_bf))
+        pipe_pct = tj.get("mcspp_fast_kernel", {}).get("ncu_pipe_fp64_pct")
         if per_stream is not None:
             traffic = per_stream * S * (N / FS) / 10.0      # ncu dram read+write of one launch, scaled to this launch
     except Exception:
         pass
     achieved = algo_bytes / (phase[dom] / 1e3) / 1e9
     # what actually bounds the dominant kernel: the fp64 pipe.  FLOP per (bin, frame) from the executed SASS mix of the
-    # ncu capture in profiles/ (764 DFMA x 2 + 230 DMUL + 125 DADD); nominal pipe peak = 148 SM x 64 FMA/clk x 2 x SM clock
+    # frame loop (profiles/traffic.json: 800 DFMA x 2 + 229 DMUL + 99 DADD); nominal pipe peak = 148 SM x 64 FMA/clk x 2 x SM clock
     bin_frames = S * (N // HOP) * (N_FFT // 2 + 1 - 2)
-    fp64_flop = 1883.0 * bin_frames
+    fp64_flop = flop_bf * bin_frames
     sm_mhz = (peaks or {}).get("sm_max_mhz", 1965.0)
     fp64_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -300,9 +303,9 @@ def main():
                 "kernel_ms": {n: float(v) for n, v in zip(names, phase)},
                 "fp64_pipe": {"achieved_tflops": fp64_flop / (phase[1] / 1e3) / 1e12, "nominal_peak_tflops": fp64_peak,
                               "frac": fp64_flop / (phase[1] / 1e3) / 1e12 / fp64_peak,
-                              "flop_per_bin_frame": 1883.0,
-                              "ncu_pipe_fp64_pct": 52.8},
-                "note": "the per-bin kernel is bound by the fp64 pipe (dependent-issue latency at 8 warps/SM), not by HBM: "
+                              "flop_per_bin_frame": flop_bf,
+                              "ncu_pipe_fp64_pct": pipe_pct},
+                "note": "the per-bin kernel is bound by the fp64 pipe (two fp64-dense warps per scheduler at 8 warps/SM), not by HBM: "
                         "the contractual hbm fraction is small by construction (SURVEY.md 8d); fp64_pipe is the binding roof; "
                         "traffic exceeds the algorithmic bytes because the complex64 spectrum (2x the waveform at 50% overlap) "
                         "is staged in HBM between the three kernels -- see DESIGN.md"}

@@ -189,6 +189,11 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
 
     // ---- u = A y, numerator a^H u, s_yu = Re(y^H u) = y^H A y, uu = |u|^2     :282-284, beamformer.py:152
     double ur[M], ui[M];
+#ifdef DS_HOIST_A0
+    double a0r[M], a0i[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { a0r[m] = ld_f64_once(a0 + 2 * m * K); a0i[m] = ld_f64_once(a0 + 2 * m * K + 1); }
+#endif
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       double sr = 0.0, sr2 = 0.0, si = 0.0, si2 = 0.0;
@@ -203,7 +208,11 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
     double Yr = 0.0, Yi = 0.0, Yr2 = 0.0, Yi2 = 0.0, syu = 0.0, syu2 = 0.0, uu = 0.0, uu2 = 0.0;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
+#ifdef DS_HOIST_A0
+      const double ar = a0r[m], ai = a0i[m];
+#else
       const double ar = ld_f64_once(a0 + 2 * m * K), ai = ld_f64_once(a0 + 2 * m * K + 1);
+#endif
       Yr = fma(ar, ur[m], Yr);   Yi = fma(-ai, ur[m], Yi);
       Yr2 = fma(ai, ui[m], Yr2); Yi2 = fma(ar, ui[m], Yi2);
       syu = fma(yr[m], ur[m], syu); syu2 = fma(yi[m], ui[m], syu2);

@@ -13,6 +13,9 @@
 
 namespace ds {
 
+#ifndef DS_FAST_SKEW
+#define DS_FAST_SKEW 8000       // cycles, about one frame of the M = 8 kernel; 0 disables
+#endif
 #ifndef DS_FAST_MINB
 #define DS_FAST_MINB 4
 #define DS_FAST_USE_C 1
@@ -64,6 +67,18 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
   const double *a0 = reinterpret_cast<const double *>(a.a0 + k);     // (re, im) pairs, mic stride 2K doubles
 
   McraRegs mc = {mS, mSmin, mStmp, mp, mlam};
+#if DS_FAST_SKEW > 0
+  {
+    // De-phase the CTAs once at start-up: every warp runs the same ~1800-instruction frame body, and warps that
+    // start together stay in lock-step for a long time (same phase => they want the fp64 pipe, the LSU and the
+    // MUFU at the same moments).  A pseudo-random delay of 0..7/8 of a frame time per warp costs < 4 us per CTA
+    // and is worth 1.9 % of the step (A/B on the B200: 23.12 -> 22.70 ms; 2 600 / 3 900 / 5 200-cycle offsets by
+    // scheduler slot, by launch round or random all land within 0.03 ms of each other).  Results are unaffected.
+    const unsigned lvl = ((blockIdx.x * 2u + (tid >> 5)) * 2654435761u) >> 29;
+    const long long wait = (long long)lvl * (DS_FAST_SKEW / 8), t0 = clock64();
+    while (clock64() - t0 < wait) { }
+  }
+#endif
 #pragma unroll 1
   for (int t = 0; t < a.T; ++t) {
     // issue the loads of this frame's spectrum first: they are consumed only after the matrix
@@ -102,7 +117,10 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
 
 template <int M>
 static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
-  constexpr int NT = 64;
+#ifndef DS_FAST_NT
+#define DS_FAST_NT 64
+#endif
+  constexpr int NT = DS_FAST_NT;
   constexpr int NP = M * (M + 1) / 2;
   constexpr int MINB = DS_FAST_MINB; // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
   const size_t smem = (size_t)(DS_FAST_USE_C ? 3 : 2) * NP * NT * sizeof(double);

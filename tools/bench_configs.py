@@ -153,6 +153,26 @@ def main():
     t0 = time.perf_counter(); O.TdgscOracle(geo4, 256, ang).process(xh); cpu = 1.0 / (time.perf_counter() - t0)
     out.append({"config": "f1", "what": "TDGSC 4-mic, %d streams x 10 s (incl. API hand-off + diagnostics outputs)" % Ss,
                 "ms": ms, "audio_s_per_s": Ss * N / FS / (ms / 1e3), "cpu_oracle_1core_audio_s_per_s": cpu})
+    # ---- f3: mask-based MVDR / GEV (mvdr.ipynb cells 6, 8), 8 mics, mask from McSppBase on the device --------
+    from distantspeech_b200.pipelines import MaskBeamformer
+    Sm = 64 if small else 256
+    xm = torch.randn((Sm, 8, N), device="cuda") * 0.1
+    for method in ("mvdr", "gev"):
+        mb = MaskBeamformer(8, method=method)
+        ms = timed(lambda: mb.process_device(xm), warm=1, reps=2)
+        pm = mb.p
+        ms_w = timed(lambda: mb.weights_device(mb.Phi_xx, mb.Phi_vv), warm=1, reps=3)
+        row = {"config": "f3", "what": "mask-based %s 8-mic, %d streams x 10 s (STFT + McSppBase mask with all taps + covariances + "
+                                      "weights + apply + ISTFT)" % (method.upper(), Sm),
+               "ms": ms, "audio_s_per_s": Sm * N / FS / (ms / 1e3), "ms_weights_only": ms_w,
+               "eigenproblems_per_s": Sm * 257 / (ms_w / 1e3)}
+        if method == "mvdr":
+            xh = xm[0, :, :16000].cpu().numpy().astype(np.float64).T
+            t0 = time.perf_counter(); O.mask_beamform(xh, method="mvdr"); row["cpu_oracle_1core_audio_s_per_s"] = 1.0 / (time.perf_counter() - t0)
+        out.append(row)
+        del mb
+    del xm
+    torch.cuda.empty_cache()
     for o in out:
         print(json.dumps(o))
 
