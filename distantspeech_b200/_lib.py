@@ -243,6 +243,12 @@ def _declare(lib):
     lib.ds_ban_run.argtypes = [C.c_longlong, i32, vp, vp, dbl, vp, vp]
     lib.ds_mvdr_from_cov_run.argtypes = [C.c_longlong, i32, vp, vp, vp, vp]
     lib.ds_apply_stream_weights_run.argtypes = [i32, i32, i32, i32, vp, i32, vp, vp, vp]
+    lib.ds_idoa_rtf_state_bytes.argtypes = [i32, i32, i32]
+    lib.ds_idoa_rtf_state_bytes.restype = C.c_size_t
+    lib.ds_idoa_spp_state_bytes.argtypes = [i32, i32, i32]
+    lib.ds_idoa_spp_state_bytes.restype = C.c_size_t
+    lib.ds_idoa_rtf_run.argtypes = [i32, i32, i32, i32, dbl, vp, i32, vp, vp, vp]
+    lib.ds_idoa_spp_run.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp]
     lib.ds_chain_state_bytes.argtypes = [C.POINTER(ChainParams)]
     lib.ds_chain_state_bytes.restype = C.c_size_t
     lib.ds_chain_workspace_bytes.argtypes = [C.POINTER(ChainParams)]

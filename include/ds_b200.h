@@ -542,6 +542,28 @@ int ds_mvdr_from_cov_run(long long n, int n_mics, const void *steer, const void 
 int ds_apply_stream_weights_run(int n_streams, int n_frames, int n_mics, int n_bins, const void *X, int x_is_c128,
                                 const void *W, void *Y, void *stream);
 
+/* ---- Idoa: spatial speech-presence probability (doa/idoa.py) ---- */
+/* replaces the RTF recursion of Idoa.estimate (idoa.py:119-127), shared by every direction:
+ *   Y_smooth <- (1-alpha) Y_smooth + alpha |X_0|^2 ; Y_xcorr <- (1-alpha) Y_xcorr + alpha X_i conj(X_0) ; B = Y_xcorr / Y_smooth
+ *   X [S][T][M][K] c64 or c128 -> B [S][T][2(M-1)+1][K] float64 (Re, Im per channel pair, then ||B||)
+ *   state: ds_idoa_rtf_state_bytes() bytes, zero-filled = reset                                          */
+size_t ds_idoa_rtf_state_bytes(int n_streams, int n_mics, int n_bins);
+int ds_idoa_rtf_run(int n_streams, int n_frames, int n_mics, int n_bins, double alpha, const void *X, int x_is_c128,
+                    void *state, double *B, void *stream);
+/* replaces the per-direction part of Idoa.estimate (idoa.py:129-165) and, with Yout, the gain of Idoa.process
+ * (:199): similarity Delta to the free-field RTF Psi, its H0 / Hd statistics, beta_n from mean(mu_Delta[72:128]),
+ * presence probability p.  Directions are independent: theta[n_slots] lists the direction index held by each
+ * state slot (any subset of the grid).  only_theta >= 0 reproduces estimate(X, theta=int): every other direction
+ * sees Delta = 0.
+ *   Psi [n_theta][M-1][K] c128   B from ds_idoa_rtf_run   state [S][n_slots][4][K] float64 (zero = reset)
+ *   p_out [S][T][n_slots][K] float64 or NULL
+ *   Yout [S][T][K] c128 or NULL: max(mean(p[64:128]), 0.01) * X[:, :, 0, :]; needs n_slots == 1 and X
+ *   128 <= K <= 288 (the reference hard-codes bins 64..127 / 72..127)                                     */
+size_t ds_idoa_spp_state_bytes(int n_streams, int n_slots, int n_bins);
+int ds_idoa_spp_run(int n_streams, int n_frames, int n_mics, int n_bins, int n_slots, const int *theta, int only_theta,
+                    const void *Psi, const double *B, void *state, double *p_out, const void *X, int x_is_c128,
+                    void *Yout, void *stream);
+
 /* ---- config-4 chain: STFT -> McSppBase -> MVDR -> OMLSA -> ISTFT ------- */
 typedef struct ds_chain_params {
   ds_mcspp_params est; /* n_frames is derived: n_samples / hop                    */

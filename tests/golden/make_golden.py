@@ -228,6 +228,7 @@ def main():
          mcra_p_last=est.mccdr.mcra.p, Pxii_last=est.mccdr.Gamma_estimator.Pxii, Pxij_last=est.mccdr.Gamma_estimator.Pxij)
 
     mask_beamformers()
+    idoa()
 
 
 def mask_beamformers():
@@ -270,8 +271,37 @@ def mask_beamformers():
          steer_pca=steer_pca)
 
 
+def idoa():
+    """8f.4: Idoa.estimate / Idoa.process (doa/idoa.py) on a 4-mic circular and a 6-mic linear array."""
+    import contextlib
+    import io
+    H.install()
+    from DistantSpeech.doa.idoa import Idoa
+    from DistantSpeech.beamformer.MicArray import MicArray
+    out = {}
+    for tag, arr, M, r, n_fft in (("c4", "circular", 4, 0.032, 256), ("l6", "linear", 6, 0.05, 512)):
+        geo = O.MicGeometry(arr, r=r, M=M, n_fft=n_fft)
+        x = np.ascontiguousarray(O.synth_streams(1, geo, (n_fft // 2) * 60, seed0=0x1D0A + M)[0].T)   # [N, M] float32
+        with contextlib.redirect_stdout(io.StringIO()):
+            mic = MicArray(arrayType=arr, r=r, M=M, n_fft=n_fft)
+            a, b, c = Idoa(mic), Idoa(mic), Idoa(mic)
+        n1 = (n_fft // 2) * 25
+        y = np.concatenate([a.process(x[:n1].astype(np.float64), default_direction=30),
+                            a.process(x[n1:].astype(np.float64), default_direction=30)])          # two chunks: state carries over
+        X = b.transform.stft(x.astype(np.float64))
+        p_all = b.estimate(X)
+        p_one = c.estimate(X, theta=40)
+        sel = np.array([30, 40, 41, 179])
+        out.update({tag + "_x": x, tag + "_n1": np.array(n1), tag + "_y": y, tag + "_sel": sel, tag + "_p_sel": p_all[:, :, sel],
+                    tag + "_p_theta40": p_one[:, :, [40, 41]], tag + "_mu_Delta_last": b.mu_Delta[:, sel],
+                    tag + "_var_last": b.var_Delta_h0[:, sel], tag + "_Psi_sel": b.Psi[:, :, sel]})
+    save("idoa.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mask":
         mask_beamformers()
+    elif len(sys.argv) > 1 and sys.argv[1] == "idoa":
+        idoa()
     else:
         main()

@@ -126,3 +126,22 @@ def test_steering_gev_mask_live(ref):
     # noise matrix that is not positive definite: the reference's fallback branch
     with _quiet():
         assert np.array_equal(O.gev_vector(Pxx[:2], -Pvv[:2]), get_gev_vector(Pxx[:2], -Pvv[:2]))
+
+
+def test_idoa_live(ref):
+    """8f.4: Idoa.estimate / Idoa.process, circular (360 directions) and linear (180) arrays"""
+    from DistantSpeech.doa.idoa import Idoa
+    from DistantSpeech.beamformer.MicArray import MicArray
+    for arr, M, r in (("circular", 4, 0.032), ("linear", 5, 0.04)):
+        geo = O.MicGeometry(arr, r=r, M=M, n_fft=256)
+        x = np.ascontiguousarray(O.synth_streams(1, geo, 128 * 40, seed0=11 + M)[0].T).astype(np.float64)
+        with _quiet():
+            mic = MicArray(arrayType=arr, r=r, M=M, n_fft=256)
+            rf, rf2 = Idoa(mic), Idoa(mic)
+        o, o2 = O.IdoaOracle(geo), O.IdoaOracle(geo)
+        assert np.max(np.abs(rf.Psi - o.Psi)) < 1e-13
+        yr = np.concatenate([rf.process(x[:128 * 15].copy(), default_direction=30), rf.process(x[128 * 15:].copy(), default_direction=30)])
+        yo = np.concatenate([o.process(x[:128 * 15].copy(), default_direction=30), o.process(x[128 * 15:].copy(), default_direction=30)])
+        assert np.max(np.abs(yr - yo)) < 1e-12
+        X = rf2.transform.stft(x)
+        assert np.max(np.abs(rf2.estimate(X, theta=40) - o2.estimate(X, theta=40))) < 1e-12
