@@ -86,8 +86,22 @@ template <int H, int NS, typename T> struct FftPass {
         const int k = j & (NS - 1);
         if (NS > 1) {
           constexpr int TSTEP = H / (NS * R);
+#ifdef DS_FFT_TW_POW
+          // experiment: one table load per butterfly, the other twiddles as powers of it (FMA pipe instead of LSU)
+          if constexpr (sizeof(T) == 4 && R >= 4) {
+            C w[R];
+            w[1] = tw[k * TSTEP];
+            w[2] = cmul(w[1], w[1]);
+            w[3] = cmul(w[2], w[1]);
+            if constexpr (R == 8) { w[4] = cmul(w[2], w[2]); w[5] = cmul(w[4], w[1]); w[6] = cmul(w[3], w[3]); w[7] = cmul(w[4], w[3]); }
 #pragma unroll
-          for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], tw[r * k * TSTEP]);
+            for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], w[r]);
+          } else
+#endif
+          {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], tw[r * k * TSTEP]);
+          }
         }
         if (R == 8) dft8<T>(v[i]);
         else if (R == 4) dft4(v[i][0], v[i][1], v[i][2], v[i][3]);

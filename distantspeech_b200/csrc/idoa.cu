@@ -68,15 +68,18 @@ struct IdoaSppArgs {
   double2 *Yout;             // [S][T][K] or null
 };
 
-// grid: (ceil(n_slots / IDOA_TH), S); block: K rounded up to a warp multiple
+// grid: (ceil(n_slots / IDOA_TH), S); block: K rounded up to a warp multiple.  M is a template parameter so that
+// Psi, B and the statistics are indexed with compile-time constants (registers, not local memory).
+template <int M>
 __global__ void __launch_bounds__(288) idoa_spp_kernel(IdoaSppArgs a) {
   __shared__ double sm_mu[2][IDOA_TH][IDOA_HI - IDOA_LO];
   __shared__ double sm_p[2][IDOA_GHI - IDOA_GLO];
-  const int k = threadIdx.x, s = blockIdx.y, K = a.K, D = a.M - 1, NE = 1 + 2 * D;
+  constexpr int D = M - 1, NE = 1 + 2 * D;
+  const int k = threadIdx.x, s = blockIdx.y, K = a.K;
   const bool live = k < K;
   const int slot0 = blockIdx.x * IDOA_TH;
   const int nth = min(IDOA_TH, a.n_slots - slot0);
-  double pr[IDOA_TH][IDOA_MAXM - 1], pi[IDOA_TH][IDOA_MAXM - 1], npsi[IDOA_TH];
+  double pr[IDOA_TH][D], pi[IDOA_TH][D], npsi[IDOA_TH];
   double mu[IDOA_TH], mu0[IDOA_TH], var0[IDOA_TH], p[IDOA_TH];
   bool zero_delta[IDOA_TH];
 #pragma unroll
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(288) idoa_spp_kernel(IdoaSppArgs a) {
       const int th = a.theta[slot0 + j];
       zero_delta[j] = a.only_theta >= 0 && th != a.only_theta;                 // estimate(X, theta=int): the other columns see Delta = 0
       double n2 = 0.0;
+#pragma unroll
       for (int i = 0; i < D; ++i) {
         const double2 v = a.Psi[((long long)th * D + i) * K + k];
         pr[j][i] = v.x; pi[j][i] = v.y;
@@ -101,12 +105,14 @@ __global__ void __launch_bounds__(288) idoa_spp_kernel(IdoaSppArgs a) {
     double delta[IDOA_TH];
     if (live) {
       const double *b = a.B + ((long long)s * a.T + t) * NE * K + k;
-      double br[IDOA_MAXM - 1], bi[IDOA_MAXM - 1];
+      double br[D], bi[D];
+#pragma unroll
       for (int i = 0; i < D; ++i) { br[i] = b[(long long)(2 * i) * K]; bi[i] = b[(long long)(2 * i + 1) * K]; }
       const double nB = b[(long long)(2 * D) * K];
 #pragma unroll
       for (int j = 0; j < IDOA_TH; ++j) {
         double acc = 0.0;
+#pragma unroll
         for (int i = 0; i < D; ++i) acc += pr[j][i] * br[i] + pi[j][i] * bi[i];               // Re(conj(Psi) B)
         delta[j] = zero_delta[j] ? 0.0 : acc / (npsi[j] * nB + 1e-6);                          // eq. 8
         double avg = (1.0 - p[j]) * 0.98;
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(288) idoa_spp_kernel(IdoaSppArgs a) {
         double sum = 0.0;
         for (int q = 0; q < IDOA_GHI - IDOA_GLO; ++q) sum += sm_p[buf][q];
         const double gain = fmax(sum / (double)(IDOA_GHI - IDOA_GLO), 0.01);
-        const long long xo = ((long long)s * a.T + t) * a.M * K + k;
+        const long long xo = ((long long)s * a.T + t) * M * K + k;
         double xr, xi;
         if (a.x_is_c128) { const double2 v = ((const double2 *)a.X)[xo]; xr = v.x; xi = v.y; }
         else { const float2 v = ((const float2 *)a.X)[xo]; xr = (double)v.x; xi = (double)v.y; }
@@ -196,7 +202,17 @@ extern "C" int ds_idoa_spp_run(int n_streams, int n_frames, int n_mics, int n_bi
   a.want_gain = Yout != nullptr; a.theta = theta; a.Psi = (const double2 *)Psi; a.B = B; a.state = (double *)state;
   a.p_out = p_out; a.X = X; a.x_is_c128 = x_is_c128; a.Yout = (double2 *)Yout;
   const dim3 grid((n_slots + IDOA_TH - 1) / IDOA_TH, n_streams);
-  idoa_spp_kernel<<<grid, ((n_bins + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(a);
+  const int nt = ((n_bins + 31) / 32) * 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n_mics) {
+    case 2: idoa_spp_kernel<2><<<grid, nt, 0, st>>>(a); break;
+    case 3: idoa_spp_kernel<3><<<grid, nt, 0, st>>>(a); break;
+    case 4: idoa_spp_kernel<4><<<grid, nt, 0, st>>>(a); break;
+    case 5: idoa_spp_kernel<5><<<grid, nt, 0, st>>>(a); break;
+    case 6: idoa_spp_kernel<6><<<grid, nt, 0, st>>>(a); break;
+    case 7: idoa_spp_kernel<7><<<grid, nt, 0, st>>>(a); break;
+    default: idoa_spp_kernel<8><<<grid, nt, 0, st>>>(a); break;
+  }
   DS_LAUNCH_CHECK();
   return DS_OK;
 }

@@ -94,3 +94,19 @@ def test_argument_validation_precedes_any_device_work():
     assert lib.ds_subband_nlms_run(ctypes.byref(np_), one, one, one, null, one, null) == EUNSUP
     assert lib.ds_srp_run(10, 4, 5, 513, 48000.0, 1024, one, one, null, one, 1, null) == EUNSUP   # tensor path: 4, 8, 16 mics
     assert lib.ds_srp_workspace_bytes(937, 16, 513, 1) == 513 * 15 * 128 * 32 * 4 and lib.ds_srp_workspace_bytes(937, 16, 513, 0) == 0
+    # 8f.3 / 8f.4 entry points
+    assert lib.ds_steering_run(4, 6, null, one, null) == EINVAL and b"null" in lib.ds_last_error()
+    assert lib.ds_steering_run(4, 9, one, one, null) == EUNSUP and b"n_mics" in lib.ds_last_error()    # > 8 sensors
+    assert lib.ds_gev_run(0, 6, one, one, one, null) == EINVAL
+    assert lib.ds_mvdr_from_cov_run(4, 12, one, one, one, null) == EUNSUP
+    assert lib.ds_ban_run(4, 6, one, null, 0.0, one, null) == EINVAL
+    assert lib.ds_phase_correction_run(1, 0, 6, one, null) == EINVAL
+    assert lib.ds_masked_cov_run(1, 10, 6, 257, 5, 20, one, 0, one, 1.0, one, one, null) == EINVAL and b"frame range" in lib.ds_last_error()
+    assert lib.ds_masked_cov_run(1, 10, 6, 257, 0, 10, one, 0, null, 1.0, one, one, null) == EINVAL    # Phi_vv without a mask
+    assert lib.ds_masked_cov_run(1, 10, 9, 257, 0, 10, one, 0, one, 1.0, one, one, null) == EUNSUP
+    assert lib.ds_apply_stream_weights_run(1, 0, 6, 257, one, 0, one, one, null) == EINVAL
+    assert lib.ds_idoa_rtf_run(1, 4, 9, 257, 0.02, one, 0, one, one, null) == EUNSUP
+    assert lib.ds_idoa_spp_run(1, 4, 4, 65, 1, one, -1, one, one, one, null, null, 0, null, null) == EINVAL   # fewer than 128 bins
+    assert b"72..127" in lib.ds_last_error()
+    assert lib.ds_idoa_spp_run(1, 4, 4, 129, 2, one, -1, one, one, one, null, one, 0, one, null) == EINVAL    # gain output needs one direction
+    assert lib.ds_idoa_rtf_state_bytes(2, 4, 129) == 2 * 7 * 129 * 8 and lib.ds_idoa_spp_state_bytes(2, 3, 129) == 2 * 3 * 4 * 129 * 8
