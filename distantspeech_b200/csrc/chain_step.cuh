@@ -50,7 +50,18 @@ template <int M> __device__ __forceinline__ void spd_inverse_packed(double (&a)[
 // keeping them live across phases (registers are the scarce resource here)
 __device__ __forceinline__ float2 ld_f2_once(const float2 *p) {
   float2 v;
+#ifdef DS_X_NOALLOC
+  // the spectrum is streamed once: keep it out of L1 so that the per-bin constants read through ld_f64_once stay there
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#else
   asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#endif
+  return v;
+}
+// one 16-byte load for a (re, im) pair: half the L2 sectors of two strided 8-byte loads
+__device__ __forceinline__ double2 ld_f64x2_once(const double *p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double ld_f64_once(const double *p) {
@@ -211,7 +222,8 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
 #ifdef DS_HOIST_A0
       const double ar = a0r[m], ai = a0i[m];
 #else
-      const double ar = ld_f64_once(a0 + 2 * m * K), ai = ld_f64_once(a0 + 2 * m * K + 1);
+      const double2 av = ld_f64x2_once(a0 + 2 * m * K);
+      const double ar = av.x, ai = av.y;
 #endif
       Yr = fma(ar, ur[m], Yr);   Yi = fma(-ai, ur[m], Yi);
       Yr2 = fma(ai, ui[m], Yr2); Yi2 = fma(ar, ui[m], Yi2);

@@ -173,6 +173,25 @@ def main():
         del mb
     del xm
     torch.cuda.empty_cache()
+    # ---- f4: Idoa spatial presence probability, 8 mics, n_fft 512 -------------------------------------------
+    from distantspeech_b200.doa.idoa import Idoa
+    Si = 128 if small else 1024
+    xi8 = torch.randn((Si, N, 8), device="cuda") * 0.1
+    ido = Idoa(mic)
+    ms = timed(lambda: ido.process(xi8, theta=30), warm=1, reps=2)
+    geo8i = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    xh = xi8[0, :16000].cpu().numpy().astype(np.float64)
+    oi = O.IdoaOracle(geo8i)
+    t0 = time.perf_counter(); oi.process(xh, theta=30); cpu = 1.0 / (time.perf_counter() - t0)
+    out.append({"config": "f4", "what": "Idoa.process 8-mic (one look direction), %d streams x 10 s (incl. API hand-off)" % Si,
+                "ms": ms, "audio_s_per_s": Si * N / FS / (ms / 1e3), "cpu_oracle_1core_audio_s_per_s_all_360_directions": cpu})
+    Xi = ido.transform.stft(xi8[0])                                                      # [K, T, M] device
+    ido2 = Idoa(mic)
+    ms = timed(lambda: ido2.estimate(Xi), warm=1, reps=2)
+    out.append({"config": "f4", "what": "Idoa.estimate 8-mic, full 360-direction map of one 10 s stream (p [257, 625, 360] on the device)",
+                "ms": ms, "audio_s_per_s": N / FS / (ms / 1e3), "bin_direction_frame_updates_per_s": 257 * 360 * (N // 256) / (ms / 1e3)})
+    del xi8
+    torch.cuda.empty_cache()
     for o in out:
         print(json.dumps(o))
 
