@@ -130,7 +130,7 @@ __device__ __forceinline__ void mcra_step_sel(McraRegs &m, double Ym1, double Y0
 // yf[m]: spectrum of this frame at bin k (complex64), ynb0/ynb1: channel-0 spectrum at k-1 / k+1.
 // smy/smv/smc: this thread's Phi_yy / Phi_vv / C columns, element e at [e * NT].
 // a0: steering vector of this bin in global memory ((re, im) pairs, mic stride 2K doubles).
-// Returns the beamformed (and gained) output bin.
+// Returns the beamformed (and gained) output bin; p_post receives the posterior speech-presence probability.
 //
 // xi and gamma are evaluated through A (Phi_vv + eps I) = I, which takes Phi_vv out of both forms:
 //   xi    = tr(A (Phi_yy' - Phi_vv))        = tr(A Phi_yy') - M + eps tr(A)
@@ -143,7 +143,7 @@ __device__ __forceinline__ void mcra_step_sel(McraRegs &m, double Ym1, double Y0
 template <int M, int NT, bool USE_C>
 __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 ynb0, float2 ynb1, int k, int K, int frm,
                                                  bool reset, McraRegs &mc, double *smy, double *smv, const double *smc,
-                                                 const double *a0, const McsppArgs &a) {
+                                                 const double *a0, const McsppArgs &a, double &p_post) {
   constexpr int NP = M * (M + 1) / 2;
     // ---- P1: A = inv(Re Phi_vv + eps I)                                     mcspp_base.py:278
     double A[NP];
@@ -271,6 +271,7 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
     const double rxi1 = rcp_pos(xi1);
     double p = rcp_pos(1.0 + q * rcp_pos(1.0 - q) * xi1 * exp_nonpos(-1.0 * (gam * rxi1)));
     p = fmin(fmax(p, a.p_min), a.p_max);
+    p_post = p;
 
     // ---- OMLSA gain and output  Y = (w^H y) G,  w = A a / den                :140-155
     // (ahead of the noise-PSD update in program order: its serial fp32 log/exp chain then overlaps the update's

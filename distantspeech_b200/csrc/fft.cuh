@@ -150,16 +150,13 @@ __device__ __forceinline__ void warp_rfft_split_store(const typename V2<T>::type
                                                       OutC *__restrict__ out, int lane) {
   typedef typename V2<T>::type C;
   constexpr int H = N / 2;
-#ifdef DS_FFT_SPLIT_POW
-  // experiment (fp32): tw_n[lane + 32 i] = tw_n[lane] * tw_n[32]^i -- two table loads per frame instead of one per pair
+  // fp32: tw_n[lane + 32 i] = tw_n[lane] * tw_n[32]^i -- two table loads per frame instead of one per bin pair
+  // (same trade as the Stockham twiddles above: -0.08 ms on the STFT); fp64 keeps the exact table
   C wrun = tw_n[lane <= H / 2 ? lane : 0];
   const C wstep = tw_n[H / 2 >= 32 ? 32 : 0];
-#endif
   for (int k = lane; k <= H / 2; k += 32) {
     if (k == 0) {
-#ifdef DS_FFT_SPLIT_POW
       if (sizeof(T) == 4) wrun = cmul(wrun, wstep);
-#endif
       const C a = buf[FPAD<T>(0)];
       OutC o0, oh;
       o0.x = a.x + a.y; o0.y = 0;
@@ -167,12 +164,8 @@ __device__ __forceinline__ void warp_rfft_split_store(const typename V2<T>::type
       out[0] = o0; out[H] = oh;
     } else {
       const C a = buf[FPAD<T>(k)], b = buf[FPAD<T>(H - k)];
-#ifdef DS_FFT_SPLIT_POW
       C w;
       if (sizeof(T) == 4) { w = wrun; wrun = cmul(wrun, wstep); } else w = tw_n[k];
-#else
-      const C w = tw_n[k];
-#endif
       const T sx = (T)0.5 * (a.x + b.x), sy = (T)0.5 * (a.y - b.y);
       const T dx = (T)0.5 * (a.x - b.x), dy = (T)0.5 * (a.y + b.y);
       const T px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;

@@ -27,7 +27,9 @@ namespace ds {
 #define DS_FAST_BOUNDS __launch_bounds__(NT, MINB)
 #endif
 
-template <int M, int NT, int MINB>
+// TAP_P: also write the posterior p per frame (the mask of the mask-based beamformers); a separate instantiation,
+// because even a predicated-off store costs the headline kernel 2 % (registers: 16.84 -> 17.17 ms measured)
+template <int M, int NT, int MINB, bool TAP_P>
 __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
   constexpr bool USE_C = DS_FAST_USE_C != 0;
   constexpr int NP = M * (M + 1) / 2;
@@ -100,7 +102,9 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(Xp + (long long)(DS_X_PREFETCH - 1) * M * K + m * K));
     }
     const bool reset = (frm > 0) && (ell_mod == 0);
-    *Yp = chain_bin_step<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a);
+    double p_post;
+    *Yp = chain_bin_step<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
+    if constexpr (TAP_P) a.tp[((long long)s * a.T + t) * K + k] = p_post;     // the only tap this kernel serves
     if (reset) ell = 0;
     ++ell; ++frm;
     ell_mod = (ell_mod + 1 == a.mc.L) ? 0 : ell_mod + 1;
@@ -124,7 +128,7 @@ static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
   constexpr int NP = M * (M + 1) / 2;
   constexpr int MINB = DS_FAST_MINB; // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
   const size_t smem = (size_t)(DS_FAST_USE_C ? 3 : 2) * NP * NT * sizeof(double);
-  auto kern = mcspp_fast_kernel<M, NT, MINB>;
+  auto kern = a.tp ? mcspp_fast_kernel<M, NT, MINB, true> : mcspp_fast_kernel<M, NT, MINB, false>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)a.S * (a.K - a.k_first);
   kern<<<(unsigned)((items + NT - 1) / NT), NT, smem, st>>>(a);

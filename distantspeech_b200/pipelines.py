@@ -225,11 +225,28 @@ class MaskBeamformer(object):
         w = B.phase_correction(w)
         return B.blind_analytic_normalization(w, Pvv, eps=self.ban_eps)
 
+    def _mask_device(self, X):
+        """Posterior speech-presence probability of McSppBase (defaults of mcspp_base.py:29-77) for every frame and bin:
+        X [S, T, M, K] complex64 CUDA -> p [S, T, K] float64 CUDA.  Runs the output-only per-bin kernel with its p tap;
+        the MVDR output it computes on the side (towards a dummy steering vector) is discarded."""
+        t = L.require_cuda()
+        S, T, M, K = X.shape
+        prm = L.McsppParams()
+        L.lib().ds_mcspp_default_params(C.byref(prm), self.n_fft, S, M, T)
+        prm.frm_cnt, prm.ell, prm.mcra_L, prm.full_state = 0, 1, 15, 0
+        state = t.zeros(L.lib().ds_mcspp_state_bytes(C.byref(prm)), dtype=t.uint8, device="cuda")
+        a0 = t.ones((M, K), dtype=t.complex128, device="cuda")
+        Y = t.empty((S, T, K), dtype=t.complex64, device="cuda")
+        p = t.empty((S, T, K), dtype=t.float64, device="cuda")
+        taps = L.McsppTaps(p.data_ptr(), None, None, None, None, None, None, None)
+        L.check(L.lib().ds_mcspp_run(C.byref(prm), L.ptr(state), L.ptr(a0), L.ptr(X), 0, L.ptr(Y), 1, C.byref(taps),
+                                     L.stream_ptr()), "ds_mcspp_run")
+        return p
+
     def process_device(self, x_dev, p_dev=None):
         """x_dev [S, M, N] float32 CUDA (N a multiple of hop), p_dev [S, T, K] float64 CUDA or None
         -> y [S, N] float32 CUDA."""
         from .beamformer import beamformer as B
-        from .noise_estimation.mcspp_base import McSppBase
         from .transform.transform import stft_device, istft_device
         t = L.require_cuda()
         S, M, N = x_dev.shape
@@ -241,8 +258,7 @@ class MaskBeamformer(object):
                         fft_fp64=self.fft_fp64)                                   # [S, T, M, K] complex64
         T = X.shape[1]
         if p_dev is None:
-            est = McSppBase(nfft=self.n_fft, channels=M)
-            p_dev = est._run(X, keep_prev_vv=False)["p"]                          # [S, T, K]
+            p_dev = self._mask_device(X)                                          # [S, T, K]
         elif tuple(p_dev.shape) != (S, T, self.K):
             raise ValueError("mask must be [S, T, K] = %s, got %s" % ((S, T, self.K), tuple(p_dev.shape)))
         self.p = p_dev

@@ -228,7 +228,10 @@ typedef struct ds_mcspp_taps { /* optional per-frame outputs, any may be NULL   
  *   a0   [M][K] c128 steering vectors (or NULL: estimator only, Yout unused)
  *   X    [S][T][M][K] c64 (x_is_c128 = 0) or c128 (x_is_c128 = 1)
  *   Yout [S][T][K] c64 beamformed+postfiltered spectrum (or NULL)
- *   apply_gain: multiply by the OMLSA gain G (1) or output the plain MVDR (0)    */
+ *   apply_gain: multiply by the OMLSA gain G (1) or output the plain MVDR (0)
+ * Kernel selection: full_state = 0 with a0, Yout, c64 input and either no tap or the p tap alone runs
+ * the output-only kernel (the headline path; with the p tap it visits every bin so that the mask of
+ * the mask-based beamformers is complete); anything else runs the full-state kernel.             */
 int ds_mcspp_run(const ds_mcspp_params *p, void *state, const void *a0, const void *X,
                  int x_is_c128, void *Yout, int apply_gain, const ds_mcspp_taps *taps,
                  void *stream);
