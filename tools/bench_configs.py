@@ -162,7 +162,7 @@ def main():
         ms = timed(lambda: mb.process_device(xm), warm=1, reps=2)
         pm = mb.p
         ms_w = timed(lambda: mb.weights_device(mb.Phi_xx, mb.Phi_vv), warm=1, reps=3)
-        row = {"config": "f3", "what": "mask-based %s 8-mic, %d streams x 10 s (STFT + McSppBase mask with all taps + covariances + "
+        row = {"config": "f3", "what": "mask-based %s 8-mic, %d streams x 10 s (STFT + McSppBase mask from the output-only kernel's p tap + covariances + "
                                       "weights + apply + ISTFT)" % (method.upper(), Sm),
                "ms": ms, "audio_s_per_s": Sm * N / FS / (ms / 1e3), "ms_weights_only": ms_w,
                "eigenproblems_per_s": Sm * 257 / (ms_w / 1e3)}
