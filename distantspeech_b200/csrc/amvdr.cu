@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(NT) amvdr_kernel(AmvdrArgs a) {
   double ar[M], ai[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) { const double2 v = a.a[(long long)m * K + k]; ar[m] = v.x; ai[m] = v.y; }
-  int frm = a.frm_cnt, ell = a.ell;
+  int frm = a.frm_cnt, ell = a.ell % a.mc.L;   // ell is kept modulo L: no integer division per frame (mcra.py:52-56)
   const double ay = a.alpha_y, one_m_ay = 1.0 - a.alpha_y, av = a.alpha_v, one_m_av = 1.0 - a.alpha_v;
 
+  startup_dephase(8000);
   for (int t = 0; t < a.T; ++t) {
     const float2 *Xp = a.X + ((long long)s * a.T + t) * M * K + k;
     double zr[M], zi[M];
@@ -70,10 +71,11 @@ __global__ void __launch_bounds__(NT) amvdr_kernel(AmvdrArgs a) {
     if (k > 0) { const float2 v = Xp[-1]; Ym1 = power_c((double)v.x, (double)v.y); }
     if (k < K - 1) { const float2 v = Xp[1]; Yp1 = power_c((double)v.x, (double)v.y); }
     const double Y0 = power_c(zr[0], zi[0]);
-    const bool reset = (frm > 0) && (ell % a.mc.L == 0);
+    const bool reset = (frm > 0) && (ell == 0);
     mcra_step(mS, mSmin, mStmp, mp, mlam, Ym1, Y0, Yp1, k, K, frm, reset, a.mc);
     if (reset) ell = 0;
     ++ell; ++frm;
+    if (ell == a.mc.L) ell = 0;
     if (a.p_out) a.p_out[((long long)s * a.T + t) * K + k] = mp;
 
     // ---- Ryy = alpha_y Ryy + (1 - alpha_y) z z^H                     :86

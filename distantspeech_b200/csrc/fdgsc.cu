@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(FD_NT, 2) fdgsc_kernel(FdgscArgs a, const type
   T *fb = reinterpret_cast<T *>(buf);
   const T invN = (T)1 / (T)N;
   const int nblk = a.Ns / L;
-  int frm = a.frm_cnt, ell = a.ell;
+  int frm = a.frm_cnt, ell = a.ell % a.mc.L;   // ell is kept modulo L: no integer division per frame (mcra.py:52-56)
 #define FIDX(n) (2 * FPAD<T>((n) >> 1) + ((n) & 1))
 
   for (int blk = 0; blk < nblk; ++blk) {
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(FD_NT, 2) fdgsc_kernel(FdgscArgs a, const type
     // ---- S5: BM input power, MCRA on mic 0, adaptation-control heuristics ------------
     double p_loc[2] = {0.0, 0.0};
     {
-      const bool reset = (frm > 0) && (ell % a.mc.L == 0);
+      const bool reset = (frm > 0) && (ell == 0);
       int q = 0;
       for (int k = tid; k < K; k += FD_NT, ++q) {
         const C2 v = Xf[k];
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(FD_NT, 2) fdgsc_kernel(FdgscArgs a, const type
       }
       if (reset) ell = 0;
       ++ell; ++frm;
+      if (ell == a.mc.L) ell = 0;
     }
     // mean(p[32:128]) > 0.8  ->  p[:32] = max(p[:32], 0.8)            (FDGSC.py:247-249)
     const double mid = block_sum((tid >= 32 && tid < 128) ? p_loc[0] : 0.0, red) / 96.0;

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(NT) gsc_kernel(GscArgs a) {
   int frm = a.frm_cnt;
   const double one_m_alpha = 1.0 - a.alpha;
 
+  startup_dephase(8000);
   for (int t = 0; t < a.T; ++t, ++frm) {
     double yr[M], yi[M];
     {

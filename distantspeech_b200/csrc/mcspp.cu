@@ -34,16 +34,17 @@ __global__ void mcra_kernel(McraArgs a) {
   const int s = (int)(g / a.K), k = (int)(g % a.K);
   double *st = a.state + (long long)s * 5 * a.K + k;
   double S = st[0], Smin = st[(long long)a.K], Stmp = st[2LL * a.K], p = st[3LL * a.K], lam = st[4LL * a.K];
-  int frm = a.frm_cnt, ell = a.ell;
+  int frm = a.frm_cnt, ell = a.ell % a.c.L;   // ell is kept modulo L: no integer division per frame (mcra.py:52-56)
   for (int t = 0; t < a.T; ++t) {
     const double *y = a.Y + ((long long)s * a.T + t) * a.K;
     const double Y0 = y[k];
     const double Ym1 = (k > 0) ? y[k - 1] : 0.0;
     const double Yp1 = (k < a.K - 1) ? y[k + 1] : 0.0;
-    const bool reset = (frm > 0) && (ell % a.c.L == 0);
+    const bool reset = (frm > 0) && (ell == 0);
     mcra_step(S, Smin, Stmp, p, lam, Ym1, Y0, Yp1, k, a.K, frm, reset, a.c);
     if (reset) ell = 0;
     ++ell; ++frm;
+    if (ell == a.c.L) ell = 0;
     const long long o = ((long long)s * a.T + t) * a.K + k;
     if (a.lam_out) a.lam_out[o] = lam;
     if (a.p_out) a.p_out[o] = p;
@@ -102,9 +103,10 @@ __global__ void __launch_bounds__(NT) mcspp_kernel(McsppArgs a) {
 #pragma unroll
     for (int m = 0; m < M; ++m) { double2 v = a.a0[(long long)m * K + k]; ar[m] = v.x; ai[m] = v.y; }
   }
-  int frm = a.frm_cnt, ell = a.ell;
+  int frm = a.frm_cnt, ell = a.ell % a.mc.L;   // ell is kept modulo L: no integer division per frame (mcra.py:52-56)
   const double one_m_alpha = 1.0 - a.alpha;
 
+  startup_dephase(8000);
   for (int t = 0; t < a.T; ++t) {
     const long long xb = ((long long)s * a.T + t) * M * K;
     double yr[M], yi[M];
@@ -190,10 +192,11 @@ __global__ void __launch_bounds__(NT) mcspp_kernel(McsppArgs a) {
     gam = fmin(fmax(gam, a.snr_min), a.snr_max);
 
     // ---- prior from MCRA on channel 0                                :98-122
-    const bool reset = (frm > 0) && (ell % a.mc.L == 0);
+    const bool reset = (frm > 0) && (ell == 0);
     mcra_step(mS, mSmin, mStmp, mp, mlam, Ym1, Y0, Yp1, k, K, frm, reset, a.mc);
     if (reset) ell = 0;
     ++ell; ++frm;
+    if (ell == a.mc.L) ell = 0;
     double q = sqrt(1.0 - mp);
     q = fmin(fmax(q, a.q_min), a.q_max);
     // ---- posterior SPP                                               :124-138

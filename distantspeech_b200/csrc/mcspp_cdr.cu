@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) cdr_prior_kernel(CdrArgs a) {
          mp = blob[(long long)(CS_MCRA + 3) * K], mlam = blob[(long long)(CS_MCRA + 4) * K];
   const double Fn = a.Fn[k], Fn2 = __dmul_rn(Fn, Fn);
   const double al = a.alpha_cdr, om = __dsub_rn(1.0, al);
-  int frm = a.frm_cnt, ell = a.ell;
+  int frm = a.frm_cnt, ell = a.ell % a.mc.L;   // ell is kept modulo L: no integer division per frame (mcra.py:52-56)
   double cdr = 0.0;
   for (int t = 0; t < a.T; ++t) {
     const long long base = ((long long)s * a.T + t) * 4 * K + k;
@@ -135,10 +135,11 @@ __global__ void __launch_bounds__(128) cdr_prior_kernel(CdrArgs a) {
     const double Y0 = load_pow0(a, i0 + k);
     const double Ym1 = (k > 0) ? load_pow0(a, i0 + k - 1) : 0.0;
     const double Yp1 = (k < K - 1) ? load_pow0(a, i0 + k + 1) : 0.0;
-    const bool reset = (frm > 0) && (ell % a.mc.L == 0);
+    const bool reset = (frm > 0) && (ell == 0);
     mcra_step(mS, mSmin, mStmp, mp, mlam, Ym1, Y0, Yp1, k, K, frm, reset, a.mc);
     if (reset) ell = 0;
     ++ell; ++frm;
+    if (ell == a.mc.L) ell = 0;
     const double gam = sqrt(__dmul_rn(G, mp));      // McCDR.estimation return value
     const long long o = ((long long)s * a.T + t) * K + k;
     a.q[o] = __dsub_rn(1.0, gam);

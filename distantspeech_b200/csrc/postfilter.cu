@@ -43,12 +43,12 @@ __global__ void omlsa_multi_kernel(OmlsaArgs a) {
   for (int c = 0; c < M - 1; ++c) zeta_U[c] = ST(o + 1 + c);
   o += M;
   double lambda_d = ST(o), gamma = ST(o + 1), G_H1 = ST(o + 2), p = ST(o + 3), G = ST(o + 4), q_hat = ST(o + 5), xi_hat = ST(o + 6);
-  int frm = a.frm_cnt, ell = a.ell, first = a.first_frame;
+  int frm = a.frm_cnt, ell = a.ell % a.mc.L, first = a.first_frame;   // ell is kept modulo L: no integer division per frame (mcra.py:52-56)
   const double w0 = 0.25, w1 = 0.5, w2 = 0.25;
   for (int t = 0; t < a.T; ++t) {
     const double *yt = a.y + ((long long)s * a.T + t) * K;
     const double y0 = yt[k], ym = (k > 0) ? yt[k - 1] : 0.0, yp = (k < K - 1) ? yt[k + 1] : 0.0;
-    const bool reset = (frm > 0) && (ell % a.mc.L == 0);
+    const bool reset = (frm > 0) && (ell == 0);
     mcra_step(mc[0][0], mc[0][1], mc[0][2], mc[0][3], mc[0][4], ym, y0, yp, k, K, frm, reset, a.mc);   // :82
     const double MU_Y = mc[0][4];
     double u0[PF_MAXM], um[PF_MAXM], up[PF_MAXM], MU_U[PF_MAXM];
@@ -60,6 +60,7 @@ __global__ void omlsa_multi_kernel(OmlsaArgs a) {
     }
     if (reset) ell = 0;
     ++ell; ++frm;
+    if (ell == a.mc.L) ell = 0;
     if (first) {                                                          // :87-93
       first = 0;
       lambda_d = y0; zeta_Y = y0;
