@@ -1,7 +1,7 @@
 // chain_step.cuh -- one frame of the McSppBase + MVDR + OMLSA chain for one frequency bin
-// (output-only state: packed real parts of Phi_yy / Phi_vv in shared memory).  Shared by the
-// stand-alone per-bin kernel (mcspp_fast.cu) and the fused STFT->chain->ISTFT kernel
-// (chain_fused.cu).  Reference citations: mcspp_base.py:262-297, :140-155, beamformer.py:133-155.
+// (output-only state: packed real parts of Phi_yy / Phi_vv in shared memory), used by the per-bin
+// kernel of the headline path (mcspp_fast.cu); gsc.cu shares the sweep inverse and the compile-time
+// loop helpers.  Reference citations: mcspp_base.py:262-297, :140-155, beamformer.py:133-155.
 #pragma once
 #include <type_traits>
 #include "mcspp_args.cuh"

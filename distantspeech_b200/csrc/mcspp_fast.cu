@@ -3,12 +3,12 @@
 //
 // Same arithmetic as mcspp_kernel (mcspp.cu) -- see the reference citations
 // there -- restructured for the fp64 pipe:
-//   * every quadratic form is evaluated against the packed upper triangle
-//     (xi = sum A_ij X_ij, gamma = sum X_ij Re(conj(u_i) u_j),
-//      a^H A a = sum A_ij Re(conj(a_i) a_j)), so no M-vector temporaries
-//     besides u = A y survive the inverse;
-//   * the live set stays under 168 registers => 3 CTAs x 128 threads per SM
-//     next to 3 x 72 KB of shared-memory state, no local-memory spills.
+//   * every quadratic form is evaluated against the packed upper triangle, xi and gamma through
+//     A (Phi_vv + eps I) = I (chain_step.cuh), so no M-vector temporaries besides u = A y survive the
+//     inverse and the updated Phi_yy takes over A's registers;
+//   * the frame loop is one basic block (branch-free MCRA / exp / sqrt, no integer division);
+//   * 4 CTAs x 64 threads per SM at 255 registers next to 4 x 55 KB of shared-memory state, no
+//     local-memory traffic inside the frame loop; the CTAs are de-phased once at start-up.
 #include "chain_step.cuh"
 
 namespace ds {
