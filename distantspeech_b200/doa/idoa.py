@@ -58,9 +58,9 @@ class Idoa(object):
 
     def _attr(self, idx):
         """mu_Delta / mu_Delta_h0 / var_Delta_h0 / p as [K, n_slots] (first stream), like the reference's attributes."""
-        t = L.require_cuda()
         if self._spp_state is None:
             return None
+        t = L.require_cuda()
         v = self._spp_state.view(t.float64).reshape(self._S, len(self._slots), 4, self.half_bin)[0, :, idx, :]
         return (v + (0.1 if idx == 2 else 0.0)).t().cpu().numpy()
 

@@ -30,3 +30,18 @@ def test_idoa_oracle_golden(tag):
     c = O.IdoaOracle(geo)
     p1 = c.estimate(X, theta=40)
     assert np.allclose(p1[:, :, [40, 41]], g[tag + "_p_theta40"], rtol=0, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("tag", ["c4", "l6"])
+def test_idoa_host_class_rtf_table(tag):
+    """host logic of the drop-in class (no device work): direction grid and free-field RTFs Psi (idoa.py:41-44, 73-76)"""
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.doa.idoa import Idoa
+    g = golden("idoa.npz")
+    arr, M, r, n_fft = CASES[tag]
+    a = Idoa(MicArray(arrayType=arr, r=r, M=M, n_fft=n_fft))
+    assert a.n_theta == (360 if arr == "circular" else 180) and a.idoa_dim == M - 1 and a.half_bin == n_fft // 2 + 1
+    assert np.allclose(a.Psi[:, :, g[tag + "_sel"]], g[tag + "_Psi_sel"], rtol=0, atol=1e-12)
+    assert a.p is None and a.mu_Delta is None                       # no state before the first call
+    with pytest.raises(NotImplementedError):
+        a.process(np.zeros((n_fft * 4, M)), pre_emphsis=True)
