@@ -87,3 +87,20 @@ def test_eig_core_golden_matrices(eig_host):
         assert np.max(np.abs(out - g["steer"][k])) < 1e-9, k
         assert eig_host.eig_host_gev(6, _p(A), _p(B), _p(out)) == 0
         assert _same_up_to_sign(out[None], g["w_gev_raw"][k][None], 1e-8), k
+
+
+def test_mask_beamformer_host_logic():
+    """constructor-level validation of the pipeline class and the loud failure without a device (no CPU fallback)"""
+    import torch
+    from distantspeech_b200 import _lib
+    from distantspeech_b200.pipelines import MaskBeamformer
+    from distantspeech_b200.beamformer.beamformer import steering
+    with pytest.raises(ValueError):
+        MaskBeamformer(8, method="lcmv")
+    bf = MaskBeamformer(6, n_fft=512, hop=256, method="gev")
+    assert bf.K == 257 and abs(bf.W0 - 256.0) < 1e-9 and bf.w is None
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DsError):
+            steering(np.eye(4, dtype=complex)[None])
+        with pytest.raises(_lib.DsError):
+            bf.process(np.zeros((256 * 4, 6), np.float32))
