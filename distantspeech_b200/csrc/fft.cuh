@@ -225,13 +225,26 @@ __device__ __forceinline__ void warp_irfft_unscaled(typename V2<T>::type *buf, c
   // merge: Z[k] = s + f, Z[H-k] = conj(s - f), s = a + conj(b), d = a - conj(b),
   // f = i conj(W^k) d   (everything x2 relative to numpy; total scale N)
   // we store conj(Z) so that a forward FFT followed by a conjugate is the inverse.
+#ifdef DS_FFT_MERGE_POW
+  // next-round A/B (default off): merge twiddles by the same recurrence as warp_rfft_split_store
+  C wrun = tw_n[lane <= H / 2 ? lane : 0];
+  const C wstep = tw_n[H / 2 >= 32 ? 32 : 0];
+#endif
   for (int k = lane; k <= H / 2; k += 32) {
     if (k == 0) {
+#ifdef DS_FFT_MERGE_POW
+      if (sizeof(T) == 4) wrun = cmul(wrun, wstep);
+#endif
       T a = buf[FPAD<T>(0)].x, b = buf[FPAD<T>(H)].x;
       buf[FPAD<T>(0)] = mk2<T>(a + b, -(a - b));
     } else {
       C a = buf[FPAD<T>(k)], b = buf[FPAD<T>(H - k)];
+#ifdef DS_FFT_MERGE_POW
+      C w;
+      if (sizeof(T) == 4) { w = wrun; wrun = cmul(wrun, wstep); } else w = tw_n[k];
+#else
       C w = tw_n[k];
+#endif
       T sx = a.x + b.x, sy = a.y - b.y;
       T dx = a.x - b.x, dy = a.y + b.y;
       // conj(w) * d
