@@ -110,3 +110,16 @@ def test_argument_validation_precedes_any_device_work():
     assert b"72..127" in lib.ds_last_error()
     assert lib.ds_idoa_spp_run(1, 4, 4, 129, 2, one, -1, one, one, one, null, one, 0, one, null) == EINVAL    # gain output needs one direction
     assert lib.ds_idoa_rtf_state_bytes(2, 4, 129) == 2 * 7 * 129 * 8 and lib.ds_idoa_spp_state_bytes(2, 3, 129) == 2 * 3 * 4 * 129 * 8
+
+
+def test_bench_static_inputs():
+    """bench.py parses on this interpreter and the ncu-derived figures it quotes are where it looks for them"""
+    import ast
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ast.parse(open(os.path.join(root, "bench.py")).read())
+    tj = json.load(open(os.path.join(root, "profiles", "traffic.json")))["mcspp_fast_kernel"]
+    assert tj["dram_bytes_per_stream_10s"] > 5e6 and 1500 < tj["fp64_flop_per_bin_frame"] < 2500 and 0 < tj["ncu_pipe_fp64_pct"] < 100
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert "audio-s/s" in base["metric"]
