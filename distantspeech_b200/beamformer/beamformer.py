@@ -315,9 +315,12 @@ class beamformer(object):
 
     # ---- diagnostics (notebook plotting only, host NumPy) ----------------
     def compute_array_gain(self, weights, steer_vector, Rvv, return_db=False):
+        """|w^H a|^2 / |w^H Rvv w| (beamformer.py:435-464).  Like the reference the result is **[bins, bins]**, not the
+        documented [bins]: the numerator is lifted to [K, 1] and the quadratic form stays [K, 1, 1] (:456-458), so
+        NumPy broadcasts to G[i, j] = |num_j|^2 / |den_i| -- the per-bin array gain is the diagonal."""
         num = np.einsum('ij, ij->i', weights.conj(), steer_vector)
-        den = weights[:, np.newaxis, :].conj() @ Rvv @ weights[..., None]
-        G = np.abs(num[..., None]) ** 2 / np.abs(den[..., 0])
+        den = weights[:, np.newaxis, :].conj() @ Rvv @ weights[..., None]          # [K, 1, 1]
+        G = np.abs(num[..., None]) ** 2 / np.abs(den)                               # [K, K, 1]
         if return_db:
             G = 10 * np.log10(G + 1e-6)
         return G.squeeze()

@@ -145,3 +145,40 @@ def test_idoa_live(ref):
         assert np.max(np.abs(yr - yo)) < 1e-12
         X = rf2.transform.stft(x)
         assert np.max(np.abs(rf2.estimate(X, theta=40) - o2.estimate(X, theta=40))) < 1e-12
+
+
+def test_srp_live(ref):
+    """a18: O.srp_angle_spectrum against srp.compute_angle_spectrum (doa/srp.py:17-53) on a fresh input, PHAT on and off"""
+    from DistantSpeech.beamformer.MicArray import MicArray
+    from DistantSpeech.doa.srp import srp
+    import DistantSpeech.doa.srp as srp_mod
+    srp_mod.tqdm = lambda it, *a, **k: it
+    geo = O.MicGeometry("circular", r=0.04, M=6, n_fft=128)
+    x = np.ascontiguousarray(O.synth_streams(1, geo, 64 * 12, look_deg=(75.0, 0.0), seed0=909)[0].T).astype(np.float64)
+    with _quiet():
+        mic = MicArray(arrayType="circular", r=0.04, M=6, n_fft=128)
+    for phat in (True, False):
+        with _quiet():
+            Pr, pr = srp(mic).compute_angle_spectrum(x.copy(), phat=phat)
+        Po, po = O.srp_angle_spectrum(x, geo, phat=phat)
+        assert np.max(np.abs(Pr - Po)) <= 1e-12 * np.max(np.abs(Pr)) and np.array_equal(pr, po)
+
+
+def test_diagnostics_live(ref):
+    """a19: the drop-in class's host diagnostics against beamformer.py:435-534 (array gain is [bins, bins] in the reference)"""
+    from DistantSpeech.beamformer.MicArray import MicArray
+    from DistantSpeech.beamformer.beamformer import beamformer
+    from distantspeech_b200.beamformer.MicArray import MicArray as OurMic
+    from distantspeech_b200.beamformer.beamformer import beamformer as our_bf
+    with _quiet():
+        mic = MicArray(arrayType="linear", r=0.03, M=5, n_fft=32)
+    rb, ob = beamformer(mic, frame_len=32, hop=16, nfft=32), our_bf(OurMic(arrayType="linear", r=0.03, M=5, n_fft=32), 32, 16, 32)
+    W = rb.compute_weights((70, 0), "SD")
+    assert np.allclose(ob.compute_weights((70, 0), "SD"), W, rtol=1e-9, atol=1e-12)
+    a0 = rb.compute_steering_vector_from_doa((70, 0))
+    Gr, Go = rb.compute_array_gain(W, a0, rb.Fvv), ob.compute_array_gain(W, a0, ob.Fvv)
+    assert Gr.shape == Go.shape == (17, 17) and np.allclose(Gr, Go, rtol=1e-11)
+    for a, b in zip(rb.compute_wng_di(W, look_angle=[70, 0]), ob.compute_wng_di(W, look_angle=[70, 0])):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-10)
+    assert np.allclose(rb.compute_beampattern(mic, weights=W.T.copy()), ob.compute_beampattern(ob.MicArray, weights=W.T.copy()),
+                       rtol=0, atol=1e-9)
