@@ -255,6 +255,10 @@ def _declare(lib):
     lib.ds_chain_workspace_bytes.restype = C.c_size_t
     lib.ds_chain_run.argtypes = [C.POINTER(ChainParams), vp, vp, vp, vp, vp, vp, vp]
     lib.ds_chain_run_profiled.argtypes = [C.POINTER(ChainParams), vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    lib.ds_chain_run_io.argtypes = [C.POINTER(ChainParams), vp, vp, vp, vp, vp, i32, vp, i32, vp]
+    lib.ds_stft_pcm16_run.argtypes = [C.POINTER(StftParams), vp, vp, vp, vp, vp]
+    lib.ds_istft_pcm16_run.argtypes = [C.POINTER(IstftParams), vp, vp, vp, vp, vp]
+    lib.ds_double_to_pcm16_run.argtypes = [C.c_size_t, vp, vp, vp]
 
 
 def lib():
@@ -335,8 +339,8 @@ def device_window(window: np.ndarray, n_fft: int):
         w = np.pad(w, (lpad, n_fft - w.shape[0] - lpad))
     key = (t.cuda.current_device(), n_fft, w.tobytes())
     if key not in _window_cache:
-        if len(_window_cache) > 64:
-            _window_cache.clear()
+        while len(_window_cache) >= 64:
+            _window_cache.pop(next(iter(_window_cache)))      # evict the oldest entry only
         _window_cache[key] = t.as_tensor(w).to("cuda")
     return _window_cache[key]
 

@@ -42,12 +42,18 @@ def pcm16_to_float(pcm):
 
 def float_to_pcm16(audio):
     """float samples -> ``(audio * 32767).astype(int16)`` on the device (save_audio, utils.py:193; the cast
-    truncates toward zero like NumPy's)."""
+    truncates toward zero like NumPy's).  The product is taken in the input's precision, like NumPy does:
+    float64 arrays (what Transform.istft and the pipelines return) multiply in double, float32 arrays in float."""
     t = L.require_cuda()
     as_torch = isinstance(audio, t.Tensor)
-    d = (audio if as_torch else t.as_tensor(np.ascontiguousarray(audio, dtype=np.float32))).to("cuda").float().contiguous()
+    d = (audio if as_torch else t.as_tensor(np.ascontiguousarray(audio))).to("cuda").contiguous()
+    if d.dtype not in (t.float32, t.float64):
+        d = d.to(t.float64)
     out = t.empty(d.shape, dtype=t.int16, device="cuda")
-    L.check(L.lib().ds_float_to_pcm16_run(d.numel(), L.ptr(d), L.ptr(out), L.stream_ptr()), "ds_float_to_pcm16_run")
+    if d.dtype == t.float64:
+        L.check(L.lib().ds_double_to_pcm16_run(d.numel(), L.ptr(d), L.ptr(out), L.stream_ptr()), "ds_double_to_pcm16_run")
+    else:
+        L.check(L.lib().ds_float_to_pcm16_run(d.numel(), L.ptr(d), L.ptr(out), L.stream_ptr()), "ds_float_to_pcm16_run")
     return out if as_torch else out.cpu().numpy()
 
 

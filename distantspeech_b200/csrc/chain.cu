@@ -42,11 +42,16 @@ size_t ds_chain_state_bytes(const ds_chain_params *p) { return p ? chain_layout(
 size_t ds_chain_workspace_bytes(const ds_chain_params *p) { return p ? chain_layout(p).ws_total : 0; }
 
 static int chain_run_impl(const ds_chain_params *p, const double *window, const void *a0, void *state, void *workspace,
-                          const float *x, float *y, void *stream, cudaEvent_t *ev);
+                          const void *x, int x_pcm16, void *y, int y_pcm16, void *stream, cudaEvent_t *ev);
 
 int ds_chain_run(const ds_chain_params *p, const double *window, const void *a0, void *state, void *workspace,
                  const float *x, float *y, void *stream) {
-  return chain_run_impl(p, window, a0, state, workspace, x, y, stream, nullptr);
+  return chain_run_impl(p, window, a0, state, workspace, x, 0, y, 0, stream, nullptr);
+}
+
+int ds_chain_run_io(const ds_chain_params *p, const double *window, const void *a0, void *state, void *workspace,
+                    const void *x, int x_is_pcm16, void *y, int y_is_pcm16, void *stream) {
+  return chain_run_impl(p, window, a0, state, workspace, x, x_is_pcm16, y, y_is_pcm16, stream, nullptr);
 }
 
 int ds_chain_run_profiled(const ds_chain_params *p, const double *window, const void *a0, void *state, void *workspace,
@@ -54,7 +59,7 @@ int ds_chain_run_profiled(const ds_chain_params *p, const double *window, const 
   DS_CHECK_ARG(phase_ms_h, "ds_chain_run_profiled: null argument");
   cudaEvent_t ev[4];
   for (int i = 0; i < 4; ++i) DS_CUDA(cudaEventCreate(&ev[i]));
-  int rc = chain_run_impl(p, window, a0, state, workspace, x, y, stream, ev);
+  int rc = chain_run_impl(p, window, a0, state, workspace, x, 0, y, 0, stream, ev);
   if (rc == DS_OK) {
     DS_CUDA(cudaEventSynchronize(ev[3]));
     for (int i = 0; i < 3; ++i) DS_CUDA(cudaEventElapsedTime(&phase_ms_h[i], ev[i], ev[i + 1]));
@@ -64,7 +69,7 @@ int ds_chain_run_profiled(const ds_chain_params *p, const double *window, const 
 }
 
 static int chain_run_impl(const ds_chain_params *p, const double *window, const void *a0, void *state, void *workspace,
-                          const float *x, float *y, void *stream, cudaEvent_t *ev) {
+                          const void *x, int x_pcm16, void *y, int y_pcm16, void *stream, cudaEvent_t *ev) {
   DS_CHECK_ARG(p && window && a0 && state && workspace && x && y, "ds_chain_run: null argument");
   DS_CHECK_ARG(p->hop >= 1 && p->hop <= p->est.n_fft, "ds_chain_run: bad hop");
   DS_CHECK_ARG(p->n_samples >= p->hop && p->n_samples % p->hop == 0, "ds_chain_run: n_samples must be a positive multiple of hop");
@@ -75,7 +80,10 @@ static int chain_run_impl(const ds_chain_params *p, const double *window, const 
   sp.n_samples = p->n_samples; sp.mode = DS_STFT_STREAMING; sp.fft_fp64 = p->fft_fp64; sp.out_c128 = 0;
   cudaStream_t cst = (cudaStream_t)stream;
   if (ev) DS_CUDA(cudaEventRecord(ev[0], cst));
-  int rc = ds_stft_run(&sp, window, (float *)(st8 + L.hist_off), x, ws8 + L.X_off, stream);
+  // int16 PCM in / out: load_audio's and save_audio's scaling (beamformer/utils.py:184-185, :193) are fused into the
+  // analysis kernel's first register-fed pass and the synthesis kernel's store -- no staging buffer, half the bytes
+  int rc = x_pcm16 ? ds_stft_pcm16_run(&sp, window, (float *)(st8 + L.hist_off), (const int16_t *)x, ws8 + L.X_off, stream)
+                   : ds_stft_run(&sp, window, (float *)(st8 + L.hist_off), (const float *)x, ws8 + L.X_off, stream);
   if (rc != DS_OK) return rc;
   if (ev) DS_CUDA(cudaEventRecord(ev[1], cst));
   ds_mcspp_params ep = p->est;
@@ -86,7 +94,8 @@ static int chain_run_impl(const ds_chain_params *p, const double *window, const 
   ds_istft_params ip;
   ip.n_fft = p->est.n_fft; ip.hop = p->hop; ip.n_streams = p->est.n_streams; ip.n_ch = 1; ip.n_frames = L.T;
   ip.mode = DS_STFT_STREAMING; ip.fft_fp64 = p->fft_fp64; ip.in_c128 = 0; ip.scale = p->scale;
-  rc = ds_istft_run(&ip, window, (float *)(st8 + L.tail_off), ws8 + L.Y_off, y, stream);
+  rc = y_pcm16 ? ds_istft_pcm16_run(&ip, window, (float *)(st8 + L.tail_off), ws8 + L.Y_off, (int16_t *)y, stream)
+               : ds_istft_run(&ip, window, (float *)(st8 + L.tail_off), ws8 + L.Y_off, (float *)y, stream);
   if (rc != DS_OK) return rc;
   if (ev) DS_CUDA(cudaEventRecord(ev[3], cst));
   return DS_OK;

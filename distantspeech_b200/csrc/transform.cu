@@ -16,7 +16,21 @@ namespace ds {
 struct StftArgs {
   const float *x; float *history; void *X; const double *window;
   int S, C, Ns, T, hop, mode, out_c128;
+  const short *x16;     // int16 PCM input instead of x (fused load_audio scaling, beamformer/utils.py:184-185)
 };
+
+// load_audio's scaling float32(pcm) / 32767.0f (utils.py:184-185; iinfo(int16).max, not 32768) without a division:
+// q = x r, rem = fma(-q, 32767, x), q' = fma(rem, r, q) with r = fl(1 / 32767) equals the correctly rounded
+// quotient for every int16 value (checked exhaustively on the host, tests/test_pcm_fused_cpu.py).
+__device__ __forceinline__ float pcm16_scale(short v) {
+  const float x = (float)v, r = 1.0f / 32767.0f;
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-q, 32767.0f, x), r, q);
+}
+// sample g of a row that is float32 or int16 PCM
+template <bool PCM> __device__ __forceinline__ float load_sample(const float *xs, const short *xs16, int g) {
+  if constexpr (PCM) return pcm16_scale(xs16[g]); else return xs[g];
+}
 
 constexpr int STFT_WARPS = 8;
 
@@ -24,7 +38,7 @@ constexpr int STFT_WARPS = 8;
 // memory; interior frames of 16-byte aligned rows are read with float4 loads
 // ([stream, mic, sample] rows are contiguous), everything else (history, reflect
 // padding, odd alignment) takes the scalar path.
-template <int N, typename T>
+template <int N, typename T, bool PCM>
 __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const typename V2<T>::type *__restrict__ tw_h_g,
                                                               const typename V2<T>::type *__restrict__ tw_n_g) {
   typedef typename V2<T>::type C2;
@@ -45,7 +59,8 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
   for (unsigned f = blockIdx.x * STFT_WARPS + warp; f < total; f += gridDim.x * STFT_WARPS) {
     const unsigned sc = f / (unsigned)a.T;
     const int t = (int)(f - sc * (unsigned)a.T);
-    const float *xs = a.x + (size_t)sc * a.Ns;
+    const float *xs = PCM ? nullptr : a.x + (size_t)sc * a.Ns;
+    const short *xs16 = PCM ? a.x16 + (size_t)sc * a.Ns : nullptr;
     int g0;
     if (a.mode == DS_STFT_STREAMING) g0 = t * a.hop - ov;
     else if (a.mode == DS_STFT_CENTER) g0 = t * a.hop - N / 2;
@@ -53,12 +68,14 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
     const unsigned s = sc / (unsigned)a.C;
     const unsigned c = sc - s * (unsigned)a.C;
     const size_t o = (((size_t)s * a.T + t) * a.C + c) * K;
-    const bool interior = (g0 >= 0) && (g0 + N <= a.Ns) && ((reinterpret_cast<size_t>(xs + g0) & 7) == 0);
+    const bool interior = (g0 >= 0) && (g0 + N <= a.Ns) &&
+                          (PCM ? ((reinterpret_cast<size_t>(xs16 + g0) & 3) == 0) : ((reinterpret_cast<size_t>(xs + g0) & 7) == 0));
     if (interior) {
-      // frame read straight from global memory in first-pass order (coalesced float2 rows)
+      // frame read straight from global memory in first-pass order (coalesced float2 / short2 rows)
       typedef FftFirst<H, T> F1;
       C2 v[F1::PER][F1::R];
       const float2 *src = reinterpret_cast<const float2 *>(xs + g0);
+      const short2 *src16 = reinterpret_cast<const short2 *>(xs16 + g0);
       const C2 *w2 = reinterpret_cast<const C2 *>(win);
 #pragma unroll
       for (int i = 0; i < F1::PER; ++i) {
@@ -67,7 +84,9 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
 #pragma unroll
           for (int r = 0; r < F1::R; ++r) {
             const int e = j + r * F1::NB;
-            const float2 xv = __ldg(src + e);
+            float2 xv;
+            if constexpr (PCM) { const short2 pv = __ldg(src16 + e); xv = make_float2(pcm16_scale(pv.x), pcm16_scale(pv.y)); }
+            else xv = __ldg(src + e);
             const C2 wv = w2[e];
             v[i][r] = mk2<T>(mul_rn((T)xv.x, wv.x), mul_rn((T)xv.y, wv.y));
           }
@@ -80,11 +99,11 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
         int g = g0 + n;
         float v;
         if (a.mode == DS_STFT_STREAMING) {
-          v = (g < 0) ? hs[ov + g] : xs[g];
+          v = (g < 0) ? hs[ov + g] : load_sample<PCM>(xs, xs16, g);
         } else {
           if (g < 0) g = -g;                              // np.pad(mode="reflect")
           if (g >= a.Ns) g = 2 * (a.Ns - 1) - g;
-          v = xs[g];
+          v = load_sample<PCM>(xs, xs16, g);
         }
         fbuf[2 * FPAD<T>(n >> 1) + (n & 1)] = (T)v * win[n];
       }
@@ -99,9 +118,11 @@ __global__ void __launch_bounds__(STFT_WARPS * 32) stft_kernel(StftArgs a, const
 }
 
 // history <- last `ov` samples of concat(history, x)        (transform.py:451)
-__global__ void stft_history_kernel(const float *x, float *history, int Ns, int ov) {
+template <bool PCM>
+__global__ void stft_history_kernel(const float *x, const short *x16, float *history, int Ns, int ov) {
   const long long sc = blockIdx.x;
-  const float *xs = x + sc * Ns;
+  const float *xs = PCM ? nullptr : x + sc * Ns;
+  const short *xs16 = PCM ? x16 + sc * Ns : nullptr;
   float *hs = history + sc * ov;
   float v[8];
 #pragma unroll
@@ -109,7 +130,7 @@ __global__ void stft_history_kernel(const float *x, float *history, int Ns, int 
     int idx = threadIdx.x + i * blockDim.x;
     if (idx < ov) {
       int g = Ns + idx;  // index into concat(history[ov], x[Ns])
-      v[i] = (g < ov) ? hs[g] : xs[g - ov];
+      v[i] = (g < ov) ? hs[g] : load_sample<PCM>(xs, xs16, g - ov);
     }
   }
   __syncthreads();
@@ -125,7 +146,7 @@ static int launch_stft(const StftArgs &a, const TwiddleSet &tw, cudaStream_t st)
   typedef typename V2<T>::type C2;
   constexpr int H = N / 2;
   const size_t smem = (size_t)(H + H / 2 + 2) * sizeof(C2) + (size_t)N * sizeof(T) + (size_t)STFT_WARPS * fft_buf_elems(N) * sizeof(C2);
-  auto kern = stft_kernel<N, T>;
+  auto kern = a.x16 ? stft_kernel<N, T, true> : stft_kernel<N, T, false>;
   if (smem > 48 * 1024) DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)a.S * a.C * a.T;
   if (total >= (1LL << 31)) { set_error("stft: more than 2^31 frames in one call"); return DS_EUNSUPPORTED; }
@@ -157,7 +178,16 @@ struct IstftArgs {
   const void *Y; float *y; float *tail; const double *window;
   int S, C, T, hop, mode, n_out, in_c128;  // n_out = samples written per (s,c)
   double scale;
+  short *y16;       // int16 PCM output instead of y (fused save_audio scaling, beamformer/utils.py:193)
 };
+
+// save_audio on the float32 sample the float path would have stored: (audio * 32767).astype(int16) with the product in
+// double (Transform.istft hands save_audio a float64 array, transform.py:474-481) and the cast truncating toward zero.
+// Out-of-range products saturate (NumPy leaves that cast undefined).
+__device__ __forceinline__ short pcm16_from_sample(float v) {
+  const double p = (double)v * 32767.0;
+  return (short)max(-32768, min(32767, __double2int_rz(p)));
+}
 
 constexpr int ISTFT_WARPS = 4;
 constexpr int ISTFT_TILE = 8;   // output hop-blocks per CTA
@@ -221,7 +251,8 @@ __global__ void __launch_bounds__(ISTFT_WARPS * 32) istft_kernel(IstftArgs a, co
   __syncthreads();
   const int g0 = b0 * a.hop;
   const int g1 = tail_pass ? total_len : min(b1 * a.hop, a.n_out);
-  float *ys = a.y + (long long)sc * a.n_out;
+  float *ys = a.y16 ? nullptr : a.y + (long long)sc * a.n_out;
+  short *ys16 = a.y16 ? a.y16 + (long long)sc * a.n_out : nullptr;
   float *tl = a.tail ? a.tail + (long long)sc * ov : nullptr;
   // tail pass: every thread first computes its values (reads old tail), then all write
   float keep[(ISTFT_MAXR * 2048 / 8) / (ISTFT_WARPS * 32) + 1];
@@ -234,10 +265,12 @@ __global__ void __launch_bounds__(ISTFT_WARPS * 32) istft_kernel(IstftArgs a, co
     for (int t = t_lo; t <= t_hi; ++t) acc = acc + frames[(size_t)(t - tf0) * N + (g - t * a.hop)];
     if (a.mode == DS_STFT_STREAMING) {
       if (g < ov) acc = acc + tl[g];                          // x[:overlap] += previous_output (:476)
-      if (!tail_pass) ys[g] = (float)((double)acc * a.scale);  // :479
-      else keep[nkeep++] = acc;
+      if (!tail_pass) {                                       // :479
+        const float o = (float)((double)acc * a.scale);
+        if (ys16) ys16[g] = pcm16_from_sample(o); else ys[g] = o;
+      } else keep[nkeep++] = acc;
     } else {
-      ys[g] = acc;
+      if (ys16) ys16[g] = pcm16_from_sample(acc); else ys[g] = acc;
     }
   }
   if (tail_pass) {
@@ -277,7 +310,8 @@ __global__ void __launch_bounds__(ISEQ_WARPS * 32) istft_seq_kernel(IstftArgs a,
   const int b0 = seg * G, b1 = min(b0 + G, nblk);
   const T *fb = reinterpret_cast<const T *>(buf);
   const T inv_n = (T)1 / (T)N;
-  float *ys = a.y + (long long)sc * a.n_out;
+  float *ys = a.y16 ? nullptr : a.y + (long long)sc * a.n_out;
+  short *ys16 = a.y16 ? a.y16 + (long long)sc * a.n_out : nullptr;
   const bool streaming = a.mode == DS_STFT_STREAMING;
 
   auto inverse = [&](int t) {          // frame t -> buf holds irfft * N
@@ -312,10 +346,9 @@ __global__ void __launch_bounds__(ISEQ_WARPS * 32) istft_seq_kernel(IstftArgs a,
       if (g < a.n_out) {
         if (streaming) {
           if (b == 0) acc = acc + a.tail[(long long)sc * HOP + j];           // x[:overlap] += previous_output (:476)
-          ys[g] = (float)((double)acc * a.scale);                           // :479
-        } else {
-          ys[g] = acc;
+          acc = (float)((double)acc * a.scale);                             // :479
         }
+        if (ys16) ys16[g] = pcm16_from_sample(acc); else ys[g] = acc;
       }
     }
     __syncwarp();
@@ -795,8 +828,9 @@ int ds_stft_num_frames(const ds_stft_params *p) {
   return DS_EINVAL;
 }
 
-int ds_stft_run(const ds_stft_params *p, const double *window, float *history, const float *x, void *X, void *stream) {
-  DS_CHECK_ARG(p && window && x && X, "ds_stft_run: null argument");
+static int stft_run_impl(const ds_stft_params *p, const double *window, float *history, const float *x, const short *x16,
+                         void *X, void *stream) {
+  DS_CHECK_ARG(p && window && (x || x16) && X, "ds_stft_run: null argument");
   DS_CHECK_ARG(p->hop >= 1 && p->hop <= p->n_fft, "ds_stft_run: hop %d out of range", p->hop);
   DS_CHECK_ARG(p->n_streams >= 1 && p->n_ch >= 1 && p->n_samples >= 1, "ds_stft_run: bad shape");
   DS_CHECK_ARG(p->mode != DS_STFT_STREAMING || history || p->hop == p->n_fft, "ds_stft_run: streaming mode needs a history buffer");
@@ -808,7 +842,7 @@ int ds_stft_run(const ds_stft_params *p, const double *window, float *history, c
   if (T < 0) { set_error("ds_stft_run: bad mode"); return DS_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   StftArgs a;
-  a.x = x; a.history = (p->mode == DS_STFT_STREAMING) ? history : nullptr; a.X = X; a.window = window; a.out_c128 = p->out_c128;
+  a.x = x; a.x16 = x16; a.history = (p->mode == DS_STFT_STREAMING) ? history : nullptr; a.X = X; a.window = window; a.out_c128 = p->out_c128;
   a.S = p->n_streams; a.C = p->n_ch; a.Ns = p->n_samples; a.T = T; a.hop = p->hop; a.mode = p->mode;
   if (T > 0) {
     rc = p->fft_fp64 ? dispatch_stft<double>(p->n_fft, a, tw, st) : dispatch_stft<float>(p->n_fft, a, tw, st);
@@ -818,14 +852,26 @@ int ds_stft_run(const ds_stft_params *p, const double *window, float *history, c
   if (p->mode == DS_STFT_STREAMING && ov > 0) {
     int threads = (ov + 7) / 8;
     threads = ((threads + 31) / 32) * 32;
-    stft_history_kernel<<<p->n_streams * p->n_ch, threads, 0, st>>>(x, history, p->n_samples, ov);
+    if (x16) stft_history_kernel<true><<<p->n_streams * p->n_ch, threads, 0, st>>>(nullptr, x16, history, p->n_samples, ov);
+    else stft_history_kernel<false><<<p->n_streams * p->n_ch, threads, 0, st>>>(x, nullptr, history, p->n_samples, ov);
     DS_LAUNCH_CHECK();
   }
   return DS_OK;
 }
 
-int ds_istft_run(const ds_istft_params *p, const double *window, float *tail, const void *Y, float *y, void *stream) {
-  DS_CHECK_ARG(p && window && Y && y, "ds_istft_run: null argument");
+int ds_stft_run(const ds_stft_params *p, const double *window, float *history, const float *x, void *X, void *stream) {
+  DS_CHECK_ARG(x, "ds_stft_run: null argument");
+  return stft_run_impl(p, window, history, x, nullptr, X, stream);
+}
+
+int ds_stft_pcm16_run(const ds_stft_params *p, const double *window, float *history, const int16_t *x_pcm, void *X, void *stream) {
+  DS_CHECK_ARG(x_pcm, "ds_stft_pcm16_run: null argument");
+  return stft_run_impl(p, window, history, nullptr, (const short *)x_pcm, X, stream);
+}
+
+static int istft_run_impl(const ds_istft_params *p, const double *window, float *tail, const void *Y, float *y, short *y16,
+                          void *stream) {
+  DS_CHECK_ARG(p && window && Y && (y || y16), "ds_istft_run: null argument");
   DS_CHECK_ARG(p->hop >= 1 && p->hop <= p->n_fft, "ds_istft_run: hop %d out of range", p->hop);
   DS_CHECK_ARG(p->n_streams >= 1 && p->n_ch >= 1 && p->n_frames >= 1, "ds_istft_run: bad shape");
   DS_CHECK_ARG(p->mode == DS_STFT_STREAMING || p->mode == DS_STFT_PLAIN, "ds_istft_run: mode must be STREAMING or PLAIN");
@@ -834,12 +880,22 @@ int ds_istft_run(const ds_istft_params *p, const double *window, float *tail, co
   int rc = get_twiddles(p->n_fft, &tw);
   if (rc != DS_OK) return rc;
   IstftArgs a;
-  a.Y = Y; a.in_c128 = p->in_c128; a.y = y; a.tail = (p->mode == DS_STFT_STREAMING) ? tail : nullptr; a.window = window;
+  a.Y = Y; a.in_c128 = p->in_c128; a.y = y; a.y16 = y16; a.tail = (p->mode == DS_STFT_STREAMING) ? tail : nullptr; a.window = window;
   a.S = p->n_streams; a.C = p->n_ch; a.T = p->n_frames; a.hop = p->hop; a.mode = p->mode;
   a.n_out = (p->mode == DS_STFT_STREAMING) ? p->n_frames * p->hop : p->n_fft + p->hop * (p->n_frames - 1);
   a.scale = p->scale;
   cudaStream_t st = (cudaStream_t)stream;
   return p->fft_fp64 ? dispatch_istft<double>(p->n_fft, a, tw, st) : dispatch_istft<float>(p->n_fft, a, tw, st);
+}
+
+int ds_istft_run(const ds_istft_params *p, const double *window, float *tail, const void *Y, float *y, void *stream) {
+  DS_CHECK_ARG(y, "ds_istft_run: null argument");
+  return istft_run_impl(p, window, tail, Y, y, nullptr, stream);
+}
+
+int ds_istft_pcm16_run(const ds_istft_params *p, const double *window, float *tail, const void *Y, int16_t *y_pcm, void *stream) {
+  DS_CHECK_ARG(y_pcm, "ds_istft_pcm16_run: null argument");
+  return istft_run_impl(p, window, tail, Y, nullptr, (short *)y_pcm, stream);
 }
 
 size_t ds_fixedbf_state_bytes(const ds_fixedbf_params *p) {

@@ -207,9 +207,11 @@ __global__ void pcm16_to_float_kernel(const short *__restrict__ in, float *__res
   }
 }
 // save_audio: (audio * 32767).astype(int16)   (:193) -- C cast truncates toward zero like numpy
-__global__ void float_to_pcm16_kernel(const float *__restrict__ in, short *__restrict__ out, size_t n) {
+// float32 input: NumPy keeps the product in float32 (array * Python int); float64 input: product in double
+template <typename T>
+__global__ void float_to_pcm16_kernel(const T *__restrict__ in, short *__restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (short)(int)(in[i] * 32767.0f);
+  if (i < n) out[i] = (short)(int)(in[i] * (T)32767);
 }
 }  // namespace ds
 
@@ -224,7 +226,14 @@ extern "C" int ds_pcm16_to_float_run(size_t n, const void *pcm, float *out, void
 extern "C" int ds_float_to_pcm16_run(size_t n, const float *in, void *pcm, void *stream) {
   DS_CHECK_ARG(pcm && in, "ds_float_to_pcm16_run: null argument");
   if (n == 0) return DS_OK;
-  ds::float_to_pcm16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (short *)pcm, n);
+  ds::float_to_pcm16_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (short *)pcm, n);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+extern "C" int ds_double_to_pcm16_run(size_t n, const double *in, void *pcm, void *stream) {
+  DS_CHECK_ARG(pcm && in, "ds_double_to_pcm16_run: null argument");
+  if (n == 0) return DS_OK;
+  ds::float_to_pcm16_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (short *)pcm, n);
   DS_LAUNCH_CHECK();
   return DS_OK;
 }

@@ -29,6 +29,8 @@ class NoiseEstimationMCRA(NoiseEstimationBase):
     def _ensure(self, S):
         t = L.require_cuda()
         if self._state is None or self._nstreams != S:
+            if self._state is not None:
+                self.frm_cnt, self.ell = 0, 1      # a different batch is a new set of streams: counters restart with the state
             self._state = t.zeros((S, 5, self.half_bin), dtype=t.float64, device="cuda")
             self._nstreams = S
 

@@ -82,6 +82,8 @@ class McSppBase(object):
     def _ensure(self, S):
         t = L.require_cuda()
         if self._state is None or self._S != S:
+            if self._state is not None:
+                self.mcra.frm_cnt, self.mcra.ell = 0, 1      # re-zeroed state = new streams: the inner MCRA's counters restart too
             nbytes = L.lib().ds_mcspp_state_bytes(C.byref(self._params(S, 1)))
             self._state = t.zeros(nbytes, dtype=t.uint8, device="cuda")
             self._S = S

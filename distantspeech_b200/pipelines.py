@@ -41,6 +41,7 @@ class MvdrMcsppChain(object):
         self._ws = None
         self._key = None
         self._a0_dev = None
+        self._hp = None
 
     # ------------------------------------------------------------------
     def _params(self, S, N):
@@ -72,38 +73,55 @@ class MvdrMcsppChain(object):
             self._a0_dev = t.as_tensor(np.ascontiguousarray(self.a0.T)).to("cuda")     # [M, K] complex128
         return p
 
-    def process_device(self, x_dev, out=None):
-        """x_dev [S, M, N] float32 CUDA (mic-major) -> y [S, N] float32 CUDA.  No copies, no sync."""
+    def _check_input(self, x_dev, out):
+        """Shared validation of the device entry points: x_dev [S, M, N] contiguous float32 or int16 CUDA tensor."""
         t = L.require_cuda()
+        if not isinstance(x_dev, t.Tensor) or x_dev.dim() != 3 or not x_dev.is_cuda:
+            raise ValueError("x_dev must be a CUDA tensor [S, %d, N]" % self.M)
         S, M, N = x_dev.shape
         if M != self.M or N % self.hop != 0 or N < self.hop:
             raise ValueError("expected [S, %d, N] with N a positive multiple of hop=%d" % (self.M, self.hop))
-        if x_dev.dtype != t.float32 or not x_dev.is_contiguous():
-            raise ValueError("x_dev must be a contiguous float32 CUDA tensor")
-        p = self._prepare(S, N)
-        y = out if out is not None else t.empty((S, N), dtype=t.float32, device="cuda")
-        L.check(L.lib().ds_chain_run(C.byref(p), L.ptr(L.device_window(self.window, self.n_fft)), L.ptr(self._a0_dev),
-                                     L.ptr(self._state), L.ptr(self._ws), L.ptr(x_dev), L.ptr(y), L.stream_ptr()),
-                "ds_chain_run")
+        if x_dev.dtype not in (t.float32, t.int16) or not x_dev.is_contiguous():
+            raise ValueError("x_dev must be a contiguous float32 (or int16 PCM) CUDA tensor")
+        if out is not None:
+            if (not out.is_cuda or tuple(out.shape) != (S, N) or out.dtype not in (t.float32, t.int16)
+                    or not out.is_contiguous()):
+                raise ValueError("out must be a contiguous float32 (or int16 PCM) CUDA tensor [S, N]")
+        return S, M, N
+
+    def _advance(self, N):
         f, e = C.c_int32(self.frm_cnt), C.c_int32(self.ell)
         L.lib().ds_mcra_advance(self.mcra_L, N // self.hop, C.byref(f), C.byref(e))
         self.frm_cnt, self.ell = f.value, e.value
+
+    def process_device(self, x_dev, out=None):
+        """x_dev [S, M, N] float32 CUDA (mic-major) -> y [S, N] float32 CUDA.  No copies, no sync.
+        int16 PCM on either side (x_dev and / or ``out`` of dtype int16) runs load_audio's ``/ 32767`` and
+        save_audio's ``* 32767 -> int16`` (beamformer/utils.py:182-196) inside the analysis / synthesis kernels."""
+        t = L.require_cuda()
+        S, M, N = self._check_input(x_dev, out)
+        p = self._prepare(S, N)
+        y = out if out is not None else t.empty((S, N), dtype=t.float32, device="cuda")
+        L.check(L.lib().ds_chain_run_io(C.byref(p), L.ptr(L.device_window(self.window, self.n_fft)), L.ptr(self._a0_dev),
+                                        L.ptr(self._state), L.ptr(self._ws), L.ptr(x_dev), int(x_dev.dtype == t.int16),
+                                        L.ptr(y), int(y.dtype == t.int16), L.stream_ptr()), "ds_chain_run_io")
+        self._advance(N)
         return y
 
     def process_device_profiled(self, x_dev, out=None):
-        """Like process_device but synchronises and returns (y, [ms_analysis, ms_perbin, ms_synthesis])
+        """Like process_device (float32 only) but synchronises and returns (y, [ms_analysis, ms_perbin, ms_synthesis])
         measured with CUDA events on the launching stream (bench/roofline use only)."""
         t = L.require_cuda()
-        S, M, N = x_dev.shape
+        S, M, N = self._check_input(x_dev, out)
+        if x_dev.dtype != t.float32 or (out is not None and out.dtype != t.float32):
+            raise ValueError("process_device_profiled takes float32 tensors")
         p = self._prepare(S, N)
         y = out if out is not None else t.empty((S, N), dtype=t.float32, device="cuda")
         ms = (C.c_float * 3)()
         L.check(L.lib().ds_chain_run_profiled(C.byref(p), L.ptr(L.device_window(self.window, self.n_fft)),
                                               L.ptr(self._a0_dev), L.ptr(self._state), L.ptr(self._ws), L.ptr(x_dev),
                                               L.ptr(y), L.stream_ptr(), ms), "ds_chain_run_profiled")
-        f, e = C.c_int32(self.frm_cnt), C.c_int32(self.ell)
-        L.lib().ds_mcra_advance(self.mcra_L, N // self.hop, C.byref(f), C.byref(e))
-        self.frm_cnt, self.ell = f.value, e.value
+        self._advance(N)
         return y, [float(v) for v in ms]
 
     def process(self, x):
@@ -120,32 +138,52 @@ class MvdrMcsppChain(object):
             y = y[0]
         return y if as_torch else y.double().cpu().numpy()
 
-    def process_host(self, x_host, y_host=None, chunk_streams=128):
-        """End-to-end call with HOST buffers: x_host [S, M, N] float32 -- or int16 PCM, converted on the
-        device exactly like load_audio (float32(pcm) / 32767, utils.py:184-185) -- (pinned for speed) ->
-        y_host [S, N] float32.  Streams are independent, so the batch is cut into groups of
-        ``chunk_streams`` and H2D copy / kernels / D2H copy of consecutive groups overlap on
-        three CUDA streams.  Each group is a fresh utterance (state reset)."""
+    # ------------------------------------------------------------------
+    def _host_pipeline(self, cs, M, N, in_dtype, out_dtype):
+        """Streams, events, staging buffers and per-slot chain objects of process_host, created once per
+        (group size, shape, dtypes) and kept for the life of the object."""
         t = L.require_cuda()
+        key = (cs, M, N, in_dtype, out_dtype, t.cuda.current_device())
+        hp = getattr(self, "_hp", None)
+        if hp is not None and hp["key"] == key:
+            return hp
+        sub = MvdrMcsppChain.__new__(MvdrMcsppChain)        # the groups' own recursive state, separate from process()'s
+        sub.__dict__.update(self.__dict__)
+        sub._state = sub._ws = sub._key = sub._hp = None
+        hp = {"key": key, "s_in": t.cuda.Stream(), "s_out": t.cuda.Stream(),
+              "xbuf": [t.empty((cs, M, N), dtype=in_dtype, device="cuda") for _ in range(2)],
+              "ybuf": [t.empty((cs, N), dtype=out_dtype, device="cuda") for _ in range(2)],
+              "ev_in": [t.cuda.Event() for _ in range(2)], "ev_done": [t.cuda.Event() for _ in range(2)],
+              "ev_out": [t.cuda.Event() for _ in range(2)], "sub": sub}
+        self._hp = hp
+        return hp
+
+    def process_host(self, x_host, y_host=None, chunk_streams=128):
+        """End-to-end call with HOST buffers: x_host [S, M, N] float32 or int16 PCM (the reference's on-disk
+        format; scaled exactly like load_audio, float32(pcm) / 32767, utils.py:184-185) -> y_host [S, N] float32,
+        or int16 PCM when an int16 ``y_host`` is handed in (save_audio's (audio * 32767).astype(int16), utils.py:193).
+        Pinned buffers for speed.  Both conversions run inside the analysis / synthesis kernels: int16 samples are
+        what crosses PCIe and what the kernels read and write.  Streams are independent, so the batch is cut into
+        groups of ``chunk_streams`` and H2D copy / kernels / D2H copy of consecutive groups overlap on three CUDA
+        streams (staging buffers, streams and events are created once per object).  Each group is a fresh utterance
+        (state reset)."""
+        t = L.require_cuda()
+        if x_host.dim() != 3 or x_host.dtype not in (t.float32, t.int16):
+            raise ValueError("x_host must be [S, M, N] float32 or int16")
         S, M, N = x_host.shape
+        if M != self.M or N % self.hop != 0 or N < self.hop:
+            raise ValueError("expected [S, %d, N] with N a positive multiple of hop=%d" % (self.M, self.hop))
         if y_host is None:
             y_host = t.empty((S, N), dtype=t.float32, pin_memory=True)
+        if tuple(y_host.shape) != (S, N) or y_host.dtype not in (t.float32, t.int16):
+            raise ValueError("y_host must be [S, N] float32 or int16")
         cs = min(chunk_streams, S)
         n_chunks = (S + cs - 1) // cs
+        hp = self._host_pipeline(cs, M, N, x_host.dtype, y_host.dtype)
         cur = t.cuda.current_stream()
-        s_in, s_out = t.cuda.Stream(), t.cuda.Stream()
-        pcm = x_host.dtype == t.int16
-        xbuf = [t.empty((cs, M, N), dtype=t.float32, device="cuda") for _ in range(2)]
-        pbuf = [t.empty((cs, M, N), dtype=t.int16, device="cuda") for _ in range(2)] if pcm else None
-        ybuf = [t.empty((cs, N), dtype=t.float32, device="cuda") for _ in range(2)]
-        ev_in = [t.cuda.Event() for _ in range(2)]
-        ev_done = [t.cuda.Event() for _ in range(2)]
-        ev_out = [t.cuda.Event() for _ in range(2)]
-        sub = MvdrMcsppChain.__new__(MvdrMcsppChain)
-        sub.__dict__.update(self.__dict__)
-        sub._state = None
-        sub._ws = None
-        sub._key = None
+        s_in, s_out, xbuf, ybuf = hp["s_in"], hp["s_out"], hp["xbuf"], hp["ybuf"]
+        ev_in, ev_done, ev_out, sub = hp["ev_in"], hp["ev_done"], hp["ev_out"], hp["sub"]
+        s_in.wait_stream(cur)
         for c in range(n_chunks):
             b = c & 1
             lo, hi = c * cs, min(S, (c + 1) * cs)
@@ -153,16 +191,13 @@ class MvdrMcsppChain(object):
             with t.cuda.stream(s_in):
                 if c >= 2:
                     s_in.wait_event(ev_done[b])          # kernels of chunk c-2 finished reading xbuf[b]
-                (pbuf if pcm else xbuf)[b][:n].copy_(x_host[lo:hi], non_blocking=True)
+                xbuf[b][:n].copy_(x_host[lo:hi], non_blocking=True)
                 ev_in[b].record(s_in)
             cur.wait_event(ev_in[b])
-            if pcm:
-                L.check(L.lib().ds_pcm16_to_float_run(n * M * N, L.ptr(pbuf[b]), L.ptr(xbuf[b]), L.stream_ptr()),
-                        "ds_pcm16_to_float_run")
             if c >= 2:
                 cur.wait_event(ev_out[b])                # D2H of chunk c-2 finished reading ybuf[b]
-            if n != cs:
-                sub._state = None
+            if sub._key is not None and sub._key[0] != n:
+                sub._state = None                        # ragged last group: state blob of its own size
                 sub._key = None
             sub.reset_counters()
             if sub._state is not None:

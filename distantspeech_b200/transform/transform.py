@@ -152,7 +152,8 @@ class Transform(object):
     [K, T, C])`` -> ``[hop*T(, C)]`` float64 (float32-rounded values, squeezed).
     With a leading batch axis: ``x[S, N, M]`` -> ``[S, K, T, M]`` and
     ``Y[S, K, T, C]`` -> ``[S, hop*T, C]``.  The chunk length must be a multiple
-    of ``hop_length`` for a gap-free stream (reference quirk 4, :441).
+    of ``hop_length`` for a gap-free stream (reference quirk 4, :441).  ``window`` must have exactly
+    ``n_fft`` taps (every reference call site passes none or a full-length window); anything else raises ValueError.
     """
 
     def __init__(self, channel=1, n_fft=256, hop_length=128, window=None, precision="fp32"):
@@ -162,6 +163,10 @@ class Transform(object):
         self.hop_length = hop_length
         self.first_frame = 1
         self.window = _sqrt_hann(n_fft) if window is None else np.asarray(window, dtype=np.float64)
+        if self.window.ndim != 1 or self.window.shape[0] != n_fft:
+            # the device history / tail hold n_fft - hop samples per channel; a shorter window would make the
+            # reference keep win_len - hop samples instead (transform.py:427,438) -- not supported, say so loudly
+            raise ValueError("Transform: window must have n_fft = %d taps, got shape %s" % (n_fft, self.window.shape))
         self.half_bin = int(n_fft / 2 + 1)
         self.win_len = self.window.shape[0]
         self.overlap = self.win_len - hop_length

@@ -87,6 +87,12 @@ int ds_stft_num_frames(const ds_stft_params *p);
  *   X       [S][T][M][K] c64 out (rounded to complex64 like :212) or c128        */
 int ds_stft_run(const ds_stft_params *p, const double *window, float *history,
                 const float *x, void *X, void *stream);
+/* Same transform fed with int16 PCM x [S][M][N]: replaces load_audio's scaling
+ * float32(pcm) / 32767 (beamformer/utils.py:182-187) followed by Transform.stft
+ * (transform.py:430-453) -- the scaling runs inside the analysis kernel, the
+ * float waveform never exists in memory; `history` stays float32.                */
+int ds_stft_pcm16_run(const ds_stft_params *p, const double *window, float *history,
+                      const int16_t *x_pcm, void *X, void *stream);
 
 typedef struct ds_istft_params {
   int32_t n_fft;
@@ -109,6 +115,12 @@ typedef struct ds_istft_params {
  *   y    [S][C][n_out] float32                                                   */
 int ds_istft_run(const ds_istft_params *p, const double *window, float *tail,
                  const void *Y, float *y, void *stream);
+/* Same synthesis writing int16 PCM y [S][C][n_out]: Transform.istft (:455-481)
+ * followed by save_audio's (audio * 32767).astype(int16) (beamformer/utils.py:190-196,
+ * product in double, truncation toward zero; out-of-range values saturate) fused
+ * into the synthesis kernel's store.                                             */
+int ds_istft_pcm16_run(const ds_istft_params *p, const double *window, float *tail,
+                       const void *Y, int16_t *y_pcm, void *stream);
 
 /* ---- fixed beamformer (beamformer/fixedbeamformer.py) ----------------- */
 typedef struct ds_fixedbf_params {
@@ -493,6 +505,8 @@ int ds_fir_run(int n_streams, int n_ch, int n_samples, int filter_len, const dou
 int ds_pcm16_to_float_run(size_t n, const void *pcm_int16, float *out, void *stream);
 /* replaces the arithmetic of save_audio (utils.py:190-196): pcm = int16(audio * 32767)          */
 int ds_float_to_pcm16_run(size_t n, const float *in, void *pcm_int16, void *stream);
+/* the same for a float64 array (what Transform.istft returns): product in double   */
+int ds_double_to_pcm16_run(size_t n, const double *in, void *pcm_int16, void *stream);
 
 /* ---- SRP-PHAT (doa/srp.py) ------------------------------------------------ */
 /* PHAT normalisation + transpose for the contraction (srp.py:49-50):
@@ -583,6 +597,14 @@ size_t ds_chain_workspace_bytes(const ds_chain_params *p);
  * mvdr.ipynb cell 4): x [S][M][N] float32 -> y [S][N] float32.                   */
 int ds_chain_run(const ds_chain_params *p, const double *window, const void *a0,
                  void *state, void *workspace, const float *x, float *y, void *stream);
+
+/* Same chain with int16 PCM on either side (the reference's on-disk format,
+ * load_audio / save_audio, beamformer/utils.py:182-196): x is [S][M][N] float32 or
+ * int16, y is [S][N] float32 or int16; the scalings are fused into the analysis and
+ * synthesis kernels (ds_stft_pcm16_run / ds_istft_pcm16_run).                    */
+int ds_chain_run_io(const ds_chain_params *p, const double *window, const void *a0,
+                    void *state, void *workspace, const void *x, int x_is_pcm16,
+                    void *y, int y_is_pcm16, void *stream);
 
 /* Profiling variant (bench only): same work, but records CUDA events between the
  * three kernels, SYNCHRONISES, and returns their durations in milliseconds in

@@ -59,3 +59,95 @@ def test_srp_reference_golden_gpu(cuda, engine):
     Pn, _ = srp(mic, engine=engine).compute_angle_spectrum(g["x"], phat=False)
     reln = np.max(np.abs(Pn - g["angle_spectrum_nophat"])) / np.max(np.abs(g["angle_spectrum_nophat"]))
     assert reln <= 1e-3
+
+
+# ---------------------------------------------------------------- f2: int16 ingest / egress fused into the transform kernels
+def test_fused_pcm16_transforms_match_the_separate_conversions(cuda):
+    """ds_stft_pcm16_run == ds_pcm16_to_float_run + ds_stft_run bit for bit (every mode, chunked streaming, odd offsets);
+    ds_istft_pcm16_run == ds_istft_run + save_audio's expression on the float64 array Transform.istft returns."""
+    import ctypes as C
+    import torch
+    from distantspeech_b200 import _lib as L
+    from distantspeech_b200.transform.transform import _sqrt_hann
+    rng = np.random.default_rng(5)
+    for n_fft, hop, mode, N in ((512, 256, L.DS_STFT_STREAMING, 256 * 9), (256, 64, L.DS_STFT_STREAMING, 64 * 21),
+                                (512, 128, L.DS_STFT_CENTER, 3001), (256, 128, L.DS_STFT_PLAIN, 1999)):
+        S, M, K = 3, 2, n_fft // 2 + 1
+        pcm = torch.from_numpy(rng.integers(-30000, 30000, size=(S, M, N), dtype=np.int16)).cuda()
+        xf = torch.empty((S, M, N), dtype=torch.float32, device="cuda")
+        L.check(L.lib().ds_pcm16_to_float_run(pcm.numel(), L.ptr(pcm), L.ptr(xf), L.stream_ptr()))
+        assert np.array_equal(xf.cpu().numpy(), pcm.cpu().numpy().astype(np.float32) / np.float32(32767.0))
+        win = L.device_window(_sqrt_hann(n_fft), n_fft)
+        p = L.StftParams(n_fft, hop, S, M, N, mode, 0, 0)
+        T = L.lib().ds_stft_num_frames(C.byref(p))
+        ov = n_fft - hop
+        h1 = torch.full((S, M, ov), 0.25, dtype=torch.float32, device="cuda")
+        h2 = h1.clone()
+        X1 = torch.empty((S, T, M, K), dtype=torch.complex64, device="cuda")
+        X2 = torch.empty_like(X1)
+        L.check(L.lib().ds_stft_run(C.byref(p), L.ptr(win), L.ptr(h1), L.ptr(xf), L.ptr(X1), L.stream_ptr()))
+        L.check(L.lib().ds_stft_pcm16_run(C.byref(p), L.ptr(win), L.ptr(h2), L.ptr(pcm), L.ptr(X2), L.stream_ptr()))
+        assert torch.equal(torch.view_as_real(X1), torch.view_as_real(X2)) and torch.equal(h1, h2), (n_fft, hop, mode)
+        if mode == L.DS_STFT_CENTER:
+            continue
+        # synthesis: int16 store == float store followed by (float64(y) * 32767).astype(int16)
+        ip = L.IstftParams(n_fft, hop, S, M, T, mode, 0, 0, 0.5 * hop / float(np.sum(_sqrt_hann(n_fft) ** 2)))
+        n_out = T * hop if mode == L.DS_STFT_STREAMING else n_fft + hop * (T - 1)
+        t1 = torch.zeros((S, M, ov), dtype=torch.float32, device="cuda")
+        t2 = t1.clone()
+        yf = torch.empty((S, M, n_out), dtype=torch.float32, device="cuda")
+        yi = torch.empty((S, M, n_out), dtype=torch.int16, device="cuda")
+        L.check(L.lib().ds_istft_run(C.byref(ip), L.ptr(win), L.ptr(t1), L.ptr(X1), L.ptr(yf), L.stream_ptr()))
+        L.check(L.lib().ds_istft_pcm16_run(C.byref(ip), L.ptr(win), L.ptr(t2), L.ptr(X1), L.ptr(yi), L.stream_ptr()))
+        ref = (yf.cpu().numpy().astype(np.float64) * np.iinfo(np.int16).max).astype(np.int16)       # utils.py:193
+        assert np.abs(yf.cpu().numpy()).max() < 1.0
+        assert np.array_equal(yi.cpu().numpy(), ref) and torch.equal(t1, t2), (n_fft, hop, mode)
+    # every int16 value through the fused scaling (non-overlapping frames, so each value is read exactly once)
+    allv = torch.arange(-32768, 32768, dtype=torch.int32).to(torch.int16).reshape(1, 1, 65536).cuda()
+    xf = torch.empty((1, 1, 65536), dtype=torch.float32, device="cuda")
+    L.check(L.lib().ds_pcm16_to_float_run(65536, L.ptr(allv), L.ptr(xf), L.stream_ptr()))
+    p = L.StftParams(128, 128, 1, 1, 65536, L.DS_STFT_PLAIN, 1, 1)               # fp64 FFT, complex128 out: injective enough
+    win = L.device_window(np.ones(128), 128)
+    Xa = torch.empty((1, 512, 1, 65), dtype=torch.complex128, device="cuda")
+    Xb = torch.empty_like(Xa)
+    L.check(L.lib().ds_stft_run(C.byref(p), L.ptr(win), None, L.ptr(xf), L.ptr(Xa), L.stream_ptr()))
+    L.check(L.lib().ds_stft_pcm16_run(C.byref(p), L.ptr(win), None, L.ptr(allv), L.ptr(Xb), L.stream_ptr()))
+    assert torch.equal(torch.view_as_real(Xa), torch.view_as_real(Xb))
+    # float64 save path (ADVICE r1): product in double
+    y64 = torch.from_numpy(rng.standard_normal(50001) * 0.3).cuda()
+    out = torch.empty(50001, dtype=torch.int16, device="cuda")
+    L.check(L.lib().ds_double_to_pcm16_run(y64.numel(), L.ptr(y64), L.ptr(out), L.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), (y64.cpu().numpy() * 32767).astype(np.int16))
+
+
+def test_chain_pcm16_in_and_out(cuda):
+    """MvdrMcsppChain with int16 PCM on both sides (device and host entry points): identical to the float path on the
+    dequantised signal followed by save_audio's quantisation; within the waveform contract of the oracle."""
+    import torch
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.pipelines import MvdrMcsppChain
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    xs = O.synth_streams(5, geo, 256 * 40, seed0=78)
+    xi = np.round(xs * 32767).astype(np.int16)
+    xf = xi.astype(np.float32) / np.float32(32767.0)
+    mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=512)
+    yf = MvdrMcsppChain(mic, look_angle=(30, 0)).process_device(torch.from_numpy(xf).cuda())
+    yi = torch.empty((5, 256 * 40), dtype=torch.int16, device="cuda")
+    MvdrMcsppChain(mic, look_angle=(30, 0)).process_device(torch.from_numpy(xi).cuda(), out=yi)
+    q = (yf.cpu().numpy().astype(np.float64) * 32767).astype(np.int16)
+    assert np.array_equal(yi.cpu().numpy(), q)
+    ch = MvdrMcsppChain(mic, look_angle=(30, 0))
+    y_host = torch.empty((5, 256 * 40), dtype=torch.int16).pin_memory()
+    for _ in range(2):                                                   # second call reuses the staging pipeline
+        ch.process_host(torch.from_numpy(xi).pin_memory(), y_host, chunk_streams=2)
+        assert np.array_equal(y_host.numpy(), q)
+    yh32 = ch.process_host(torch.from_numpy(xi).pin_memory(), chunk_streams=2)         # int16 in, float32 out
+    assert np.array_equal(yh32.numpy(), yf.cpu().numpy())
+    ref0 = O.mvdr_mcspp_chain(xf[3].T.astype(np.float64), geo, (30, 0), 512, 256)
+    assert_wave_parity(ref0, yf[3].cpu().numpy(), "pcm16 chain (float out)")
+    err = np.max(np.abs(q[3].astype(np.float64) / 32767.0 - ref0))
+    assert err <= 1.0 / 32767 + 1e-4                                     # one LSB of the 16-bit output format
+    with pytest.raises(ValueError):
+        ch.process_device_profiled(torch.from_numpy(xf[:, :, :100]).cuda())     # ADVICE r1: profiled entry validates its input
+    with pytest.raises(ValueError):
+        ch.process_device(torch.from_numpy(xf).cuda().double())
