@@ -2,23 +2,23 @@
 """bench.py -- headline benchmark of BASELINE.json: audio-seconds per second
 (x real time) of the 8-mic MVDR + McSppBase + OMLSA-postfilter chain.
 
-    python bench.py --gpus N --steps K --warmup W          (our CUDA path)
-    python bench.py --impl reference ...                   (reference CPU path, oracle port)
+    python bench.py --gpus N --steps K --warmup W          (our CUDA path, config 4 = configs[3] of BASELINE.json)
+    python bench.py --impl reference ...                   (the reference's CPU path on the host cores)
+    python bench.py --config {1,2,3,5} ...                 (the other BASELINE configurations, same JSON shape)
 
-Workload (configs[3], the configuration the metric is quoted on): 1024 streams
-per GPU x 10 s x 8 mics @ 16 kHz, n_fft 512 / hop 256, synthetic data of the
-SURVEY.md 8d recipe generated on the device (weak scaling: 8192 streams on 8 GPUs).
-A step = one pass of the whole chain over the batch.  Inputs (5.2 GB per GPU)
-are far larger than L2, so every step streams from HBM.
-Prints ONE JSON line on rank 0.
+Workload of the headline (configs[3], the configuration the metric is quoted on): 1024 streams per GPU x 10 s x 8 mics
+@ 16 kHz, n_fft 512 / hop 256, synthetic data of the SURVEY.md 8d recipe generated on the device (weak scaling: 8192
+streams on 8 GPUs).  A step = one pass of the whole chain over the batch.  Inputs (5.2 GB per GPU) are far larger than
+L2, so every step streams from HBM.  Prints ONE JSON line on rank 0; at N = 1 the default run also measures configs
+1, 2, 3 and 5 (short runs, `configs` key) so that every BASELINE configuration has a clocked, parity-checked number.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
 import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -30,6 +30,16 @@ FS = 16000
 N_FFT, HOP, M = 512, 256, 8
 LOOK, INTERF = (30.0, 0.0), (200.0, 0.0)
 ALGO_BYTES_PER_AUDIO_S = M * FS * 4 + FS * 4          # fp32 in (M*fs*4) + fp32 out (fs*4) = 576000
+METRIC = "audio-s/s (x realtime) for 8-mic MVDR+postfilter chain"
+WORKLOADS = {
+    1: "configs[0]: online MVDR (adaptivebeamfomer.process, method 2), 4-mic linear r=0.032 16 kHz, n_fft 512 hop 256",
+    2: "configs[1]: fixed superdirective beamformer (FixedBeamformer.process), 8-mic circular r=0.05 16 kHz, n_fft 512 hop 256",
+    3: "configs[2]: FDGSC (adaptive blocking matrix + NLMS canceller), 6-mic linear r=0.05 16 kHz, frameLen 256",
+    4: "configs[3]: MVDR + McSppBase + OMLSA chain, 8-mic circular r=0.05 16 kHz, n_fft 512 hop 256",
+    5: "configs[4]: SRP-PHAT over a 360x90 direction grid, 16-mic circular r=0.05 48 kHz, n_fft 1024 hop 512",
+}
+METRICS = {1: "audio-s/s (x realtime) for 4-mic online MVDR", 2: "audio-s/s (x realtime) for 8-mic fixed SD beamformer",
+           3: "audio-s/s (x realtime) for 6-mic FDGSC", 4: METRIC, 5: "audio-s/s (x realtime) for 16-mic SRP-PHAT 360x90"}
 
 
 def parse():
@@ -38,89 +48,55 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams-per-gpu", type=int, default=1024)
+    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--streams-per-gpu", type=int, default=0, help="0: the configuration's own size")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--full-state", type=int, default=0)
     ap.add_argument("--fft", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-streams-per-core", type=int, default=1)
-    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="audio seconds per CPU-baseline stream")
+    ap.add_argument("--no-configs", action="store_true", help="headline only: skip the short runs of configs 1, 2, 3, 5")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="audio seconds per CPU-baseline stream (0: per config)")
+    ap.add_argument("--chunk-streams", type=int, default=128)
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------
-# CPU baseline: the numpy oracle port of the reference, one process per core
+# process group / timing helpers
 # --------------------------------------------------------------------------
-def _cpu_worker(args):
-    first, count, n_samples = args
-    os.environ["OMP_NUM_THREADS"] = "1"
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    os.environ["MKL_NUM_THREADS"] = "1"
-    from oracle import np_oracle as O
-    geo = O.MicGeometry("circular", r=0.05, M=M, n_fft=N_FFT)
-    xs = O.synth_streams(count, geo, n_samples, look_deg=LOOK, interf_deg=INTERF, first_stream=first)
-    O.mvdr_mcspp_chain(xs[0, :, :HOP * 8].T.astype(np.float64), geo, LOOK, N_FFT, HOP)      # warm-up
-    t0 = time.perf_counter()
-    for s in range(count):
-        O.mvdr_mcspp_chain(xs[s].T.astype(np.float64), geo, LOOK, N_FFT, HOP)
-    return time.perf_counter() - t0
+class Env(object):
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = None
+        self.dist = None
 
+    def init_gpu(self):
+        import torch
+        import torch.distributed as dist
+        assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its banner on stdout; stdout carries exactly one JSON line
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.torch, self.dist = torch, dist
 
-def cpu_baseline(streams_per_core, seconds, repeats=1):
-    """Reference CPU path (oracle port, kind='port'): every host core runs the per-stream
-    frame loop of the reference on its own streams.  Returns (audio_s_per_s, cores, sample)."""
-    import multiprocessing as mp
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    n_samples = int(seconds * FS) // HOP * HOP
-    jobs = [(i * streams_per_core, streams_per_core, n_samples) for i in range(cores)]
-    ctx = mp.get_context("fork")
-    best = None
-    with ctx.Pool(cores) as pool:
-        for _ in range(repeats):
-            per = pool.map(_cpu_worker, jobs)  # each worker: generate data, warm up, then time its frame loops
-            wall = max(per)                    # slowest worker's timed region (all workers run concurrently)
-            best = wall if best is None else min(best, wall)
-    audio = cores * streams_per_core * n_samples / FS
-    sample = "%d streams x %.1f s (%d per core), numpy oracle port of the reference frame loop" % (
-        cores * streams_per_core, n_samples / FS, streams_per_core)
-    return audio / best, cores, sample
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-
-# --------------------------------------------------------------------------
-# synthetic data on the device (SURVEY 8d recipe)
-# --------------------------------------------------------------------------
-def synth_device(torch, S, mic, n_samples, seed, out=None, chunk=64):
-    from distantspeech_b200.beamformer.MicArray import compute_tau
-    dev = "cuda"
-    tau_s = torch.as_tensor(compute_tau(mic, np.array(LOOK) / 180 * np.pi)[:, 0], device=dev)
-    tau_i = torch.as_tensor(compute_tau(mic, np.array(INTERF) / 180 * np.pi)[:, 0], device=dev)
-    nfft = 1 << int(np.ceil(np.log2(n_samples + 64)))
-    f = torch.fft.rfftfreq(nfft, 1.0 / FS, device=dev, dtype=torch.float64)
-    t = torch.arange(n_samples, device=dev, dtype=torch.float64) / FS
-    env = (torch.sin(2 * np.pi * 0.7 * t) >= 0).to(torch.float32)
-    ph_s = torch.exp(-2j * np.pi * f[None, :] * tau_s[:, None]).to(torch.complex64)       # [M, F]
-    ph_i = torch.exp(-2j * np.pi * f[None, :] * tau_i[:, None]).to(torch.complex64)
-    x = out if out is not None else torch.empty((S, M, n_samples), dtype=torch.float32, device=dev)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
-    for lo in range(0, S, chunk):
-        hi = min(S, lo + chunk)
-        n = hi - lo
-        tgt = torch.randn((n, n_samples), generator=gen, device=dev) * env * 0.3
-        itf = torch.randn((n, n_samples), generator=gen, device=dev) * 0.2
-        Ft = torch.fft.rfft(tgt, nfft)
-        Fi = torch.fft.rfft(itf, nfft)
-        for m in range(M):
-            d = torch.fft.irfft(Ft * ph_s[m] + Fi * ph_i[m], nfft)[:, :n_samples]
-            d = d + torch.randn((n, n_samples), generator=gen, device=dev) * 0.05
-            x[lo:hi, m, :] = 0.5 * d
-    return x
+    def max_over_ranks(self, v):
+        from distantspeech_b200.sharding import max_over_ranks
+        return max_over_ranks(v, device="cuda")
 
 
 class ClockSampler(object):
     """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (2 ms period; the
-    timed region of the default run is ~130 ms, too short for `nvidia-smi -lms`), nvidia-smi as a fallback."""
+    timed region of the default run is ~0.4 s, too short for `nvidia-smi -lms`), nvidia-smi as a fallback."""
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
                (0x80, "hw_power_brake_slowdown"))
 
@@ -177,6 +153,26 @@ class ClockSampler(object):
                 "samples": len(self.sm), "source": self._how}
 
 
+def time_steps(env, step, steps, warmup):
+    """W untimed warm-up steps, then exactly K timed steps bracketed by barrier + synchronize, CUDA events on the
+    launching stream, max over ranks.  Returns (ms_total, clocks)."""
+    t = env.torch
+    for _ in range(max(warmup, 3)):
+        step()
+    env.barrier()
+    sampler = ClockSampler(env.local_rank) if env.rank == 0 else None
+    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    env.barrier()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    env.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    return env.max_over_ranks(ms), clocks
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -184,87 +180,224 @@ def measured_peaks():
         return None
 
 
-def run_reference(args, rank, world):
-    if rank != 0:
+def measure_fp64_peak(t):
+    """DFMA microbenchmark of the library (ds_fp64_peak_run), best of 3, CUDA events -> TFLOP/s (None on failure)."""
+    from distantspeech_b200 import _lib as L
+    try:
+        scratch = t.zeros(8, dtype=t.float64, device="cuda")
+        best = None
+        for it in range(4):
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            flops = L.lib().ds_fp64_peak_run(8000, L.ptr(scratch), L.stream_ptr())
+            e1.record()
+            t.cuda.synchronize()
+            if flops <= 0:
+                return None
+            tf = flops / (e0.elapsed_time(e1) / 1e3) / 1e12
+            if it > 0:
+                best = tf if best is None else max(best, tf)
+        return best
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------
+# synthetic data on the device (SURVEY 8d recipe)
+# --------------------------------------------------------------------------
+def synth_device(torch, S, mic, n_samples, seed, look=LOOK, interf=INTERF, fs=FS, chunk=64, dtype=None):
+    from distantspeech_b200.beamformer.MicArray import compute_tau
+    dev = "cuda"
+    Mm = mic.M
+    tau_s = torch.as_tensor(compute_tau(mic, np.array(look) / 180 * np.pi)[:, 0], device=dev)
+    tau_i = torch.as_tensor(compute_tau(mic, np.array(interf) / 180 * np.pi)[:, 0], device=dev)
+    nfft = 1 << int(np.ceil(np.log2(n_samples + 64)))
+    f = torch.fft.rfftfreq(nfft, 1.0 / fs, device=dev, dtype=torch.float64)
+    t = torch.arange(n_samples, device=dev, dtype=torch.float64) / fs
+    env = (torch.sin(2 * np.pi * 0.7 * t) >= 0).to(torch.float32)
+    ph_s = torch.exp(-2j * np.pi * f[None, :] * tau_s[:, None]).to(torch.complex64)       # [M, F]
+    ph_i = torch.exp(-2j * np.pi * f[None, :] * tau_i[:, None]).to(torch.complex64)
+    x = torch.empty((S, Mm, n_samples), dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    for lo in range(0, S, chunk):
+        hi = min(S, lo + chunk)
+        n = hi - lo
+        tgt = torch.randn((n, n_samples), generator=gen, device=dev) * env * 0.3
+        itf = torch.randn((n, n_samples), generator=gen, device=dev) * 0.2
+        Ft = torch.fft.rfft(tgt, nfft)
+        Fi = torch.fft.rfft(itf, nfft)
+        for m in range(Mm):
+            d = torch.fft.irfft(Ft * ph_s[m] + Fi * ph_i[m], nfft)[:, :n_samples]
+            d = d + torch.randn((n, n_samples), generator=gen, device=dev) * 0.05
+            x[lo:hi, m, :] = 0.5 * d
+    return x
+
+
+# --------------------------------------------------------------------------
+# host placement for the end-to-end path (one rank per GPU: CPUs and pinned memory next to the rank's GPU)
+# --------------------------------------------------------------------------
+def bind_near_gpu(torch, local_rank):
+    """Binds this process's CPU affinity (and, when the kernel allows it, its memory policy) to the NUMA node the
+    rank's GPU hangs off, before the pinned staging buffers are allocated (first touch).  Reports what happened."""
+    info = {"gpu_numa_node": None, "cpus_visible": None, "cpus_bound": None, "mempolicy": "unchanged"}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        info["cpus_visible"] = len(allowed)
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        near = sorted(cpus & set(allowed))
+        if near:
+            os.sched_setaffinity(0, near)
+            info["cpus_bound"] = len(near)
+        else:
+            info["cpus_bound"] = 0                                      # the container's cpuset has no CPU on that node
+        try:                                                            # set_mempolicy(MPOL_PREFERRED, node): x86-64 syscall 238
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy refused (errno %d)" % ctypes.get_errno()
+        except Exception as e:
+            info["mempolicy"] = "unavailable (%s)" % type(e).__name__
+    except Exception as e:
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
+def copy_only(env, chain, x_host, y_host, cs, steps):
+    """Bare-copy ceiling of process_host: the same pinned buffers, staging buffers, group size and streams, copies only
+    (H2D of every input group and D2H of every output group, both directions in flight at once)."""
+    t = env.torch
+    S = x_host.shape[0]
+    hp = chain._host_pipeline(min(cs, S), x_host.shape[1], x_host.shape[2], x_host.dtype, y_host.dtype)
+    n_chunks = (S + cs - 1) // cs
+
+    def once():
+        for c in range(n_chunks):
+            b = c & 1
+            lo, hi = c * cs, min(S, (c + 1) * cs)
+            with t.cuda.stream(hp["s_in"]):
+                hp["xbuf"][b][:hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+            with t.cuda.stream(hp["s_out"]):
+                y_host[lo:hi].copy_(hp["ybuf"][b][:hi - lo], non_blocking=True)
+        hp["s_in"].synchronize()
+        hp["s_out"].synchronize()
+    once()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    env.barrier()
+    return env.max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+
+# --------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# --------------------------------------------------------------------------
+CPU_SECONDS = {1: 1.0, 2: 10.0, 3: 1.0, 4: 2.0, 5: 0.25}      # audio seconds per stream and step: about a second of CPU work
+
+
+def run_reference(args, env):
+    if env.rank != 0:
         return
-    val, cores, sample = cpu_baseline(args.cpu_streams_per_core, args.cpu_seconds, repeats=max(1, min(args.steps, 3)))
-    step_audio = cores * args.cpu_streams_per_core * (int(args.cpu_seconds * FS) // HOP * HOP) / FS
+    from oracle import cpu_baselines as B           # the one other place bench.py may execute oracle/
+    cfg = args.config
+    secs = args.cpu_seconds or CPU_SECONDS[cfg]
+    r = B.time_cpu(cfg, secs, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
     line = {
-        "impl": "reference", "metric": "audio-s/s (x realtime) for 8-mic MVDR+postfilter chain", "value": val,
-        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_audio / val * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "configs[3]: MVDR + McSppBase + OMLSA chain, 8-mic circular r=0.05 16 kHz, n_fft 512 hop 256",
-                   "step": "one bounded sample of the workload: %s (best of up to 3 repeats)" % sample,
-                   "note": "reference CPU path = numpy oracle port (the reference is Python and cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRICS[cfg], "value": r["value"], "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[cfg],
+                   "step": "one bounded sample of the workload: %s; every step and warm-up step really runs" % r["sample"],
+                   "audio_s_per_step": r["audio_s_per_step"]},
+        "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+def cpu_baseline(cfg, args):
+    from oracle import cpu_baselines as B
+    secs = args.cpu_seconds or {1: 2.0, 2: 10.0, 3: 2.0, 4: 10.0, 5: 0.25}[cfg]
+    r = B.time_cpu(cfg, secs, steps=2 if cfg == 4 else 1, warmup=0)
+    return {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
-    import torch
-    import torch.distributed as dist
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its banner on stdout; stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+def _parity_job(job):
+    cfg, x, n = job
+    from oracle import cpu_baselines as B
+    return np.asarray(B.parity_reference(cfg, x[:, :n] if n else x), dtype=np.float64)
+
+
+def parity_streams(cfg, xs, ys, what):
+    """xs: list of [M, N] float32 arrays, ys: list of [N'] outputs; the oracle runs one stream per host core."""
+    import multiprocessing as mp
+    jobs = [(cfg, np.asarray(x, dtype=np.float64), 0) for x in xs]
+    cores = min(len(jobs), len(os.sched_getaffinity(0)))
+    with mp.get_context("fork").Pool(cores) as pool:
+        refs = pool.map(_parity_job, jobs)
+    worst_err, worst_snr = 0.0, 1e9
+    for ref, out in zip(refs, ys):
+        out = np.asarray(out, dtype=np.float64)[:ref.shape[0]]
+        ref = ref[:out.shape[0]]
+        worst_err = max(worst_err, float(np.max(np.abs(ref - out))))
+        worst_snr = min(worst_snr, float(10 * np.log10(np.sum(ref ** 2) / max(np.sum((ref - out) ** 2), 1e-300))))
+    return {"max_abs": worst_err, "snr_db": worst_snr, "streams_checked": len(xs), "seconds": what,
+            "tolerance": "max-abs <= 1e-4 and SNR >= 60 dB (BASELINE.json north_star)",
+            "ok": bool(worst_err <= 1e-4 and worst_snr >= 60)}
+
+
+def kernel_sources_sha():
+    """sha1 over the CUDA sources: ncu-derived figures in profiles/traffic.json are only quoted for the build they were
+    captured from."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "distantspeech_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:12]
+
+
+# --------------------------------------------------------------------------
+# headline: config 4
+# --------------------------------------------------------------------------
+def run_headline(args, env):
+    t, rank, world = env.torch, env.rank, env.world
     from distantspeech_b200 import _lib
     from distantspeech_b200.beamformer.MicArray import MicArray
     from distantspeech_b200.pipelines import MvdrMcsppChain
+    from distantspeech_b200.sharding import shard_bounds, gather_validation_streams
     _lib.ensure_init()
-
-    from distantspeech_b200.sharding import shard_bounds, gather_validation_streams, max_over_ranks
-    lo, hi = shard_bounds(args.streams_per_gpu * world, rank, world)      # weak scaling: fixed streams per GPU
+    spg = args.streams_per_gpu or 1024
+    lo, hi = shard_bounds(spg * world, rank, world)      # weak scaling: fixed streams per GPU
     S = hi - lo
     N = int(args.seconds * FS) // HOP * HOP
     mic = MicArray(arrayType="circular", r=0.05, M=M, n_fft=N_FFT)
     chain = MvdrMcsppChain(mic, look_angle=LOOK, n_fft=N_FFT, hop=HOP, full_state=bool(args.full_state),
                            fft_precision=args.fft)
-    x = synth_device(torch, S, mic, N, seed=0x5EED + lo)
-    y = torch.empty((S, N), dtype=torch.float32, device="cuda")
-    torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    x = synth_device(t, S, mic, N, seed=0x5EED + lo)
+    y = t.empty((S, N), dtype=t.float32, device="cuda")
+    t.cuda.synchronize()
 
     def step():
         chain.reset_counters()
         chain._state.zero_() if chain._state is not None else None
         chain.process_device(x, out=y)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
-    ms_max = max_over_ranks(ms, device="cuda")
-    audio_total = world * S * (N / FS) * args.steps
-    value = audio_total / (ms_max / 1e3)
+    ms_max, clocks = time_steps(env, step, args.steps, args.warmup)
+    audio_step = world * S * (N / FS)
+    value = audio_step * args.steps / (ms_max / 1e3)
 
     # ---- per-kernel timing for the roofline (CUDA events inside the library, same stream) ----
     phase = np.zeros(3)
@@ -279,104 +412,124 @@ def main():
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     algo_bytes = ALGO_BYTES_PER_AUDIO_S * S * (N / FS)
     dom = int(np.argmax(phase))
-    names = ["stft_kernel", "mcspp_fast_kernel" if not args.full_state else "mcspp_kernel", "istft_kernel"]
-    traffic = None
+    names = ["stft_kernel", "mcspp_fast_kernel" if not args.full_state else "mcspp_kernel", "istft_seq_kernel"]
+    traffic, traffic_note = None, "no ncu capture of this build (profiles/traffic.json is keyed by the CUDA sources' sha)"
     flop_bf, pipe_pct = 1928.0, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        per_stream = tj.get(names[dom], {}).get("dram_bytes_per_stream_10s")
         flop_bf = float(tj.get("mcspp_fast_kernel", {}).get("fp64_flop_per_bin_frame", flop_bf))
-        pipe_pct = tj.get("mcspp_fast_kernel", {}).get("ncu_pipe_fp64_pct")
-        if per_stream is not None:
-            traffic = per_stream * S * (N / FS) / 10.0      # ncu dram read+write of one launch, scaled to this launch
+        if tj.get("csrc_sha") == kernel_sources_sha():
+            per_stream = tj.get(names[dom], {}).get("dram_bytes_per_stream_10s")
+            pipe_pct = tj.get("mcspp_fast_kernel", {}).get("ncu_pipe_fp64_pct")
+            if per_stream is not None:
+                traffic = per_stream * S * (N / FS) / 10.0      # ncu dram read+write of one launch, scaled to this launch
+                traffic_note = "ncu --set full capture of this build (%s), dram__bytes_read.sum + dram__bytes_write.sum" % tj.get("capture", "profiles/")
     except Exception:
         pass
     achieved = algo_bytes / (phase[dom] / 1e3) / 1e9
     # what actually bounds the dominant kernel: the fp64 pipe.  FLOP per (bin, frame) from the executed SASS mix of the
-    # frame loop (profiles/traffic.json: 800 DFMA x 2 + 229 DMUL + 99 DADD); nominal pipe peak = 148 SM x 64 FMA/clk x 2 x SM clock
+    # frame loop (profiles/traffic.json); the pipe's peak is MEASURED here with the library's DFMA microbenchmark
     bin_frames = S * (N // HOP) * (N_FFT // 2 + 1 - 2)
     fp64_flop = flop_bf * bin_frames
     sm_mhz = (peaks or {}).get("sm_max_mhz", 1965.0)
-    fp64_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+    fp64_nominal = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+    fp64_measured = measure_fp64_peak(t)
+    fp64_peak = fp64_measured or fp64_nominal
+    fp64_ach = fp64_flop / (phase[1] / 1e3) / 1e12
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic,
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": {n: float(v) for n, v in zip(names, phase)},
-                "fp64_pipe": {"achieved_tflops": fp64_flop / (phase[1] / 1e3) / 1e12, "nominal_peak_tflops": fp64_peak,
-                              "frac": fp64_flop / (phase[1] / 1e3) / 1e12 / fp64_peak,
-                              "flop_per_bin_frame": flop_bf,
-                              "ncu_pipe_fp64_pct": pipe_pct},
-                "note": "the per-bin kernel is bound by the fp64 pipe (two fp64-dense warps per scheduler at 8 warps/SM), not by HBM: "
-                        "the contractual hbm fraction is small by construction (SURVEY.md 8d); fp64_pipe is the binding roof; "
-                        "traffic exceeds the algorithmic bytes because the complex64 spectrum (2x the waveform at 50% overlap) "
-                        "is staged in HBM between the three kernels -- see DESIGN.md"}
+                "whole_step": {"achieved": algo_bytes / (ms_max / args.steps / 1e3) / 1e9,
+                               "frac": algo_bytes / (ms_max / args.steps / 1e3) / 1e9 / hbm_peak},
+                "fp64_pipe": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak,
+                              "peak_source": "measured: ds_fp64_peak_run DFMA microbenchmark, best of 3, CUDA events" if fp64_measured
+                              else "nominal 148 SM x 64 FMA/clk x 2 x SM clock (microbenchmark failed)",
+                              "nominal_peak_tflops": fp64_nominal, "frac": fp64_ach / fp64_peak,
+                              "flop_per_bin_frame": flop_bf, "ncu_pipe_fp64_pct": pipe_pct},
+                "note": "the per-bin kernel is bound by the fp64 pipe, not by HBM: the contractual hbm fraction is small by "
+                        "construction (SURVEY.md 8d); fp64_pipe is the binding roof -- see DESIGN.md"}
 
-    # ---- parity spot check on the first stream of every rank (first 2 s; the chain is causal) ----
+    # ---- parity: 8 streams spread over the whole job, full length, against the oracle ----
+    n_sel = max(1, 8 // world)
+    sel = [int(round(i)) for i in np.linspace(0, S - 1, n_sel)]
+    ys = gather_validation_streams(y[sel].contiguous(), dst=0)     # NCCL gather: validation only, outside the timed region
+    xs = gather_validation_streams(x[sel].contiguous(), dst=0)
     parity = None
-    n_chk = HOP * 125
-    y_first = y[0, :n_chk].clone()
-    x_first = x[0, :, :n_chk].clone()
-    ys = gather_validation_streams(y_first, dst=0)     # NCCL gather: validation only, outside the timed region
-    xs = gather_validation_streams(x_first, dst=0)
     if rank == 0:
-        from oracle import np_oracle as O       # checker only
-        geo = O.MicGeometry("circular", r=0.05, M=M, n_fft=N_FFT)
-        worst_err, worst_snr = 0.0, 1e9
-        for r in range(min(world, 2)):
-            ref = O.mvdr_mcspp_chain(xs[r].cpu().numpy().T.astype(np.float64), geo, LOOK, N_FFT, HOP)
-            out = ys[r].cpu().numpy().astype(np.float64)
-            worst_err = max(worst_err, float(np.max(np.abs(ref - out))))
-            worst_snr = min(worst_snr, float(10 * np.log10(np.sum(ref ** 2) / max(np.sum((ref - out) ** 2), 1e-300))))
-        parity = {"max_abs": worst_err, "snr_db": worst_snr, "streams_checked": min(world, 2), "seconds": n_chk / FS,
-                  "ok": bool(worst_err <= 1e-4 and worst_snr >= 60)}
+        xl = [xx.cpu().numpy() for blk in xs for xx in blk]
+        yl = [yy.cpu().numpy() for blk in ys for yy in blk]
+        parity = parity_streams(4, xl, yl, N / FS)
+        parity["streams"] = "local indices %s of every rank's shard" % sel
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        x_host = torch.empty((S, M, N), dtype=torch.float32, pin_memory=True)
+        place = bind_near_gpu(t, env.local_rank)
+        cs = args.chunk_streams
+
+        def e2e_run(xh, yh):
+            chain.process_host(xh, yh, chunk_streams=cs)          # warm-up (allocates the staging pipeline once)
+            env.barrier()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(args.steps):
+                chain.process_host(xh, yh, chunk_streams=cs)
+            e1.record()
+            env.barrier()
+            wall = (time.perf_counter() - t0) * 1e3
+            return env.max_over_ranks(e0.elapsed_time(e1)), env.max_over_ranks(wall)
+
+        # int16 PCM in and out (the reference's on-disk format: load_audio / save_audio, beamformer/utils.py:182-196)
+        x_pcm = t.empty((S, M, N), dtype=t.int16, pin_memory=True)
+        x_pcm.copy_((x * 32767.0).round_().clamp_(-32768, 32767))   # x is scratch from here on
+        y_pcm = t.empty((S, N), dtype=t.int16, pin_memory=True)
+        ms_p, wall_p = e2e_run(x_pcm, y_pcm)
+        ms_c = copy_only(env, chain, x_pcm, y_pcm, cs, args.steps)
+        h2d, d2h = int(S * M * N * 2), int(S * N * 2)
+        v_pcm, v_copy = audio_step * args.steps / (ms_p / 1e3), audio_step * args.steps / (ms_c / 1e3)
+        e2e = {"value": v_pcm, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "MvdrMcsppChain.process_host(int16 PCM x[S,M,N], int16 y[S,N]): pinned host buffers, %d-stream groups, "
+                      "copy/compute overlap on three streams; load_audio / save_audio scalings fused into the kernels" % cs,
+               "ms_per_step": ms_p / args.steps, "wall_ms_per_step": wall_p / args.steps,
+               "copy_ceiling": {"value": v_copy, "unit": "audio-s/s", "ms_per_step": ms_c / args.steps,
+                                "h2d_GBps_per_gpu": h2d / (ms_c / args.steps / 1e3) / 1e9,
+                                "what": "same pinned buffers, staging buffers, group size and streams, cudaMemcpyAsync only "
+                                        "(H2D and D2H in flight together), wall clock, max over ranks"},
+               "frac_of_copy_ceiling": v_pcm / v_copy,
+               "limiter": "host->device copy over PCIe (kernels hidden behind the copies)" if v_pcm / v_copy > 0.85
+               else "see frac_of_copy_ceiling: below the bare-copy ceiling",
+               "host_placement": place}
+        del x_pcm, y_pcm
+        # float32 host buffers beside it (twice the bytes over PCIe)
+        x = synth_device(t, S, mic, N, seed=0x5EED + lo)
+        x_host = t.empty((S, M, N), dtype=t.float32, pin_memory=True)
         x_host.copy_(x)
-        y_host = torch.empty((S, N), dtype=torch.float32, pin_memory=True)
+        y_host = t.empty((S, N), dtype=t.float32, pin_memory=True)
         del x
-        torch.cuda.empty_cache()
-        chain.process_host(x_host, y_host, chunk_streams=128)          # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            chain.process_host(x_host, y_host, chunk_streams=128)
-        e1.record()
-        barrier()
-        ms_e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0)     # device clock
-        e2e = {"value": audio_total / (max_over_ranks(ms_e, device="cuda") / 1e3), "unit": "audio-s/s",
-               "h2d_bytes_per_step": int(S * M * N * 4), "d2h_bytes_per_step": int(S * N * 4),
-               "api": "MvdrMcsppChain.process_host (pinned float32 host buffers, 128-stream groups, copy/compute overlap)"}
-        # same call with int16 PCM host buffers (the reference's on-disk format; load_audio's /32767 runs on the device)
-        x_pcm = torch.empty((S, M, N), dtype=torch.int16, pin_memory=True)
-        x_pcm.copy_((x_host * 32767.0).round_().clamp_(-32768, 32767))
-        del x_host
-        chain.process_host(x_pcm, y_host, chunk_streams=128)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            chain.process_host(x_pcm, y_host, chunk_streams=128)
-        e1.record()
-        barrier()
-        e2e["pcm16"] = {"value": audio_total / (max_over_ranks(e0.elapsed_time(e1), device="cuda") / 1e3), "unit": "audio-s/s",
-                        "h2d_bytes_per_step": int(S * M * N * 2), "d2h_bytes_per_step": int(S * N * 4),
-                        "api": "MvdrMcsppChain.process_host with int16 PCM host buffers"}
+        t.cuda.empty_cache()
+        chain._hp = None
+        ms_f, _ = e2e_run(x_host, y_host)
+        e2e["f32"] = {"value": audio_step * args.steps / (ms_f / 1e3), "unit": "audio-s/s",
+                      "h2d_bytes_per_step": int(S * M * N * 4), "d2h_bytes_per_step": int(S * N * 4),
+                      "api": "MvdrMcsppChain.process_host with float32 host buffers"}
+        del x_host, y_host
+        chain._hp = None
+        t.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample = cpu_baseline(args.cpu_streams_per_core, args.cpu_seconds)
-        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
+        cpu = cpu_baseline(4, args)
 
+    line = None
     if rank == 0:
         line = {
-            "metric": "audio-s/s (x realtime) for 8-mic MVDR+postfilter chain", "value": value, "unit": "audio-s/s",
+            "metric": METRIC, "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[3]: MVDR + McSppBase + OMLSA chain, 8-mic circular r=0.05 16 kHz, n_fft 512 hop 256",
+            "config": {"workload": WORKLOADS[4],
                        "streams_per_gpu": S, "seconds_per_stream": N / FS, "streams_total": S * world,
                        "fft": args.fft, "state": "full" if args.full_state else "output-only",
                        "l2": "inputs (%.1f GB per GPU) exceed L2; no flush needed" % (S * M * N * 4 / 1e9),
@@ -384,9 +537,255 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         }
+    return line
+
+
+# --------------------------------------------------------------------------
+# configs 1, 2, 3, 5 -- same measurement rules, smaller step counts
+# --------------------------------------------------------------------------
+def run_config(cfg, args, env, steps, warmup, with_cpu=True, with_e2e=True):
+    """One line of the same shape as the headline's for configuration cfg of BASELINE.json."""
+    t, rank, world = env.torch, env.rank, env.world
+    from distantspeech_b200 import _lib as L
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.sharding import gather_validation_streams
+    from oracle import cpu_baselines as B            # configuration table + checker (parity / cpu_baseline legs only)
+    L.ensure_init()
+    c = B.CONFIGS[cfg]
+    fs, hop, Mm = c["fs"], c["hop"], c["M"]
+    N = int(args.seconds * fs) // hop * hop
+    mic = MicArray(arrayType=c["array"], r=c["r"], M=Mm, n_fft=c["n_fft"])
+    if fs != 16000:                                  # the reference hard-wires 16 kHz (MicArray.py:27)
+        mic.fs = fs
+        mic.omega = 2 * np.pi * mic.freq_bin * mic.fs / mic.n_fft
+    S = args.streams_per_gpu or {1: 2048, 2: 1024, 3: 4096, 5: 1}[cfg]
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    x = synth_device(t, S, mic, N, seed=0x5EED + rank * S, look=c["look"], interf=c["interf"], fs=fs)     # [S, M, N]
+    extra = {}
+    launches = None
+
+    if cfg == 1:
+        from distantspeech_b200.beamformer.adaptivebeamformer import adaptivebeamfomer
+        ang = np.array(c["look"]) / 180 * np.pi
+        ab = adaptivebeamfomer(mic, c["n_fft"], hop, c["n_fft"])
+        out = {}
+
+        def step():
+            ab._state = None
+            out["y"] = ab.process(x, ang, method=2)["data"]
+        algo_per_s = Mm * fs * 4 + fs * 4
+        launches, api = 6, "adaptivebeamfomer.process(x[S,M,N] CUDA tensor, angle, method=2)['data']"
+        get_y = lambda: out["y"]                                                        # noqa: E731
+        one = adaptivebeamfomer(mic, c["n_fft"], hop, c["n_fft"])
+        x1 = x[0].contiguous()
+
+        def step1():
+            one._state = None
+            one.process(x1, ang, method=2)
+    elif cfg == 2:
+        from distantspeech_b200.beamformer.fixedbeamformer import FixedBeamformer
+        fb = FixedBeamformer(mic, c["n_fft"], hop, c["n_fft"])
+        W = fb.compute_weights(list(c["look"]), "SD")[None]
+        Wd = L.to_device(np.asarray(W, dtype=np.complex64), t.complex64)
+        p = L.FixedBfParams(c["n_fft"], hop, S, Mm, N, 1, 0, 0, float(hop / fb.transform.W0))
+        state = t.zeros(L.lib().ds_fixedbf_state_bytes(ctypes.byref(p)), dtype=t.uint8, device="cuda")
+        y2 = t.empty((S, 1, N), dtype=t.float32, device="cuda")
+        win = L.device_window(fb.transform.window, c["n_fft"])
+
+        def step():
+            state.zero_()
+            L.check(L.lib().ds_fixedbf_run(ctypes.byref(p), L.ptr(win), L.ptr(Wd), L.ptr(state), L.ptr(x), L.ptr(y2),
+                                           L.stream_ptr()), "ds_fixedbf_run")
+        algo_per_s = Mm * fs * 4 + fs * 4
+        launches, api = 2, "ds_fixedbf_run (the call FixedBeamformer.process makes) on x[S,M,N] CUDA"
+        get_y = lambda: y2[:, 0, :]                                                     # noqa: E731
+    elif cfg == 3:
+        from distantspeech_b200.beamformer.FDGSC import FDGSC
+        fd = FDGSC(mic, frameLen=256, angle=list(c["look"]))
+        out = {}
+
+        def step():
+            fd.reset()
+            out["y"] = fd.process_device(x)
+        algo_per_s = Mm * fs * 4 + fs * 4
+        launches, api = 1, "FDGSC.process_device(x[S,M,N] CUDA tensor) (the kernel call FDGSC.process makes, output only)"
+        get_y = lambda: out["y"]                                                        # noqa: E731
+    else:
+        from distantspeech_b200.doa.srp import srp
+        sp = srp(mic, engine="tensor")
+        az, el = np.arange(360), np.arange(90)
+        tau = np.stack([mic.compute_tau(np.array([a, e]) * np.pi / 180)[:, 0] for a in az for e in el])
+        xin = x[0].t().contiguous()                                                     # [N, M]
+        X = sp._spectrum(xin)                                                           # [T, M, K]
+        out = {}
+
+        def step():
+            out["P"] = sp._steered_response(X, tau, True)
+        D, T, K = tau.shape[0], X.shape[0], X.shape[2]
+        launches, api = 3, "srp._steered_response (PHAT + re-tiling + tcgen05 contraction) over 32400 directions"
+
+    ms_max, clocks = time_steps(env, step, steps, warmup)
+    audio_step = world * S * (N / fs)
+    value = audio_step * steps / (ms_max / 1e3)
+    ms_step = ms_max / steps
+
+    # ---- roofline ----
+    if cfg == 5:
+        flops = 8.0 * D * Mm * K * T
+        bf16 = (peaks or {}).get("bf16_tflops", 1685.9)
+        ach = flops / (ms_step / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "srp_tc_kernel (+ phat_kernel, srp_pack_kernel in the same step)", "achieved": ach,
+                    "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); the kernel runs kind::tf32, whose dense rate is half of bf16",
+                    "frac_of_tf32_rate": ach / (bf16 / 2), "algorithmic_flop_per_launch": flops,
+                    "note": "8*D*M*K flop per frame (SURVEY.md 8d), D=%d directions, K=%d bins, T=%d frames" % (D, K, T)}
+    else:
+        algo = algo_per_s * S * (N / fs)
+        ach = algo / (ms_step / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": {1: "amvdr_kernel (+ stft / istft kernels in the same step)",
+                                               2: "fixedbf_seq_kernel", 3: "fdgsc kernels"}[cfg],
+                    "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_launch": algo,
+                    "note": "whole step against SURVEY.md 8d's bytes (%d B per audio-second per stream)" % algo_per_s}
+
+    # ---- parity against the oracle ----
+    parity = None
+    if cfg == 5:
+        if rank == 0:
+            from oracle import np_oracle as O
+            geo = B.geometry(5)
+            rng = np.random.default_rng(0)
+            ti = np.sort(rng.choice(T, min(64, T), replace=False))
+            di = np.sort(rng.choice(D, 256, replace=False))
+            Y = O.Transform(channel=Mm, n_fft=c["n_fft"], hop_length=hop).stft(xin.cpu().numpy().astype(np.float64))
+            tau_o = np.stack([O.method_tau(geo, np.array([i // 90, i % 90]) * np.pi / 180)[:, 0] for i in di])
+            Pref = O.srp_map(Y[:, ti, :], geo.omega, tau_o)
+            got = out["P"][t.as_tensor(di, device="cuda")][:, t.as_tensor(ti, device="cuda")].double().cpu().numpy()
+            rel = float(np.max(np.abs(got - Pref) / np.abs(Pref)))
+            Pfull = out["P"].sum(dim=1)
+            ia = int(t.argmax(Pfull).item())
+            parity = {"max_rel": rel, "frames_checked": int(len(ti)), "directions_checked": int(len(di)), "grid": "full 360 x 90",
+                      "tolerance": "map rel-err <= 1e-3 (SURVEY.md 8d)", "argmax_az_el": [ia // 90, ia % 90],
+                      "source_az_el": list(c["look"]),
+                      "ok": bool(rel <= 1e-3 and abs(ia // 90 - c["look"][0]) <= 3)}
+            if not parity["ok"]:
+                raise RuntimeError("config 5 parity failed: %s" % parity)
+    else:
+        n_chk = {1: N, 2: N, 3: min(N, 256 * 125)}[cfg]           # FDGSC oracle: 2 s per stream (causal chain)
+        n_sel = max(1, {1: 4, 2: 8, 3: 4}[cfg] // world)
+        sel = [int(round(i)) for i in np.linspace(0, S - 1, n_sel)]
+        yv = get_y()
+        ys = gather_validation_streams(yv[sel][:, :n_chk].contiguous(), dst=0)
+        xs = gather_validation_streams(x[sel][:, :, :n_chk].contiguous(), dst=0)
+        if rank == 0:
+            xl = [xx.cpu().numpy() for blk in xs for xx in blk]
+            yl = [yy.cpu().numpy() for blk in ys for yy in blk]
+            parity = parity_streams(cfg, xl, yl, n_chk / fs)
+    if cfg == 1:
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        step1(); step1()
+        t.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            step1()
+        e1.record()
+        t.cuda.synchronize()
+        extra["single_utterance"] = {"ms": e0.elapsed_time(e1) / 5, "x_realtime": (N / fs) / (e0.elapsed_time(e1) / 5 / 1e3),
+                                     "what": "configs[0] as worded: ONE 10 s utterance through adaptivebeamfomer.process (incl. API hand-off)"}
+
+    # ---- end to end: the same call with HOST buffers ----
+    e2e = None
+    if with_e2e and cfg in (1, 2, 3):
+        reps = 2
+        Se = min(S, 512)
+        xh = t.empty((Se, Mm, N), dtype=t.float32, pin_memory=True)
+        xh.copy_(x[:Se])
+        yh = t.empty((Se, N), dtype=t.float32, pin_memory=True)
+
+        def host_call():
+            xd = xh.to("cuda", non_blocking=True)
+            if cfg == 1:
+                a1 = adaptivebeamfomer(mic, c["n_fft"], hop, c["n_fft"])
+                yd = a1.process(xd, ang, method=2)["data"]
+            elif cfg == 2:
+                yd = fb._run(xd.permute(0, 2, 1), W)[:, 0, :]
+            else:
+                fd.reset()
+                yd = fd.process_device(xd)
+            yh.copy_(yd, non_blocking=True)
+            t.cuda.synchronize()
+        host_call()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            host_call()
+        dt = (time.perf_counter() - t0) / reps
+        e2e = {"value": world * Se * (N / fs) / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(Se * Mm * N * 4),
+               "d2h_bytes_per_step": int(Se * N * 4), "api": "pinned float32 host buffers -> %s -> pinned host buffer, %d streams per call, wall clock" % (api, Se)}
+        del xh, yh
+    elif with_e2e and cfg == 5:
+        xh = xin.cpu().pin_memory()
+
+        def host_call5():
+            Ph = sp.compute_grid_spectrum(xh, az, el, as_torch=True)
+            am = int(t.argmax(Ph.sum(dim=2)).item())              # the DOA estimate is what comes back to the host
+            return am
+        host_call5()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            host_call5()
+        dt = (time.perf_counter() - t0) / 2
+        e2e = {"value": (N / fs) / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(N * Mm * 4), "d2h_bytes_per_step": 8,
+               "api": "srp.compute_grid_spectrum(host x[N,16], 360 az x 90 el) + argmax back to the host (includes the host-side "
+                      "compute_tau loop over 32400 directions), wall clock"}
+
+    cpu = None
+    if rank == 0 and world == 1 and with_cpu and not args.no_cpu:
+        cpu = cpu_baseline(cfg, args)
+    line = None
+    if rank == 0:
+        line = {"metric": METRICS[cfg], "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if cfg == 5 else "f64", "data": "synthetic",
+                "config": {"workload": WORKLOADS[cfg], "streams_per_gpu": S, "seconds_per_stream": N / fs, "api": api,
+                           "l2": "inputs exceed L2" if S * Mm * N * 4 > 126e6 else "single utterance: spectrum tiles are L2-resident by design"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches or 0) * steps, "roofline": roofline, "cpu_baseline": cpu,
+                "parity": parity}
+        line.update(extra)
+    del x
+    t.cuda.empty_cache()
+    return line
+
+
+def main():
+    args = parse()
+    env = Env()
+    if args.impl == "reference":
+        run_reference(args, env)
+        return
+    env.init_gpu()
+    if args.config != 4:
+        line = run_config(args.config, args, env, args.steps, args.warmup)
+    else:
+        line = run_headline(args, env)
+        if env.world == 1 and not args.no_configs:
+            subs = {}
+            for cfg in (1, 2, 3, 5):
+                try:
+                    sub = run_config(cfg, args, env, steps=5, warmup=3, with_cpu=True, with_e2e=False)
+                    subs[str(cfg)] = {k: sub[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "dtype", "config",
+                                                          "clocks", "roofline", "cpu_baseline", "parity", "gpu_launches") if k in sub}
+                    if "single_utterance" in sub:
+                        subs[str(cfg)]["single_utterance"] = sub["single_utterance"]
+                except Exception as e:                      # a failing side configuration must not take the headline down
+                    subs[str(cfg)] = {"error": "%s: %s" % (type(e).__name__, e)}
+                    env.torch.cuda.empty_cache()
+            line["configs"] = subs
+    if env.rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -174,6 +174,35 @@ class FDGSC(object):
         d["fix"] = fx[:, Nb - Lf:].clone()
         return fix_d, aligned.permute(0, 2, 1), al_d.permute(0, 2, 1)
 
+    def process_device(self, xs, out=None, dc_notch=True):
+        """Device entry point of the batched path: xs [S, M, N] float32 CUDA (mic-major, N a multiple of frameLen;
+        overwritten with the DC-notched signal like FDGSC.py:213) -> output [S, N] float32 CUDA.  Only ``output`` of
+        the reference's tuple is produced (no diagnostics streams are written); the recursive state carries over
+        between calls exactly like ``process``."""
+        t = L.require_cuda()
+        L.ensure_init()
+        if not isinstance(xs, t.Tensor) or not xs.is_cuda or xs.dim() != 3 or xs.dtype != t.float32 or not xs.is_contiguous():
+            raise ValueError("xs must be a contiguous float32 CUDA tensor [S, M, N]")
+        S, M, N = xs.shape
+        if M != self.M or N < self.frameLen or N % self.frameLen != 0:
+            raise ValueError("expected [S, %d, N] with N a positive multiple of frameLen=%d" % (self.M, self.frameLen))
+        if self._state is None or self._S != S:
+            self._state = t.zeros(L.lib().ds_fdgsc_state_bytes(C.byref(self._params(S, N))), dtype=t.uint8, device="cuda")
+            self._S = S
+            self.spp.frm_cnt, self.spp.ell = 0, 1
+        prm = self._params(S, N)
+        prm.dc_notch = int(bool(dc_notch))
+        y = out if out is not None else t.empty((S, N), dtype=t.float32, device="cuda")
+        key = (t.cuda.current_device(),)
+        if getattr(self, "_h_dev", None) is None or self._h_dev[0] != key:
+            self._h_dev = (key, t.as_tensor(np.ascontiguousarray(self.time_alignment.delay_filter.T)).to("cuda"))     # [M, FL]
+        L.check(L.lib().ds_fdgsc_run(C.byref(prm), L.ptr(self._h_dev[1]), L.ptr(L.device_window(_sqrt_hann(512), 512)),
+                                     L.ptr(self._state), L.ptr(xs), L.ptr(y), None, None, None, L.stream_ptr()), "ds_fdgsc_run")
+        f, e = C.c_int32(self.spp.frm_cnt), C.c_int32(self.spp.ell)
+        L.lib().ds_mcra_advance(int(self.spp.L), N // self.frameLen, C.byref(f), C.byref(e))
+        self.spp.frm_cnt, self.spp.ell = f.value, e.value
+        return y
+
     def process(self, x, postfilter=False, dc_notch=True, diagnostics=None):
         """x [n_samples, n_chs] (or [S, n_samples, n_chs]) -> (output, p, fix_output, fix_output_delayed,
         bm_output, aligned_output, aligned_output_delayed, bm, aic_filter) like FDGSC.py:307-317.

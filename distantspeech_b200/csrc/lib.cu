@@ -78,9 +78,38 @@ int get_twiddles(int n_fft, TwiddleSet *out) {
   return DS_OK;
 }
 
+// fp64-pipe microbenchmark: 8 independent DFMA chains per thread, 8 warps per scheduler -- the measured
+// denominator of the per-bin kernels' fp64 roofline (MEASURED_PEAKS.json has no fp64 figure)
+__global__ void __launch_bounds__(1024) fp64_peak_kernel(int iters, double seed, double *out) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0 - 1e-9, c = 1e-9;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 12345.678) out[0] = r;      // never true: keeps the chains alive
+}
+
 }  // namespace ds
 
 extern "C" {
+
+// Launches the DFMA microbenchmark on `stream` (time it with events around the call); returns the number of
+// floating-point operations the launch executes (2 per DFMA), or 0 on error.
+double ds_fp64_peak_run(int iters, double *scratch, void *stream) {
+  if (iters < 1 || !scratch) { ds::set_error("ds_fp64_peak_run: bad argument"); return 0.0; }
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0.0;
+  const int blocks = sms * 2, threads = 1024;
+  ds::fp64_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, 1.0, scratch);
+  if (cudaGetLastError() != cudaSuccess) { ds::set_error("ds_fp64_peak_run: launch failed"); return 0.0; }
+  return 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+}
 
 int ds_version(void) { return DS_VERSION; }
 

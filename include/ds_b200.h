@@ -57,6 +57,10 @@ const char *ds_last_error(void);
 int ds_init(void);
 /* SM count and compute capability of the current device. */
 int ds_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* fp64-pipe microbenchmark (8 independent DFMA chains per thread, 2 x 1024 threads per SM): launches on `stream`
+ * and returns the floating-point operations executed (0 on error); the caller times it with CUDA events.  It is the
+ * measured denominator of roofline.fp64_pipe in bench.py (no reference counterpart: measurement infrastructure). */
+double ds_fp64_peak_run(int iters, double *scratch, void *stream);
 
 /* ---- STFT / ISTFT  (transform/transform.py) --------------------------- */
 enum {

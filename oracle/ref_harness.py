@@ -34,13 +34,32 @@ import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get("DS_REFERENCE_ROOT", "/root/reference")
+_COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root():
+    """The reference's source tree when it is there (build container), else the byte-compiled copy that
+    oracle/build_ref.py wrote into oracle/_ref (what travels to the GPU box: outputs only, no sources)."""
+    env = os.environ.get("DS_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/DistantSpeech"):
+        return "/root/reference"
+    return _COMPILED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 _installed = False
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "DistantSpeech"))
+
+
+def reference_kind() -> str:
+    """'source' (the tree under /root/reference) or 'compiled' (sourceless .pyc under oracle/_ref)."""
+    return "source" if os.path.exists(os.path.join(REFERENCE_ROOT, "DistantSpeech", "transform", "transform.py")) else "compiled"
 
 
 def _make_librosa_stub():
@@ -107,6 +126,8 @@ def install():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/ds_numba_cache")
     sys.dont_write_bytecode = True
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)      # invalid escapes in the reference's plot labels
 
     import numpy as np
 
@@ -131,6 +152,15 @@ def install():
 
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+
+    if reference_kind() == "compiled":
+        # sourceless modules: numba cannot key an on-disk cache on a source file that is not there
+        # (transform.py:224 asks for cache=True) -- same JIT, just not cached across processes
+        import numba
+        _jit = numba.jit
+        if not getattr(numba, "_ds_nocache", False):
+            numba.jit = lambda *a, **k: _jit(*a, **dict(k, cache=False))
+            numba._ds_nocache = True
 
     # patch (ii)
     from DistantSpeech.beamformer import beamformer as _bf_mod
@@ -190,3 +220,31 @@ def make_subband_gsc(mic, frameLen=256, angle=None):
 
     with contextlib.redirect_stdout(io.StringIO()):
         return SubbandGSC(mic, frameLen=frameLen) if angle is None else SubbandGSC(mic, frameLen=frameLen, angle=angle)
+
+
+def reference_chain(x_nm, array_type="circular", r=0.05, M=8, look_angle=(30, 0), n_fft=512, hop=256):
+    """The config-4 composition of SURVEY.md 8c run on the REFERENCE's own classes (example/mcsppbase.ipynb cell 3,
+    example/mvdr.ipynb cell 4): Transform.stft -> McSppBase.estimation -> compute_mvdr_weight -> compute_omlsa_weight
+    -> (w^H y) G -> Transform.istft.  x_nm [N, M] float64 -> y [N].  Used as the timed CPU baseline of bench.py
+    (kind "reference") and to pin oracle.mvdr_mcspp_chain."""
+    install()
+    import contextlib
+    import io
+    import numpy as np
+    from DistantSpeech.transform.transform import Transform
+    from DistantSpeech.beamformer.MicArray import MicArray
+    from DistantSpeech.beamformer.beamformer import beamformer, compute_mvdr_weight
+    from DistantSpeech.noise_estimation.mcspp_base import McSppBase
+    with contextlib.redirect_stdout(io.StringIO()):
+        mic = MicArray(arrayType=array_type, r=r, M=M, n_fft=n_fft)
+    D = Transform(n_fft=n_fft, hop_length=hop, channel=M).stft(x_nm)
+    est = McSppBase(nfft=n_fft, channels=M)
+    a0 = beamformer(mic, frame_len=n_fft, hop=hop, nfft=n_fft).compute_steering_vector_from_doa(look_angle)
+    Y = np.zeros((n_fft // 2 + 1, D.shape[1], 1), dtype=complex)
+    for n in range(D.shape[1]):
+        yv = D[:, n, :]
+        est.estimation(yv)
+        w = compute_mvdr_weight(a0, est.Phi_vv_inv)
+        est.compute_omlsa_weight(est.xi, est.p)
+        Y[:, n, 0] = np.einsum("ij,ij->i", w.conj(), yv) * est.G
+    return Transform(n_fft=n_fft, hop_length=hop, channel=1).istft(Y)
