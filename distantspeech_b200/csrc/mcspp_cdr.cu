@@ -1,5 +1,7 @@
 // mcspp_cdr.cu -- McSpp (noise_estimation/mcspp.py:46-305) with its McCDR prior
-// (noise_estimation/mccdr.py:25-192, coherence/BinauralEnhancement.py:24-59), 4 microphones.
+// (noise_estimation/mccdr.py:25-192, coherence/BinauralEnhancement.py:24-59), M = 4 ... 8 microphones (M = 4 is the
+// only count the reference runs as shipped: mcspp.py:54 builds McCDR with its default channels = 4; above 4 the pin
+// is the reference with McCDR(nfft, channels = M) handed in, oracle/ref_harness.make_mcspp).
 //
 // Per frame the reference does (file:line):
 //   q = 1 - McCDR.estimation(y)                               mcspp.py:117-118
@@ -25,47 +27,56 @@
 
 namespace ds {
 
-constexpr int CDR_M = 4, CDR_NQ = 6;
-// state blob [S][CDR_NE][K] float64
-enum {
-  CS_PYY = 0,      // d[4] ur[6] ui[6]
-  CS_PVV = 16,
-  CS_PXII = 32,    // [4]
-  CS_PXIJ_R = 36,  // [6] pairs in (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) order
-  CS_PXIJ_I = 42,
-  CS_MCRA = 48,    // S Smin Stmp p lambda
-  CS_P = 53,
-  CS_AINV = 54,    // outputs of the last frame from here on
-  CS_PXX = 70,
-  CS_W_R = 86, CS_W_I = 90,
-  CS_XI = 94, CS_GAMMA = 95, CS_Q = 96, CS_CDR = 97,
-  CDR_NE = 98
+// state blob [S][NE][K] float64; element offsets for M microphones (NQ = M (M - 1) / 2 pairs, row-major i < j)
+template <int M> struct CdrLayout {
+  static constexpr int NQ = M * (M - 1) / 2, MM = M * M;
+  static constexpr int PYY = 0;                 // d[M] ur[NQ] ui[NQ]
+  static constexpr int PVV = MM;
+  static constexpr int PXII = 2 * MM;           // [M]
+  static constexpr int PXIJ_R = PXII + M;       // [NQ]
+  static constexpr int PXIJ_I = PXIJ_R + NQ;
+  static constexpr int MCRA = PXIJ_I + NQ;      // S Smin Stmp p lambda
+  static constexpr int P = MCRA + 5;
+  static constexpr int AINV = P + 1;            // outputs of the last frame from here on
+  static constexpr int PXX = AINV + MM;
+  static constexpr int W_R = PXX + MM, W_I = W_R + M;
+  static constexpr int XI = W_I + M, GAMMA = XI + 1, Q = XI + 2, CDR = XI + 3;
+  static constexpr int NE = XI + 4;
 };
+struct CdrOffsets { int M, NQ, PYY, PVV, PXII, MCRA, AINV, PXX, W_R, XI, NE; };
+static CdrOffsets cdr_offsets(int M) {
+  CdrOffsets o;
+  const int NQ = M * (M - 1) / 2, MM = M * M;
+  o.M = M; o.NQ = NQ; o.PYY = 0; o.PVV = MM; o.PXII = 2 * MM; o.MCRA = o.PXII + M + 2 * NQ; o.AINV = o.MCRA + 6;
+  o.PXX = o.AINV + MM; o.W_R = o.PXX + MM; o.XI = o.W_R + 2 * M; o.NE = o.XI + 4;
+  return o;
+}
 
 struct CdrArgs {
   double *state;
-  const void *X;            // [S][T][4][K]
+  const void *X;            // [S][T][M][K]
   int x_c128;
   const double *Fn;         // [K] diffuse coherence of pair (1,2)
   double *q;                // [S][T][K] workspace: prior speech absence probability
   double *qavg;             // [S][T]    workspace
   double *tp, *txi, *tgamma, *tq, *tcdr;     // taps [S][T][K] or null
-  double2 *tw;              // [S][T][4][K] or null
+  double2 *tw;              // [S][T][M][K] or null
   float2 *Yout;             // [S][T][K] or null
-  int S, K, T, frm_cnt, ell, lo, hi, init_frames, fallback_frames;
+  int S, K, T, frm_cnt, ell, lo, hi, init_frames, fallback_frames, repeat;
   double alpha, alpha_d, alpha_cdr, load_min, load_max, snr_min, snr_max, beta, q_init;
   McraConst mc;
 };
 
-__device__ __forceinline__ void load_y4(const CdrArgs &a, long long base, int K, double (&yr)[4], double (&yi)[4]) {
+template <int M>
+__device__ __forceinline__ void load_y4(const CdrArgs &a, long long base, int K, double (&yr)[M], double (&yi)[M]) {
   if (a.x_c128) {
     const double2 *X = reinterpret_cast<const double2 *>(a.X) + base;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { const double2 v = X[(long long)m * K]; yr[m] = v.x; yi[m] = v.y; }
+    for (int m = 0; m < M; ++m) { const double2 v = X[(long long)m * K]; yr[m] = v.x; yi[m] = v.y; }
   } else {
     const float2 *X = reinterpret_cast<const float2 *>(a.X) + base;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { const float2 v = X[(long long)m * K]; yr[m] = (double)v.x; yi[m] = (double)v.y; }
+    for (int m = 0; m < M; ++m) { const float2 v = X[(long long)m * K]; yr[m] = (double)v.x; yi[m] = (double)v.y; }
   }
 }
 __device__ __forceinline__ double load_pow0(const CdrArgs &a, long long idx) {
@@ -77,43 +88,46 @@ __device__ __forceinline__ double load_pow0(const CdrArgs &a, long long idx) {
 }
 
 // ---- (1) CDR prior ---------------------------------------------------------------------------------
+template <int M>
 __global__ void __launch_bounds__(128) cdr_prior_kernel(CdrArgs a) {
+  typedef CdrLayout<M> LO;
+  constexpr int NQ = LO::NQ;
   const int K = a.K;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)a.S * K) return;
   const int s = (int)(g / K), k = (int)(g % K);
-  double *blob = a.state + (long long)s * CDR_NE * K + k;
-  double pii[4], pr[CDR_NQ], pi[CDR_NQ];
+  double *blob = a.state + (long long)s * LO::NE * K + k;
+  double pii[M], pr[NQ], pi[NQ];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pii[i] = blob[(long long)(CS_PXII + i) * K];
+  for (int i = 0; i < M; ++i) pii[i] = blob[(long long)(LO::PXII + i) * K];
 #pragma unroll
-  for (int e = 0; e < CDR_NQ; ++e) { pr[e] = blob[(long long)(CS_PXIJ_R + e) * K]; pi[e] = blob[(long long)(CS_PXIJ_I + e) * K]; }
-  double mS = blob[(long long)(CS_MCRA + 0) * K], mSmin = blob[(long long)(CS_MCRA + 1) * K], mStmp = blob[(long long)(CS_MCRA + 2) * K],
-         mp = blob[(long long)(CS_MCRA + 3) * K], mlam = blob[(long long)(CS_MCRA + 4) * K];
+  for (int e = 0; e < NQ; ++e) { pr[e] = blob[(long long)(LO::PXIJ_R + e) * K]; pi[e] = blob[(long long)(LO::PXIJ_I + e) * K]; }
+  double mS = blob[(long long)(LO::MCRA + 0) * K], mSmin = blob[(long long)(LO::MCRA + 1) * K], mStmp = blob[(long long)(LO::MCRA + 2) * K],
+         mp = blob[(long long)(LO::MCRA + 3) * K], mlam = blob[(long long)(LO::MCRA + 4) * K];
   const double Fn = a.Fn[k], Fn2 = __dmul_rn(Fn, Fn);
   const double al = a.alpha_cdr, om = __dsub_rn(1.0, al);
   int frm = a.frm_cnt, ell = a.ell % a.mc.L;   // ell is kept modulo L: no integer division per frame (mcra.py:52-56)
   double cdr = 0.0;
   for (int t = 0; t < a.T; ++t) {
-    const long long base = ((long long)s * a.T + t) * 4 * K + k;
-    double yr[4], yi[4];
-    load_y4(a, base, K, yr, yi);
+    const long long base = ((long long)s * a.T + t) * M * K + k;
+    double yr[M], yi[M];
+    load_y4<M>(a, base, K, yr, yi);
     // auto / cross spectra, operation order of the reference (no contraction)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < M; ++i)
       pii[i] = __dadd_rn(__dmul_rn(al, pii[i]), __dmul_rn(om, __dadd_rn(__dmul_rn(yr[i], yr[i]), __dmul_rn(yi[i], yi[i]))));
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < M - 1; ++i)
 #pragma unroll
-      for (int j = i + 1; j < 4; ++j) {
-        const int e = qidx<4>(i, j);
+      for (int j = i + 1; j < M; ++j) {
+        const int e = qidx<M>(i, j);
         const double cr = __dadd_rn(__dmul_rn(yr[i], yr[j]), __dmul_rn(yi[i], yi[j]));      // y_i conj(y_j)
         const double ci = __dsub_rn(__dmul_rn(yi[i], yr[j]), __dmul_rn(yr[i], yi[j]));
         pr[e] = __dadd_rn(__dmul_rn(al, pr[e]), __dmul_rn(om, cr));
         pi[e] = __dadd_rn(__dmul_rn(al, pi[e]), __dmul_rn(om, ci));
       }
     // coherence of pair (1,2): complex / real the way NumPy divides (multiply by 1/d)
-    const int e12 = qidx<4>(1, 2);
+    constexpr int e12 = qidx<M>(1, 2);
     const double scl = 1.0 / sqrt(__dmul_rn(pii[1], pii[2]));
     const double fr = __dmul_rn(pr[e12], scl), fi = __dmul_rn(pi[e12], scl);
     const double fa = hypot(fr, fi);
@@ -131,7 +145,7 @@ __global__ void __launch_bounds__(128) cdr_prior_kernel(CdrArgs a) {
     if (G < 0.0) G = 1e-3;
     cdr = G;
     // MCRA (L = 65) on channel 0
-    const long long i0 = ((long long)s * a.T + t) * 4 * K;
+    const long long i0 = ((long long)s * a.T + t) * M * K;
     const double Y0 = load_pow0(a, i0 + k);
     const double Ym1 = (k > 0) ? load_pow0(a, i0 + k - 1) : 0.0;
     const double Yp1 = (k < K - 1) ? load_pow0(a, i0 + k + 1) : 0.0;
@@ -146,12 +160,12 @@ __global__ void __launch_bounds__(128) cdr_prior_kernel(CdrArgs a) {
     if (a.tcdr) a.tcdr[o] = gam;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) blob[(long long)(CS_PXII + i) * K] = pii[i];
+  for (int i = 0; i < M; ++i) blob[(long long)(LO::PXII + i) * K] = pii[i];
 #pragma unroll
-  for (int e = 0; e < CDR_NQ; ++e) { blob[(long long)(CS_PXIJ_R + e) * K] = pr[e]; blob[(long long)(CS_PXIJ_I + e) * K] = pi[e]; }
-  blob[(long long)(CS_MCRA + 0) * K] = mS; blob[(long long)(CS_MCRA + 1) * K] = mSmin; blob[(long long)(CS_MCRA + 2) * K] = mStmp;
-  blob[(long long)(CS_MCRA + 3) * K] = mp; blob[(long long)(CS_MCRA + 4) * K] = mlam;
-  blob[(long long)CS_CDR * K] = cdr;
+  for (int e = 0; e < NQ; ++e) { blob[(long long)(LO::PXIJ_R + e) * K] = pr[e]; blob[(long long)(LO::PXIJ_I + e) * K] = pi[e]; }
+  blob[(long long)(LO::MCRA + 0) * K] = mS; blob[(long long)(LO::MCRA + 1) * K] = mSmin; blob[(long long)(LO::MCRA + 2) * K] = mStmp;
+  blob[(long long)(LO::MCRA + 3) * K] = mp; blob[(long long)(LO::MCRA + 4) * K] = mlam;
+  blob[(long long)LO::CDR * K] = cdr;
 }
 
 // ---- (2) q_avg = np.mean(q[lo:hi]) with NumPy's pairwise summation order ----------------------------
@@ -186,37 +200,40 @@ __global__ void cdr_qavg_kernel(CdrArgs a) {
 }
 
 // ---- (3) covariance recursions, SPP, PMWF weights -----------------------------------------------------
-__device__ __forceinline__ void herm_load(Herm<4> &h, const double *blob, int off, int K) {
+template <int M> __device__ __forceinline__ void herm_load(Herm<M> &h, const double *blob, int off, int K) {
+  constexpr int NQ = Herm<M>::NQ;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h.d[i] = blob[(long long)(off + i) * K];
+  for (int i = 0; i < M; ++i) h.d[i] = blob[(long long)(off + i) * K];
 #pragma unroll
-  for (int e = 0; e < CDR_NQ; ++e) { h.ur[e] = blob[(long long)(off + 4 + e) * K]; h.ui[e] = blob[(long long)(off + 10 + e) * K]; }
+  for (int e = 0; e < NQ; ++e) { h.ur[e] = blob[(long long)(off + M + e) * K]; h.ui[e] = blob[(long long)(off + M + NQ + e) * K]; }
 }
-__device__ __forceinline__ void herm_store(const Herm<4> &h, double *blob, int off, int K) {
+template <int M> __device__ __forceinline__ void herm_store(const Herm<M> &h, double *blob, int off, int K) {
+  constexpr int NQ = Herm<M>::NQ;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) blob[(long long)(off + i) * K] = h.d[i];
+  for (int i = 0; i < M; ++i) blob[(long long)(off + i) * K] = h.d[i];
 #pragma unroll
-  for (int e = 0; e < CDR_NQ; ++e) { blob[(long long)(off + 4 + e) * K] = h.ur[e]; blob[(long long)(off + 10 + e) * K] = h.ui[e]; }
+  for (int e = 0; e < NQ; ++e) { blob[(long long)(off + M + e) * K] = h.ur[e]; blob[(long long)(off + M + NQ + e) * K] = h.ui[e]; }
 }
 // Re tr(A B) for Hermitian A, B
-__device__ __forceinline__ double herm_trace_prod(const Herm<4> &A, const Herm<4> &B) {
+template <int M> __device__ __forceinline__ double herm_trace_prod(const Herm<M> &A, const Herm<M> &B) {
   double d = 0.0, o = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) d = fma(A.d[i], B.d[i], d);
+  for (int i = 0; i < M; ++i) d = fma(A.d[i], B.d[i], d);
 #pragma unroll
-  for (int e = 0; e < CDR_NQ; ++e) o = fma(A.ur[e], B.ur[e], fma(A.ui[e], B.ui[e], o));
+  for (int e = 0; e < Herm<M>::NQ; ++e) o = fma(A.ur[e], B.ur[e], fma(A.ui[e], B.ui[e], o));
   return fma(2.0, o, d);
 }
 // u = A y
-__device__ __forceinline__ void herm_matvec(const Herm<4> &A, const double (&yr)[4], const double (&yi)[4], double (&ur)[4], double (&ui)[4]) {
+template <int M>
+__device__ __forceinline__ void herm_matvec(const Herm<M> &A, const double (&yr)[M], const double (&yi)[M], double (&ur)[M], double (&ui)[M]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < M; ++i) {
     double sr = A.d[i] * yr[i], si = A.d[i] * yi[i];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < M; ++j) {
       if (j == i) continue;
-      const double ar = (i < j) ? A.ur[qidx<4>(i, j)] : A.ur[qidx<4>(j, i)];
-      const double ai = (i < j) ? A.ui[qidx<4>(i, j)] : -A.ui[qidx<4>(j, i)];
+      const double ar = (i < j) ? A.ur[qidx<M>(i, j)] : A.ur[qidx<M>(j, i)];
+      const double ai = (i < j) ? A.ui[qidx<M>(i, j)] : -A.ui[qidx<M>(j, i)];
       sr = fma(ar, yr[j], fma(-ai, yi[j], sr));
       si = fma(ar, yi[j], fma(ai, yr[j], si));
     }
@@ -224,16 +241,16 @@ __device__ __forceinline__ void herm_matvec(const Herm<4> &A, const double (&yr)
   }
 }
 // Re(u^H B u)
-__device__ __forceinline__ double herm_quad(const Herm<4> &B, const double (&ur)[4], const double (&ui)[4]) {
+template <int M> __device__ __forceinline__ double herm_quad(const Herm<M> &B, const double (&ur)[M], const double (&ui)[M]) {
   double d = 0.0, o = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) d = fma(B.d[i], fma(ur[i], ur[i], ui[i] * ui[i]), d);
+  for (int i = 0; i < M; ++i) d = fma(B.d[i], fma(ur[i], ur[i], ui[i] * ui[i]), d);
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < M - 1; ++i)
 #pragma unroll
-    for (int j = i + 1; j < 4; ++j) {
+    for (int j = i + 1; j < M; ++j) {
       // conj(u_i) B_ij u_j + c.c. = 2 Re(conj(u_i) u_j B_ij)
-      const int e = qidx<4>(i, j);
+      const int e = qidx<M>(i, j);
       const double cr = fma(ur[i], ur[j], ui[i] * ui[j]);      // conj(u_i) u_j
       const double ci = fma(ur[i], ui[j], -ui[i] * ur[j]);
       o = fma(cr, B.ur[e], fma(-ci, B.ui[e], o));
@@ -241,144 +258,198 @@ __device__ __forceinline__ double herm_quad(const Herm<4> &B, const double (&ur)
   return fma(2.0, o, d);
 }
 
+// estimation_core (mcspp.py:199-243): inverse with loading and the xi < 0 fallback, xi, gamma, posterior p
+template <int M>
+__device__ __forceinline__ void cdr_core(const CdrArgs &a, const Herm<M> &Pyy, const Herm<M> &Pvv, Herm<M> &A, double load, int frm,
+                                         const double (&yr)[M], const double (&yi)[M], double q, double &p_prev, double &xi, double &gamma) {
+  A = Pvv;
+#pragma unroll
+  for (int i = 0; i < M; ++i) A.d[i] += load;
+  herm_inverse<M, true>(A);
+  xi = herm_trace_prod<M>(A, Pyy) - (double)M;                                     // :217
+  if (xi < 0.0) {                                                                  // :220-228
+    A = Pyy;
+    if (frm < a.fallback_frames) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) A.d[i] += load;
+    }
+    herm_inverse<M, true>(A);
+    xi = herm_trace_prod<M>(A, Pyy) - (double)M;
+  }
+  xi = (xi != xi) ? xi : fmin(fmax(xi, a.snr_min), a.snr_max);                     // :229 (NaN propagates like np.minimum)
+  double ur[M], ui[M];
+  herm_matvec<M>(A, yr, yi, ur, ui);
+  double yAy = 0.0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) yAy = fma(yr[i], ur[i], fma(yi[i], ui[i], yAy));
+  gamma = herm_quad<M>(Pyy, ur, ui) - yAy;                                         // :231-235
+  gamma = (gamma != gamma) ? gamma : fmin(fmax(gamma, a.snr_min), a.snr_max);
+  // compute_p(alpha_p = 0)                                                        :76-91
+  double p = 1.0 / (1.0 + q / (1.0 - q) * (1.0 + xi) * exp(-1.0 * (gamma / (1.0 + xi))));
+  p = 0.0 * p_prev + p;
+  p = (p != p) ? p : fmin(fmax(p, 0.0), 1.0);
+  p_prev = p;
+}
+
+// M > 4: the four packed matrices no longer fit the register file; the compiler keeps what does not fit in local
+// memory (L1-resident).  M = 4 -- the reference's own case -- compiles without spills.
+template <int M>
 __global__ void __launch_bounds__(64) mcspp_cdr_kernel(CdrArgs a) {
+  typedef CdrLayout<M> LO;
+  constexpr int NQ = LO::NQ;
   const int K = a.K;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)a.S * K) return;
   const int s = (int)(g / K), k = (int)(g % K);
-  double *blob = a.state + (long long)s * CDR_NE * K + k;
-  Herm<4> Pyy, Pvv, A, Pxx;
-  herm_load(Pyy, blob, CS_PYY, K);
-  herm_load(Pvv, blob, CS_PVV, K);
-  double p_prev = blob[(long long)CS_P * K];
+  double *blob = a.state + (long long)s * LO::NE * K + k;
+  Herm<M> Pyy, Pvv, A, Pxx;
+  herm_load<M>(Pyy, blob, LO::PYY, K);
+  herm_load<M>(Pvv, blob, LO::PVV, K);
+  double p_prev = blob[(long long)LO::P * K];
   int frm = a.frm_cnt;
-  double xi = 0.0, gamma = 0.0, q = 0.0, wr[4] = {0, 0, 0, 0}, wi[4] = {0, 0, 0, 0};
+  double xi = 0.0, gamma = 0.0, q = 0.0, wr[M], wi[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) { wr[i] = 0.0; wi[i] = 0.0; }
   const double om_alpha = 1.0 - a.alpha;
   for (int t = 0; t < a.T; ++t, ++frm) {
-    const long long base = ((long long)s * a.T + t) * 4 * K + k;
+    const long long base = ((long long)s * a.T + t) * M * K + k;
     const long long o = ((long long)s * a.T + t) * K + k;
-    double yr[4], yi[4];
-    load_y4(a, base, K, yr, yi);
+    double yr[M], yi[M];
+    load_y4<M>(a, base, K, yr, yi);
     q = a.q[o];
     const double qa = a.qavg[(long long)s * a.T + t];
     const double load = qa * a.load_max + (1.0 - qa) * a.load_min;                 // mcspp.py:269
     // Phi_yy                                                                        :271-273
 #pragma unroll
-    for (int i = 0; i < 4; ++i) Pyy.d[i] = a.alpha * Pyy.d[i] + om_alpha * fma(yr[i], yr[i], yi[i] * yi[i]);
+    for (int i = 0; i < M; ++i) Pyy.d[i] = a.alpha * Pyy.d[i] + om_alpha * fma(yr[i], yr[i], yi[i] * yi[i]);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < M - 1; ++i)
 #pragma unroll
-      for (int j = i + 1; j < 4; ++j) {
-        const int e = qidx<4>(i, j);
+      for (int j = i + 1; j < M; ++j) {
+        const int e = qidx<M>(i, j);
         Pyy.ur[e] = a.alpha * Pyy.ur[e] + om_alpha * fma(yr[i], yr[j], yi[i] * yi[j]);
         Pyy.ui[e] = a.alpha * Pyy.ui[e] + om_alpha * fma(yi[i], yr[j], -yr[i] * yi[j]);
       }
     if (frm < a.init_frames) { Pvv = Pyy; q = a.q_init; }                           // :276-278
-    // estimation_core                                                               :199-243
+    double p = 0.0;
+    for (int pass = 0; pass < 1 + a.repeat; ++pass) {
+      // Phi_xx = Phi_yy - Phi_vv of the matrices estimation_core sees                 :209
 #pragma unroll
-    for (int i = 0; i < 4; ++i) Pxx.d[i] = Pyy.d[i] - Pvv.d[i];
+      for (int i = 0; i < M; ++i) Pxx.d[i] = Pyy.d[i] - Pvv.d[i];
 #pragma unroll
-    for (int e = 0; e < CDR_NQ; ++e) { Pxx.ur[e] = Pyy.ur[e] - Pvv.ur[e]; Pxx.ui[e] = Pyy.ui[e] - Pvv.ui[e]; }
-    A = Pvv;
+      for (int e = 0; e < NQ; ++e) { Pxx.ur[e] = Pyy.ur[e] - Pvv.ur[e]; Pxx.ui[e] = Pyy.ui[e] - Pvv.ui[e]; }
+      cdr_core<M>(a, Pyy, Pvv, A, load, frm, yr, yi, q, p_prev, xi, gamma);
+      if (pass == 0) {
+        p = p_prev;
+        // update_noise_psd(beta = 1) with the first pass's p                           mcspp_base.py:312-319, mcspp.py:281
+        const double at = a.alpha_d + (1.0 - a.alpha_d) * p;
+        const double om_at = 1.0 * (1.0 - at);
+        if (a.repeat) {
+          // repeat = True re-runs estimation_core on the UPDATED Phi_vv (:282-284): update first, then second pass
 #pragma unroll
-    for (int i = 0; i < 4; ++i) A.d[i] += load;
-    herm_inverse<4, true>(A);
-    xi = herm_trace_prod(A, Pyy) - 4.0;                                              // :217
-    if (xi < 0.0) {                                                                  // :220-228
-      A = Pyy;
-      if (frm < a.fallback_frames) {
+          for (int i = 0; i < M; ++i) Pvv.d[i] = at * Pvv.d[i] + om_at * fma(yr[i], yr[i], yi[i] * yi[i]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) A.d[i] += load;
+          for (int i = 0; i < M - 1; ++i)
+#pragma unroll
+            for (int j = i + 1; j < M; ++j) {
+              const int e = qidx<M>(i, j);
+              Pvv.ur[e] = at * Pvv.ur[e] + om_at * fma(yr[i], yr[j], yi[i] * yi[j]);
+              Pvv.ui[e] = at * Pvv.ui[e] + om_at * fma(yi[i], yr[j], -yr[i] * yi[j]);
+            }
+        }
       }
-      herm_inverse<4, true>(A);
-      xi = herm_trace_prod(A, Pyy) - 4.0;
     }
-    xi = (xi != xi) ? xi : fmin(fmax(xi, a.snr_min), a.snr_max);                     // :229 (NaN propagates like np.minimum)
-    double ur[4], ui[4];
-    herm_matvec(A, yr, yi, ur, ui);
-    double yAy = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) yAy = fma(yr[i], ur[i], fma(yi[i], ui[i], yAy));
-    gamma = herm_quad(Pyy, ur, ui) - yAy;                                            // :231-235
-    gamma = (gamma != gamma) ? gamma : fmin(fmax(gamma, a.snr_min), a.snr_max);
-    // compute_p(alpha_p = 0)                                                        :76-91
-    double p = 1.0 / (1.0 + q / (1.0 - q) * (1.0 + xi) * exp(-1.0 * (gamma / (1.0 + xi))));
-    p = 0.0 * p_prev + p;
-    p = (p != p) ? p : fmin(fmax(p, 0.0), 1.0);
-    p_prev = p;
-    // PMWF weights from the matrices estimation_core used (Phi_xx before the noise update)   :286
+    // PMWF weights from the matrices the last estimation_core pass used                :286
     {
-      // column 0 of Phi_xx: (Pxx_00, conj(Pxx_01), conj(Pxx_02), conj(Pxx_03))
-      const double cr[4] = {Pxx.d[0], Pxx.ur[qidx<4>(0, 1)], Pxx.ur[qidx<4>(0, 2)], Pxx.ur[qidx<4>(0, 3)]};
-      const double ci[4] = {0.0, -Pxx.ui[qidx<4>(0, 1)], -Pxx.ui[qidx<4>(0, 2)], -Pxx.ui[qidx<4>(0, 3)]};
-      herm_matvec(A, cr, ci, wr, wi);
+      double cr[M], ci[M];      // column 0 of Phi_xx: (Pxx_00, conj(Pxx_01), conj(Pxx_02), ...)
+      cr[0] = Pxx.d[0]; ci[0] = 0.0;
+#pragma unroll
+      for (int i = 1; i < M; ++i) { cr[i] = Pxx.ur[qidx<M>(0, i)]; ci[i] = -Pxx.ui[qidx<M>(0, i)]; }
+      herm_matvec<M>(A, cr, ci, wr, wi);
       const double sc = 1.0 / (a.beta + xi);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { wr[i] *= sc; wi[i] *= sc; }
+      for (int i = 0; i < M; ++i) { wr[i] *= sc; wi[i] *= sc; }
     }
-    // update_noise_psd(beta = 1)                                                    mcspp_base.py:312-319
-    const double at = a.alpha_d + (1.0 - a.alpha_d) * p;
-    const double om_at = 1.0 * (1.0 - at);
+    if (!a.repeat) {
+      // update_noise_psd(beta = 1)                                                    mcspp_base.py:312-319
+      const double at = a.alpha_d + (1.0 - a.alpha_d) * p;
+      const double om_at = 1.0 * (1.0 - at);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) Pvv.d[i] = at * Pvv.d[i] + om_at * fma(yr[i], yr[i], yi[i] * yi[i]);
+      for (int i = 0; i < M; ++i) Pvv.d[i] = at * Pvv.d[i] + om_at * fma(yr[i], yr[i], yi[i] * yi[i]);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < M - 1; ++i)
 #pragma unroll
-      for (int j = i + 1; j < 4; ++j) {
-        const int e = qidx<4>(i, j);
-        Pvv.ur[e] = at * Pvv.ur[e] + om_at * fma(yr[i], yr[j], yi[i] * yi[j]);
-        Pvv.ui[e] = at * Pvv.ui[e] + om_at * fma(yi[i], yr[j], -yr[i] * yi[j]);
-      }
-    if (a.tp) a.tp[o] = p;
+        for (int j = i + 1; j < M; ++j) {
+          const int e = qidx<M>(i, j);
+          Pvv.ur[e] = at * Pvv.ur[e] + om_at * fma(yr[i], yr[j], yi[i] * yi[j]);
+          Pvv.ui[e] = at * Pvv.ui[e] + om_at * fma(yi[i], yr[j], -yr[i] * yi[j]);
+        }
+    }
+    if (a.tp) a.tp[o] = p_prev;
     if (a.txi) a.txi[o] = xi;
     if (a.tgamma) a.tgamma[o] = gamma;
     if (a.tq) a.tq[o] = q;
     if (a.tw) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a.tw[base + (long long)i * K] = make_double2(wr[i], wi[i]);
+      for (int i = 0; i < M; ++i) a.tw[base + (long long)i * K] = make_double2(wr[i], wi[i]);
     }
     if (a.Yout) {                               // Y = w^H y
       double Yr = 0.0, Yi = 0.0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < M; ++i) {
         Yr = fma(wr[i], yr[i], fma(wi[i], yi[i], Yr));
         Yi = fma(wr[i], yi[i], fma(-wi[i], yr[i], Yi));
       }
       a.Yout[o] = make_float2((float)Yr, (float)Yi);
     }
   }
-  herm_store(Pyy, blob, CS_PYY, K);
-  herm_store(Pvv, blob, CS_PVV, K);
-  herm_store(A, blob, CS_AINV, K);
-  herm_store(Pxx, blob, CS_PXX, K);
-  blob[(long long)CS_P * K] = p_prev;
+  herm_store<M>(Pyy, blob, LO::PYY, K);
+  herm_store<M>(Pvv, blob, LO::PVV, K);
+  herm_store<M>(A, blob, LO::AINV, K);
+  herm_store<M>(Pxx, blob, LO::PXX, K);
+  blob[(long long)LO::P * K] = p_prev;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { blob[(long long)(CS_W_R + i) * K] = wr[i]; blob[(long long)(CS_W_I + i) * K] = wi[i]; }
-  blob[(long long)CS_XI * K] = xi; blob[(long long)CS_GAMMA * K] = gamma; blob[(long long)CS_Q * K] = q;
+  for (int i = 0; i < M; ++i) { blob[(long long)(LO::W_R + i) * K] = wr[i]; blob[(long long)(LO::W_I + i) * K] = wi[i]; }
+  blob[(long long)LO::XI * K] = xi; blob[(long long)LO::GAMMA * K] = gamma; blob[(long long)LO::Q * K] = q;
 }
 
 // ---- export ---------------------------------------------------------------------------------------------
-__global__ void cdr_export_herm_kernel(const double *state, int off, int S, int K, double2 *out) {
+__global__ void cdr_export_herm_kernel(const double *state, int off, int S, int K, int M, int NE, double2 *out) {
+  const int MM = M * M, NQ = M * (M - 1) / 2;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (long long)S * K * 16) return;
-  const int ij = (int)(g % 16), k = (int)((g / 16) % K), s = (int)(g / (16LL * K));
-  const int i = ij / 4, j = ij % 4;
-  const double *b = state + (long long)s * CDR_NE * K + k;
+  if (g >= (long long)S * K * MM) return;
+  const int ij = (int)(g % MM), k = (int)((g / MM) % K), s = (int)(g / ((long long)MM * K));
+  const int i = ij / M, j = ij % M;
+  const double *b = state + (long long)s * NE * K + k;
   double re, im = 0.0;
   if (i == j) re = b[(long long)(off + i) * K];
   else {
-    const int lo = min(i, j), hi = max(i, j), e = lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo - 1);
-    re = b[(long long)(off + 4 + e) * K];
-    im = b[(long long)(off + 10 + e) * K];
+    const int lo = min(i, j), hi = max(i, j), e = lo * (M - 1) - (lo * (lo - 1)) / 2 + (hi - lo - 1);
+    re = b[(long long)(off + M + e) * K];
+    im = b[(long long)(off + M + NQ + e) * K];
     if (i > j) im = -im;
   }
   out[g] = make_double2(re, im);
 }
-__global__ void cdr_export_rows_kernel(const double *state, int off, int n, int S, int K, double *out) {   // -> [S][n][K]
+__global__ void cdr_export_rows_kernel(const double *state, int off, int n, int S, int K, int NE, double *out) {   // -> [S][n][K]
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)S * n * K) return;
   const int k = (int)(g % K), e = (int)((g / K) % n), s = (int)(g / ((long long)n * K));
-  out[g] = state[((long long)s * CDR_NE + off + e) * K + k];
+  out[g] = state[((long long)s * NE + off + e) * K + k];
+}
+
+template <int M>
+static int launch_cdr(const CdrArgs &a, int cdr_only, cudaStream_t st) {
+  const long long items = (long long)a.S * a.K;
+  cdr_prior_kernel<M><<<(unsigned)((items + 127) / 128), 128, 0, st>>>(a);
+  DS_LAUNCH_CHECK();
+  if (cdr_only) return DS_OK;
+  const long long frames = (long long)a.S * a.T;
+  cdr_qavg_kernel<<<(unsigned)((frames + 127) / 128), 128, 0, st>>>(a);
+  DS_LAUNCH_CHECK();
+  mcspp_cdr_kernel<M><<<(unsigned)((items + 63) / 64), 64, 0, st>>>(a);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
 }
 
 }  // namespace ds
@@ -399,7 +470,8 @@ void ds_mcspp_cdr_default_params(ds_mcspp_cdr_params *p, int n_fft, int n_stream
 }
 
 size_t ds_mcspp_cdr_state_bytes(const ds_mcspp_cdr_params *p) {
-  return p ? (size_t)p->n_streams * CDR_NE * (p->n_fft / 2 + 1) * sizeof(double) : 0;
+  if (!p || p->n_mics < 4 || p->n_mics > 8) return 0;
+  return (size_t)p->n_streams * cdr_offsets(p->n_mics).NE * (p->n_fft / 2 + 1) * sizeof(double);
 }
 size_t ds_mcspp_cdr_workspace_bytes(const ds_mcspp_cdr_params *p) {
   if (!p) return 0;
@@ -410,8 +482,8 @@ size_t ds_mcspp_cdr_workspace_bytes(const ds_mcspp_cdr_params *p) {
 int ds_mcspp_cdr_run(const ds_mcspp_cdr_params *p, void *state, void *workspace, const double *Fn, const void *X, int x_is_c128,
                      void *Yout, const ds_mcspp_cdr_taps *taps, void *stream) {
   DS_CHECK_ARG(p && state && workspace && Fn && X, "ds_mcspp_cdr_run: null argument");
-  if (p->n_mics != 4) {
-    set_error("ds_mcspp_cdr_run: n_mics must be 4 (the reference builds McCDR with 4 channels, mcspp.py:54, and crashes above)");
+  if (p->n_mics < 4 || p->n_mics > 8) {
+    set_error("ds_mcspp_cdr_run: n_mics must be 4..8 (pair (1, 2) of the CDR prior is undefined below 4 in the reference)");
     return DS_EUNSUPPORTED;
   }
   DS_CHECK_ARG(p->n_streams >= 1 && p->n_frames >= 1 && p->n_fft >= 64 && p->mcra_L >= 1, "ds_mcspp_cdr_run: bad shape");
@@ -425,43 +497,45 @@ int ds_mcspp_cdr_run(const ds_mcspp_cdr_params *p, void *state, void *workspace,
   a.Yout = (float2 *)Yout;
   a.S = p->n_streams; a.K = K; a.T = p->n_frames; a.frm_cnt = p->frm_cnt; a.ell = p->ell; a.lo = p->band_lo_bin; a.hi = p->band_hi_bin;
   a.init_frames = p->init_frames; a.fallback_frames = p->fallback_loaded_frames;
+  a.repeat = (p->cdr_only & 2) ? 1 : 0;          // bit 1 of cdr_only: McSpp.estimation(repeat=True), mcspp.py:282-284
   a.alpha = p->alpha; a.alpha_d = p->alpha_d; a.alpha_cdr = p->alpha_cdr; a.load_min = p->load_min; a.load_max = p->load_max;
   a.snr_min = p->snr_min; a.snr_max = p->snr_max; a.beta = p->pmwf_beta; a.q_init = p->q_init;
   a.mc.alpha_d = p->mcra_alpha_d; a.mc.alpha_s = p->mcra_alpha_s; a.mc.delta_s = p->mcra_delta_s;
   a.mc.alpha_p = p->mcra_alpha_p; a.mc.p_min = p->mcra_p_min; a.mc.p_max = p->mcra_p_max; a.mc.L = p->mcra_L;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long items = (long long)a.S * K;
-  cdr_prior_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(a);
-  DS_LAUNCH_CHECK();
-  if (p->cdr_only) return DS_OK;
-  const long long frames = (long long)a.S * a.T;
-  cdr_qavg_kernel<<<(unsigned)((frames + 127) / 128), 128, 0, st>>>(a);
-  DS_LAUNCH_CHECK();
-  mcspp_cdr_kernel<<<(unsigned)((items + 63) / 64), 64, 0, st>>>(a);
-  DS_LAUNCH_CHECK();
-  return DS_OK;
+  const int cdr_only = p->cdr_only & 1;
+  switch (p->n_mics) {
+    case 4: return launch_cdr<4>(a, cdr_only, st);
+    case 5: return launch_cdr<5>(a, cdr_only, st);
+    case 6: return launch_cdr<6>(a, cdr_only, st);
+    case 7: return launch_cdr<7>(a, cdr_only, st);
+    case 8: return launch_cdr<8>(a, cdr_only, st);
+  }
+  return DS_EUNSUPPORTED;
 }
 
 int ds_mcspp_cdr_export(const ds_mcspp_cdr_params *p, const void *state, int field, void *out, void *stream) {
   DS_CHECK_ARG(p && state && out, "ds_mcspp_cdr_export: null argument");
-  const int K = p->n_fft / 2 + 1, S = p->n_streams;
+  DS_CHECK_ARG(p->n_mics >= 4 && p->n_mics <= 8, "ds_mcspp_cdr_export: n_mics must be 4..8");
+  const int K = p->n_fft / 2 + 1, S = p->n_streams, M = p->n_mics;
+  const CdrOffsets lo = cdr_offsets(M);
   cudaStream_t st = (cudaStream_t)stream;
   const double *sd = (const double *)state;
   if (field >= 0 && field <= 3) {
-    const int off = field == 0 ? CS_PYY : field == 1 ? CS_PVV : field == 2 ? CS_AINV : CS_PXX;
-    const long long n = (long long)S * K * 16;
-    cdr_export_herm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sd, off, S, K, (double2 *)out);
+    const int off = field == 0 ? lo.PYY : field == 1 ? lo.PVV : field == 2 ? lo.AINV : lo.PXX;
+    const long long n = (long long)S * K * M * M;
+    cdr_export_herm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sd, off, S, K, M, lo.NE, (double2 *)out);
   } else {
     int off, cnt;
     switch (field) {
-      case 4: off = CS_W_R; cnt = 8; break;       // [S][8][K]: re[4], im[4]
-      case 5: off = CS_XI; cnt = 4; break;        // xi gamma q cdr
-      case 6: off = CS_PXII; cnt = 16; break;     // Pxii[4] Pxij_re[6] Pxij_im[6]
-      case 7: off = CS_MCRA; cnt = 6; break;      // S Smin Stmp p lambda | p (posterior)
+      case 4: off = lo.W_R; cnt = 2 * M; break;            // [S][2M][K]: re[M], im[M]
+      case 5: off = lo.XI; cnt = 4; break;                 // xi gamma q cdr
+      case 6: off = lo.PXII; cnt = M + 2 * lo.NQ; break;   // Pxii[M] Pxij_re[NQ] Pxij_im[NQ]
+      case 7: off = lo.MCRA; cnt = 6; break;               // S Smin Stmp p lambda | p (posterior)
       default: set_error("ds_mcspp_cdr_export: unknown field %d", field); return DS_EINVAL;
     }
     const long long n = (long long)S * cnt * K;
-    cdr_export_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sd, off, cnt, S, K, (double *)out);
+    cdr_export_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sd, off, cnt, S, K, lo.NE, (double *)out);
   }
   DS_LAUNCH_CHECK();
   return DS_OK;

@@ -6,10 +6,15 @@ Phi_yy recursion; complex 4x4 inverse of herm(Phi_vv) + loading I with the refer
 where xi < 0; xi, gamma, posterior p; noise-covariance update; PMWF weights with beta = 10.
 Everything runs in CUDA (``ds_mcspp_cdr_run``); the float64 state lives on the device.
 
-The reference only works with 4 channels: ``McSpp.__init__`` builds ``McCDR(nfft)`` with its default
-``channels=4`` (mcspp.py:54) whose PSD tracker then raises IndexError for more microphones, and the CDR
-uses the microphone pair (1, 2), which is undefined below 4.  Other channel counts raise ValueError here.
-Extensions: a leading stream axis and ``estimation_frames`` (many frames per launch).
+As shipped the reference only works with 4 channels: ``McSpp.__init__`` builds ``McCDR(nfft)`` with its default
+``channels=4`` (mcspp.py:54) whose PSD tracker then raises IndexError for more microphones.  Here 4 ... 8 channels
+run ("lift the M <= 4 limit"): above 4 the behaviour is the reference's with ``McCDR(nfft,
+channels=M)`` handed in (the pin: oracle/ref_harness.make_mcspp, tests/golden/mcspp_cdr_m68.npz).  With 7 or 8
+channels the patched reference still raises LinAlgError in frames 5 .. M-2 (the xi < 0 fallback inverse of
+mcspp.py:224-227 drops its loading after 5 frames, when Phi_yy is still rank deficient); here the loading is kept until
+Phi_yy has full rank (``fallback_loaded_frames = max(5, M - 1)``: the reference's behaviour for M <= 6).  Fewer than 4
+channels raise ValueError (the CDR's microphone pair (1, 2) is read at the 4-channel pair index and is 0/0 below).
+Extensions: a leading stream axis, ``estimation_frames`` (many frames per launch), ``repeat=True`` on the device.
 """
 import ctypes as C
 
@@ -49,14 +54,14 @@ class _CdrCore(object):
     """Device state + launches shared by McSpp and McCDR."""
 
     def __init__(self, nfft, channels):
-        if channels != 4:
-            raise ValueError("McSpp / McCDR need exactly 4 channels: the reference builds McCDR with channels=4 "
-                             "(mcspp.py:54) and fails above; pair (1, 2) of the CDR is undefined below")
+        if not 4 <= channels <= 8:
+            raise ValueError("McSpp / McCDR run with 4..8 channels: pair (1, 2) of the CDR is undefined below 4 in the "
+                             "reference (mcspp.py:54 builds McCDR with channels=4); the kernels are compiled up to 8")
         self.nfft, self.channels = int(nfft), int(channels)
         self.half_bin = int(self.nfft / 2 + 1)
         self.alpha = self.alpha_d = 0.92
         self.mcra = _CdrMcra(self)
-        self.MicArray = MicArray(arrayType="circular", r=0.032, M=4)              # mccdr.py:58
+        self.MicArray = MicArray(arrayType="circular", r=0.032, M=self.channels)  # mccdr.py:58 (channels = 4 as shipped)
         self.Fvv = gen_noise_msc(mic=self.MicArray, nfft=self.nfft)                # diffuse model of that array
         self._Fn_dev = None
         self._state = None
@@ -69,6 +74,7 @@ class _CdrCore(object):
         m = self.mcra
         p.frm_cnt, p.ell, p.mcra_L, p.cdr_only = int(m.frm_cnt), int(m.ell), int(m.L), int(cdr_only)
         p.alpha, p.alpha_d = float(self.alpha), float(self.alpha_d)
+        p.fallback_loaded_frames = max(5, self.channels - 1)
         p.mcra_alpha_d, p.mcra_alpha_s, p.mcra_delta_s = float(m.alpha_d), float(m.alpha_s), float(m.delta_s)
         p.mcra_alpha_p, p.mcra_p_min, p.mcra_p_max = float(m.alpha_p), float(m.p_min), float(m.p_max)
         return p
@@ -83,17 +89,16 @@ class _CdrCore(object):
         if self._Fn_dev is None:
             self._Fn_dev = t.as_tensor(np.ascontiguousarray(self.Fvv[:, 1, 2], dtype=np.float64)).to("cuda")
 
-    _EXPORT_ROWS = {4: 8, 5: 4, 6: 16, 7: 6}
-
     def _export(self, field):
         if self._state is None:
             return None
         t = L.require_cuda()
-        S, K = self._S, self.half_bin
+        S, K, M = self._S, self.half_bin, self.channels
         if field <= 3:
-            out = t.empty((S, K, 4, 4), dtype=t.complex128, device="cuda")
+            out = t.empty((S, K, M, M), dtype=t.complex128, device="cuda")
         else:
-            out = t.empty((S, self._EXPORT_ROWS[field], K), dtype=t.float64, device="cuda")
+            rows = {4: 2 * M, 5: 4, 6: M + M * (M - 1), 7: 6}[field]
+            out = t.empty((S, rows, K), dtype=t.float64, device="cuda")
         L.check(L.lib().ds_mcspp_cdr_export(C.byref(self._params(S, 1)), L.ptr(self._state), field, L.ptr(out),
                                             L.stream_ptr()), "ds_mcspp_cdr_export")
         return out.cpu().numpy()
@@ -110,13 +115,13 @@ class _CdrCore(object):
             yd = yd[None]
         return yd.permute(0, 2, 1)[:, None, :, :].contiguous()
 
-    def _run(self, Xd, cdr_only=False, want_Y=False, want_w=True):
+    def _run(self, Xd, cdr_only=False, want_Y=False, want_w=True, repeat=False):
         t = L.require_cuda()
         S, T, M, K = Xd.shape
         if M != self.channels or K != self.half_bin:
             raise ValueError("expected [.., %d bins, %d channels]" % (self.half_bin, self.channels))
         self._ensure(S)
-        prm = self._params(S, T, cdr_only=int(cdr_only))
+        prm = self._params(S, T, cdr_only=int(bool(cdr_only)) | (2 if repeat else 0))
         ws = t.empty(L.lib().ds_mcspp_cdr_workspace_bytes(C.byref(prm)), dtype=t.uint8, device="cuda")
         f64 = dict(dtype=t.float64, device="cuda")
         out = {"cdr": t.empty((S, T, K), **f64)}
@@ -183,24 +188,23 @@ class McSpp(_CdrCore):
             self.w = _sq(out["w"][:, -1].permute(0, 2, 1).cpu().numpy())            # [K, M]
 
     def estimation(self, y, diag_value=1e-4, repeat=False):
-        """One frame: y [K, 4] complex (or [S, K, 4]) -> posterior SPP p [K]  (mcspp.py:248-305).
-        ``diag_value`` is ignored like in the reference (overwritten at :269)."""
-        if repeat:
-            raise NotImplementedError("repeat=True (second estimation_core pass, mcspp.py:282-284) is not built")
-        out = self._run(self._to_stmk(y))
+        """One frame: y [K, M] complex (or [S, K, M]) -> posterior SPP p [K]  (mcspp.py:248-305).
+        ``diag_value`` is ignored like in the reference (overwritten at :269); ``repeat=True`` runs estimation_core a
+        second time on the updated noise covariance (:282-284)."""
+        out = self._run(self._to_stmk(y), repeat=repeat)
         self._publish(out)
         return self.p
 
-    def estimation_frames(self, D, want_Y=False):
-        """Extension: D [K, T, 4] (or [S, K, T, 4]) complex -> dict of per-frame arrays p, xi, gamma, q, cdr
-        [K, T], w [K, T, 4] and (want_Y) the PMWF output spectrum Y = w^H y [K, T]."""
+    def estimation_frames(self, D, want_Y=False, repeat=False):
+        """Extension: D [K, T, M] (or [S, K, T, M]) complex -> dict of per-frame arrays p, xi, gamma, q, cdr
+        [K, T], w [K, T, M] and (want_Y) the PMWF output spectrum Y = w^H y [K, T]."""
         t = L.require_cuda()
         Dd = D.to("cuda") if isinstance(D, t.Tensor) else t.as_tensor(
             np.ascontiguousarray(np.asarray(D, dtype=np.complex128))).to("cuda")
         batched = Dd.dim() == 4
         if not batched:
             Dd = Dd[None]
-        out = self._run(Dd.permute(0, 2, 3, 1).contiguous(), want_Y=want_Y)
+        out = self._run(Dd.permute(0, 2, 3, 1).contiguous(), want_Y=want_Y, repeat=repeat)
         self._publish(out)
         res = {k: out[k].permute(0, 2, 1) for k in ("p", "xi", "gamma", "q", "cdr")}
         res["w"] = out["w"].permute(0, 3, 1, 2)

@@ -260,13 +260,16 @@ int ds_mcspp_export(const ds_mcspp_params *p, const void *state, int field, void
 typedef struct ds_mcspp_cdr_params {
   int32_t n_fft;
   int32_t n_streams;
-  int32_t n_mics;   /* must be 4: McSpp builds McCDR with its default 4 channels
-                       (mcspp.py:54) and the reference raises IndexError above that  */
+  int32_t n_mics;   /* 4..8.  4 is what the reference runs as shipped (McSpp builds McCDR
+                       with its default 4 channels, mcspp.py:54, and raises IndexError
+                       above); 5..8 follow the reference with McCDR(nfft, channels=M)  */
   int32_t n_frames;
   int32_t frm_cnt;  /* frames already processed (host-tracked; McSpp.frm_cnt)        */
   int32_t ell;      /* window counter of McCDR's MCRA at entry                       */
   int32_t mcra_L;   /* 65                                              mccdr.py:56   */
-  int32_t cdr_only; /* 1: only McCDR.estimation (taps->cdr), state of the prior only */
+  int32_t cdr_only; /* bit 0: only McCDR.estimation (taps->cdr), state of the prior only;
+                       bit 1: McSpp.estimation(repeat=True): second estimation_core pass
+                       on the updated noise covariance (mcspp.py:282-284)             */
   int32_t band_lo_bin, band_hi_bin; /* int(500 nfft/16000), int(2000 nfft/16000) :266-267 */
   int32_t init_frames;              /* 10: Phi_vv = Phi_yy, q = q_init     :276-278  */
   int32_t fallback_loaded_frames;   /* 5: loaded fallback inverse          :224-227  */
@@ -288,20 +291,21 @@ typedef struct ds_mcspp_cdr_taps { /* optional per-frame outputs, any may be NUL
   double *gamma; /* [S][T][K]                                                      */
   double *q;     /* [S][T][K] prior speech absence probability used by compute_p   */
   double *cdr;   /* [S][T][K] McCDR.estimation return value sqrt(CDR^2 p_mcra)     */
-  void *w;       /* [S][T][4][K] c128 PMWF weights (beta = pmwf_beta)              */
+  void *w;       /* [S][T][M][K] c128 PMWF weights (beta = pmwf_beta)              */
 } ds_mcspp_cdr_taps;
 
 /* replaces, per frame, McSpp.estimation (mcspp.py:248-305) including McCDR.estimation
  * (mccdr.py:164-177) and compute_pmwf_weight (mcspp_base.py:220-240).
- *   Fn   [K] float64: diffuse coherence Fvv[:, 1, 2] of the 4-mic circular r = 0.032 array
+ *   Fn   [K] float64: diffuse coherence Fvv[:, 1, 2] of the M-mic circular r = 0.032 array
  *        McCDR owns (mccdr.py:58-59, gen_noise_msc.py)
- *   X    [S][T][4][K] c64 (x_is_c128 = 0) or c128
+ *   X    [S][T][M][K] c64 (x_is_c128 = 0) or c128
  *   Yout [S][T][K] c64 = w^H y (or NULL)                                            */
 int ds_mcspp_cdr_run(const ds_mcspp_cdr_params *p, void *state, void *workspace, const double *Fn,
                      const void *X, int x_is_c128, void *Yout, const ds_mcspp_cdr_taps *taps, void *stream);
-/* state views. field: 0 Phi_yy, 1 Phi_vv, 2 Phi_vv_inv, 3 Phi_xx (c128 [S][K][4][4]; 2-3 as of the
- * last frame); 4 w [S][8][K] (re[4], im[4]); 5 [S][4][K] xi gamma q cdr^2; 6 [S][16][K] Pxii[4]
- * Re Pxij[6] Im Pxij[6]; 7 [S][6][K] MCRA S Smin Stmp p lambda_d, posterior p      */
+/* state views. field: 0 Phi_yy, 1 Phi_vv, 2 Phi_vv_inv, 3 Phi_xx (c128 [S][K][M][M]; 2-3 as of the
+ * last frame); 4 w [S][2M][K] (re[M], im[M]); 5 [S][4][K] xi gamma q cdr^2; 6 [S][M + M(M-1)][K]
+ * Pxii[M] Re Pxij[NQ] Im Pxij[NQ] (NQ = M(M-1)/2 pairs, i < j row-major); 7 [S][6][K] MCRA S Smin Stmp p
+ * lambda_d, posterior p                                                             */
 int ds_mcspp_cdr_export(const ds_mcspp_cdr_params *p, const void *state, int field, void *out, void *stream);
 
 /* ---- McMcra + frequency-domain GSC (noise_estimation/mc_mcra.py, beamformer/GSC.py) -------- */

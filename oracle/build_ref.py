@@ -1,8 +1,9 @@
 """TEST / BASELINE INFRASTRUCTURE ONLY -- build recipe for ``oracle/_ref``.
 
 The reference is pure Python; its "build" is byte-compilation.  This recipe compiles the reference package from the
-sources WHERE THEY LIE under ``/root/reference`` (nothing is copied) and writes only the outputs -- sourceless ``.pyc``
-modules -- into ``oracle/_ref/DistantSpeech/...``.  ``oracle/_ref/`` is git-ignored (it never enters the history) but
+sources WHERE THEY LIE under ``/root/reference`` (nothing is copied) and writes only the outputs -- byte-compiled
+modules, stored as ``module.refc`` (a ``.pyc`` under another suffix: the gpurun snapshot drops ``*.pyc``) -- into
+``oracle/_ref/DistantSpeech/...``; ``oracle/ref_harness.py`` installs a small import hook that loads them.  ``oracle/_ref/`` is git-ignored (it never enters the history) but
 not gpurun-ignored, so the compiled reference travels to the GPU box like the repo's own ``.so`` and can be
 
   * timed there as the CPU baseline of ``bench.py`` (``cpu_baseline.kind = "reference"``), and
@@ -26,7 +27,7 @@ PACKAGE = "DistantSpeech"
 
 def available() -> bool:
     """True when a compiled reference is present (marker written by build())."""
-    return os.path.exists(os.path.join(OUT_ROOT, PACKAGE, "transform", "transform.pyc"))
+    return os.path.exists(os.path.join(OUT_ROOT, PACKAGE, "transform", "transform.refc"))
 
 
 def build(verbose: bool = False) -> int:
@@ -34,8 +35,10 @@ def build(verbose: bool = False) -> int:
     src_pkg = os.path.join(SRC_ROOT, PACKAGE)
     if not os.path.isdir(src_pkg):
         raise RuntimeError("reference sources not present at %s" % src_pkg)
+    import shutil
     import warnings
     warnings.filterwarnings("ignore", category=SyntaxWarning)          # the reference's own docstring escapes
+    shutil.rmtree(os.path.join(OUT_ROOT, PACKAGE), ignore_errors=True)
     n = 0
     for dirpath, dirnames, filenames in os.walk(src_pkg):
         dirnames[:] = [d for d in dirnames if d != "__pycache__"]
@@ -44,7 +47,7 @@ def build(verbose: bool = False) -> int:
             if not f.endswith(".py"):
                 continue
             src = os.path.join(dirpath, f)
-            dst = os.path.join(OUT_ROOT, rel, f + "c")                 # module.pyc next to where module.py would be
+            dst = os.path.join(OUT_ROOT, rel, f[:-3] + ".refc")        # byte code next to where module.py would be
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             try:
                 # dfile: the path recorded in tracebacks / co_filename -- the reference's own location, for citations

@@ -44,9 +44,15 @@ def make_input(config, stream, seconds):
 
 
 def reference_importable():
+    """True when the reference's classes really import here (source tree or the byte-compiled copy)."""
     try:
         from oracle import ref_harness as H
-        return H.reference_available()
+        if not H.reference_available():
+            return False
+        H.install()
+        from DistantSpeech.noise_estimation.mcspp_base import McSppBase  # noqa: F401
+        from DistantSpeech.transform.transform import Transform  # noqa: F401
+        return True
     except Exception:
         return False
 

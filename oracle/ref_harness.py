@@ -53,13 +53,50 @@ REFERENCE_ROOT = _pick_root()
 _installed = False
 
 
-def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "DistantSpeech"))
-
-
 def reference_kind() -> str:
-    """'source' (the tree under /root/reference) or 'compiled' (sourceless .pyc under oracle/_ref)."""
-    return "source" if os.path.exists(os.path.join(REFERENCE_ROOT, "DistantSpeech", "transform", "transform.py")) else "compiled"
+    """'source' (the tree under /root/reference), 'compiled' (byte code under oracle/_ref) or 'absent'."""
+    base = os.path.join(REFERENCE_ROOT, "DistantSpeech", "transform", "transform")
+    return "source" if os.path.exists(base + ".py") else ("compiled" if os.path.exists(base + ".refc") else "absent")
+
+
+def reference_available() -> bool:
+    return reference_kind() != "absent"
+
+
+class _CompiledFinder(object):
+    """Import hook for the byte-compiled reference: ``DistantSpeech.x.y`` -> ``<root>/DistantSpeech/x/y.refc`` (a .pyc
+    file under another suffix), packages = directories (the reference has no __init__ files except noise_estimation's)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if fullname != "DistantSpeech" and not fullname.startswith("DistantSpeech."):
+            return None
+        rel = os.path.join(self.root, *fullname.split("."))
+        if os.path.isdir(rel):
+            init = os.path.join(rel, "__init__.refc")
+            spec = importlib.machinery.ModuleSpec(fullname, self, origin=init if os.path.exists(init) else None, is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        if os.path.exists(rel + ".refc"):
+            return importlib.machinery.ModuleSpec(fullname, self, origin=rel + ".refc")
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+        origin = module.__spec__.origin
+        if origin is None:
+            return                                   # plain directory package
+        with open(origin, "rb") as fh:
+            data = fh.read()
+        module.__file__ = origin
+        exec(marshal.loads(data[16:]), module.__dict__)      # 16-byte pyc header (PEP 552), then the code object
 
 
 def _make_librosa_stub():
@@ -150,8 +187,11 @@ def install():
         sys.modules["librosa.filters"] = filters
         sys.modules["librosa.display"] = librosa.display
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if reference_kind() == "source":
+        if REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, REFERENCE_ROOT)
+    elif not any(isinstance(f, _CompiledFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _CompiledFinder(REFERENCE_ROOT))
 
     if reference_kind() == "compiled":
         # sourceless modules: numba cannot key an on-disk cache on a source file that is not there
@@ -185,6 +225,24 @@ def make_adaptive_mvdr(mic, frameLen, hop, nfft):
     obj = adaptivebeamfomer(mic, frameLen=frameLen, hop=hop, nfft=nfft)
     orig = obj.transformer.istft
     obj.transformer.istft = lambda Y: orig(Y[..., None] if Y.ndim == 2 else Y)
+    return obj
+
+
+def make_mcspp(nfft=512, channels=4):
+    """Construct the reference ``McSpp``.  For more than 4 channels patch (v) applies: ``McSpp.__init__`` builds its
+    prior as ``McCDR(nfft=self.nfft)`` with McCDR's default ``channels=4`` (mcspp.py:54), whose PSD tracker is then
+    indexed up to the real channel count and raises IndexError (coherence/BinauralEnhancement.py:21,48-51).  The
+    missing argument is supplied from the outside: ``obj.mccdr = McCDR(nfft, channels=channels)``.  Nothing else is
+    touched; with 4 channels the object is exactly what the reference builds."""
+    install()
+    import contextlib
+    import io
+    from DistantSpeech.noise_estimation.mcspp import McSpp
+    from DistantSpeech.noise_estimation.mccdr import McCDR
+    with contextlib.redirect_stdout(io.StringIO()):
+        obj = McSpp(nfft=nfft, channels=channels)
+        if channels != 4:
+            obj.mccdr = McCDR(nfft=nfft, channels=channels)
     return obj
 
 

@@ -151,3 +151,47 @@ def test_chain_pcm16_in_and_out(cuda):
         ch.process_device_profiled(torch.from_numpy(xf[:, :, :100]).cuda())     # profiled entry validates its input
     with pytest.raises(ValueError):
         ch.process_device(torch.from_numpy(xf).cuda().double())
+
+
+# ---------------------------------------------------------------- f3: McSpp beyond 4 microphones, repeat=True
+@pytest.mark.parametrize("tag,M,rep", [("m6", 6, False), ("m5", 5, False), ("m4r", 4, True)])
+def test_mcspp_more_than_4_mics_golden_gpu(cuda, tag, M, rep):
+    """McSpp with 5 / 6 microphones against the reference run with McCDR(nfft, channels=M) handed in
+    (oracle/ref_harness.make_mcspp; mcspp.py:54 hard-wires 4), and estimation(repeat=True) (mcspp.py:282-284)."""
+    from distantspeech_b200.noise_estimation.mcspp import McSpp
+    g = golden("mcspp_cdr_m68.npz")
+    D = O.Transform(channel=M, n_fft=256, hop_length=128).stft(g[tag + "_x"].astype(np.float64))     # the reference's spectrum
+    est = McSpp(nfft=256, channels=M)
+    res = est.estimation_frames(D, repeat=rep)
+    for k in ("p", "xi", "gamma", "q"):
+        assert np.allclose(res[k], g[tag + "_" + k], rtol=1e-7, atol=1e-11), (tag, k, np.max(np.abs(res[k] - g[tag + "_" + k])))
+    scale = lambda a: np.max(np.abs(a))                                                           # noqa: E731
+    for nm, a in (("w_last", est.w), ("Phi_vv_last", est.Phi_vv), ("Phi_vv_inv_last", est.Phi_vv_inv)):
+        assert a.shape == g[tag + "_" + nm].shape
+        assert np.max(np.abs(a - g[tag + "_" + nm])) <= 1e-8 * scale(g[tag + "_" + nm]), (tag, nm)
+    # frame by frame == many frames per launch
+    e2 = McSpp(nfft=256, channels=M)
+    for n in range(12):
+        p = e2.estimation(D[:, n, :], repeat=rep)
+    assert np.array_equal(p, res["p"][:, 11])
+
+
+def test_mcspp_8_mics_matches_the_oracle_gpu(cuda):
+    """8 microphones: the patched reference raises LinAlgError in frames 5..6 (unloaded fallback inverse of a rank-deficient
+    Phi_yy, mcspp.py:224-227); the drop-in and the oracle keep the loading until Phi_yy has full rank (deviations)."""
+    from distantspeech_b200.noise_estimation.mcspp import McSpp
+    geo = O.MicGeometry("circular", r=0.05, M=8, n_fft=512)
+    x = np.ascontiguousarray(O.synth_streams(1, geo, 256 * 160, seed0=0xC8)[0].T)
+    D = O.Transform(channel=8, n_fft=512, hop_length=256).stft(x.astype(np.float64))
+    ref, taps = O.McSpp(nfft=512, channels=8), {k: [] for k in ("p", "xi", "q")}
+    with np.errstate(all="ignore"):
+        for n in range(D.shape[1]):
+            ref.estimation(D[:, n, :])
+            for k in taps:
+                taps[k].append(getattr(ref, k).copy())
+    est = McSpp(nfft=512, channels=8)
+    res = est.estimation_frames(D)
+    assert np.all(np.isfinite(res["p"]))
+    for k in taps:
+        assert np.allclose(res[k], np.array(taps[k]).T, rtol=1e-6, atol=1e-10), (k, np.max(np.abs(res[k] - np.array(taps[k]).T)))
+    assert np.max(np.abs(est.w - ref.w)) <= 1e-7 * np.max(np.abs(ref.w))

@@ -182,3 +182,29 @@ def test_diagnostics_live(ref):
         assert np.allclose(a, b, rtol=1e-10, atol=1e-10)
     assert np.allclose(rb.compute_beampattern(mic, weights=W.T.copy()), ob.compute_beampattern(ob.MicArray, weights=W.T.copy()),
                        rtol=0, atol=1e-9)
+
+
+def test_mcspp_more_than_4_mics_live(ref):
+    """8f.3: McSpp with 6 microphones = the reference with McCDR(nfft, channels=6) handed in; as shipped it raises IndexError
+    (mcspp.py:54); with 8 microphones even the patched reference fails in frames 5..6 (singular unloaded fallback inverse)"""
+    from DistantSpeech.transform.transform import Transform
+    from DistantSpeech.noise_estimation.mcspp import McSpp
+    geo = O.MicGeometry("circular", r=0.04, M=6, n_fft=256)
+    x = np.ascontiguousarray(O.synth_streams(1, geo, 128 * 30, seed0=505)[0].T).astype(np.float64)
+    D = Transform(n_fft=256, hop_length=128, channel=6).stft(x)
+    with _quiet():
+        shipped = McSpp(nfft=256, channels=6)
+    with pytest.raises(IndexError):
+        shipped.estimation(D[:, 0, :])
+    r, o = H.make_mcspp(256, 6), O.McSpp(nfft=256, channels=6)
+    with np.errstate(all="ignore"):
+        for n in range(D.shape[1]):
+            assert np.array_equal(r.estimation(D[:, n, :]), o.estimation(D[:, n, :]))
+    assert np.array_equal(r.w, o.w)
+    geo8 = O.MicGeometry("circular", r=0.04, M=8, n_fft=256)
+    x8 = np.ascontiguousarray(O.synth_streams(1, geo8, 128 * 12, seed0=7)[0].T).astype(np.float64)
+    D8 = Transform(n_fft=256, hop_length=128, channel=8).stft(x8)
+    r8 = H.make_mcspp(256, 8)
+    with pytest.raises(np.linalg.LinAlgError), np.errstate(all="ignore"):
+        for n in range(D8.shape[1]):
+            r8.estimation(D8[:, n, :])

@@ -76,3 +76,19 @@ def test_adaptive_mvdr_rec1_golden():
         y = O.adaptive_mvdr(x, geo, g["angle_rad"], 256, 128)
     assert y.shape == g["y"].shape == (160000,)
     assert np.max(np.abs(y - g["y"])) < 1e-6 and snr_db(g["y"], y) > 110
+
+
+def test_mcspp_more_than_4_mics_golden():
+    """8f.3: the McSpp oracle with 5 / 6 microphones is bit-identical to the reference run with McCDR(nfft, channels=M)
+    handed in (oracle/ref_harness.make_mcspp), and so is estimation(repeat=True) at 4 microphones."""
+    g = golden("mcspp_cdr_m68.npz")
+    for tag, M, rep in (("m6", 6, False), ("m5", 5, False), ("m4r", 4, True)):
+        D = O.Transform(channel=M, n_fft=256, hop_length=128).stft(g[tag + "_x"].astype(np.float64))
+        est = O.McSpp(nfft=256, channels=M)
+        with np.errstate(all="ignore"):
+            for n in range(D.shape[1]):
+                p = est.estimation(D[:, n, :], repeat=rep)
+                assert np.array_equal(p, g[tag + "_p"][:, n]) and np.array_equal(est.xi, g[tag + "_xi"][:, n]), (tag, n)
+                assert np.array_equal(est.q, g[tag + "_q"][:, n]) and np.array_equal(est.gamma, g[tag + "_gamma"][:, n]), (tag, n)
+        assert np.array_equal(est.w, g[tag + "_w_last"]) and np.array_equal(est.Phi_vv_inv, g[tag + "_Phi_vv_inv_last"])
+        assert np.array_equal(est.mccdr.Pxii, g[tag + "_Pxii_last"])
