@@ -258,6 +258,9 @@ def _declare(lib):
     lib.ds_chain_run_io.argtypes = [C.POINTER(ChainParams), vp, vp, vp, vp, vp, i32, vp, i32, vp]
     lib.ds_stft_pcm16_run.argtypes = [C.POINTER(StftParams), vp, vp, vp, vp, vp]
     lib.ds_istft_pcm16_run.argtypes = [C.POINTER(IstftParams), vp, vp, vp, vp, vp]
+    lib.ds_wpe_state_bytes.argtypes = [i32, i32, i32, i32, i32]
+    lib.ds_wpe_state_bytes.restype = C.c_size_t
+    lib.ds_wpe_run.argtypes = [i32, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, i32, vp, vp]
     lib.ds_fp64_peak_run.argtypes = [i32, vp, vp]
     lib.ds_fp64_peak_run.restype = C.c_double
     lib.ds_double_to_pcm16_run.argtypes = [C.c_size_t, vp, vp, vp]

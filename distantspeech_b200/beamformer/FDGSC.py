@@ -103,6 +103,14 @@ class FDGSC(object):
         p.mu_bm, p.mu_aic, p.alpha = float(self.mu_bm), float(self.mu_aic), float(self.alpha)
         return p
 
+    def reset_state(self):
+        """Zero the recursive state in place (a fresh utterance for the same batch size, no reallocation)."""
+        if self._state is not None:
+            self._state.zero_()
+        self._pf = None
+        self._diag = None
+        self.spp.frm_cnt, self.spp.ell = 0, 1
+
     def reset(self):
         self._state = None
         self._pf = None

@@ -308,6 +308,17 @@ int ds_mcspp_cdr_run(const ds_mcspp_cdr_params *p, void *state, void *workspace,
  * lambda_d, posterior p                                                             */
 int ds_mcspp_cdr_export(const ds_mcspp_cdr_params *p, const void *state, int field, void *out, void *stream);
 
+/* ---- adaptive (RLS) WPE dereverberation (dereverberation/awpe.py) ----------------------------- */
+/* state blob [S][NE][K] float64 (NE from ds_wpe_state_bytes): W re/im [C][C L], P re/im [C L][C L], the last
+ * delay + filter_len - 1 input frames re/im [.][C] (most recent first), var.  A fresh filter has P = 1e-3 I
+ * (awpe.py:66-71) and everything else zero -- the caller writes the diagonal.                                  */
+size_t ds_wpe_state_bytes(int n_streams, int n_bins, int n_ch, int filter_len, int delay);
+/* replaces the arithmetic of Wpe.update (awpe.py:152-187) for T frames per call: X [S][T][C][K] c64 (x_is_c128 = 0)
+ * or c128, the streaming STFT of the observed signals; Err [S][T][C][K] c128 receives the prior error d - W^H X of
+ * every channel (the dereverberated spectrum).  delay = D frames (awpe.py:72: D hops in the time domain).      */
+int ds_wpe_run(int n_streams, int n_bins, int n_frames, int n_ch, int filter_len, int delay, double forgetting_factor,
+               double alpha_var, void *state, const void *X, int x_is_c128, void *Err, void *stream);
+
 /* ---- McMcra + frequency-domain GSC (noise_estimation/mc_mcra.py, beamformer/GSC.py) -------- */
 typedef struct ds_gsc_params {
   int32_t n_fft;

@@ -246,6 +246,49 @@ def make_mcspp(nfft=512, channels=4):
     return obj
 
 
+def make_wpe(channels=2, filter_len=2, num_bands=512, delay=4, hop_length=None):
+    """Make the reference ``Wpe`` (dereverberation/awpe.py:28-193) executable so that the arithmetic of its ``update``
+    (:152-187) can be pinned.  As shipped it cannot run; three things are supplied from the outside, the body of
+    ``update`` is the reference's own:
+      (vi)   ``Subband`` (the Nyquist(M) filter bank, outside the hot path; its designer needs ``np.float_`` and writes
+             pickles under /home/wangwei) is replaced, for this class only, by the reference's own streaming ``Transform``;
+      (vii)  the method ``check_input_data`` that ``update`` calls (:150) exists nowhere in the reference; the injected one
+             does what its siblings' ``update_input_data`` does (SubbandAF.py:53-59): analyse both blocks, one frame each;
+      (viii) ``update`` ends in ``return output, self.W`` with ``output`` unassigned (:188-191): ``step`` lets the state
+             update finish, swallows that UnboundLocalError and returns the filter state (W, P, var).
+    Returns an object whose ``step(x_n[hop, C]) -> (W, P, var)`` runs one reference update."""
+    install()
+    import numpy as np
+    import DistantSpeech.dereverberation.awpe as awpe_mod
+    from DistantSpeech.transform.transform import Transform
+
+    class _Bank(Transform):                                   # (vi)
+        def __init__(self, n_fft=256, hop_length=128, channel=1):
+            Transform.__init__(self, n_fft=n_fft, hop_length=hop_length, channel=channel)
+
+    saved = awpe_mod.Subband
+    awpe_mod.Subband = _Bank
+    try:
+        obj = awpe_mod.Wpe(channels=channels, filter_len=filter_len, num_bands=num_bands, delay=delay, hop_length=hop_length)
+    finally:
+        awpe_mod.Subband = saved
+
+    def check_input_data(x_delayed, x_n):                     # (vii)
+        Xd = obj.transform_x.stft(x_delayed)[:, 0, :]
+        Dn = obj.transform_d.stft(x_n)[:, 0, :]
+        return Xd, Dn
+    obj.check_input_data = check_input_data
+
+    def step(x_n):                                            # (viii)
+        try:
+            obj.update(np.asarray(x_n, dtype=np.float64))
+        except UnboundLocalError:
+            pass
+        return obj.W, obj.P, obj.var
+    obj.step = step
+    return obj
+
+
 def make_gsc(mic, frameLen=256, angle=None):
     """Construct the reference frequency-domain ``GSC`` (beamformer/GSC.py) with the same patch (iii):
     ``GSC.process`` hands its 2-D ``[K, T]`` spectrum to ``Transform.istft`` (:289), which reads 2-D as one

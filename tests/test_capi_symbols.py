@@ -82,9 +82,11 @@ def test_argument_validation_precedes_any_device_work():
     lib.ds_mcspp_default_params(ctypes.byref(mp), 512, 1, 9, 4)              # 9 microphones: outside 2..8
     assert lib.ds_mcspp_run(ctypes.byref(mp), one, null, one, 0, null, 0, None, null) == EUNSUP
     cp = _lib.McsppCdrParams()
-    lib.ds_mcspp_cdr_default_params(ctypes.byref(cp), 512, 1, 8, 4)          # McSpp needs 4 channels
+    lib.ds_mcspp_cdr_default_params(ctypes.byref(cp), 512, 1, 3, 4)          # McSpp needs 4..8 channels
     assert lib.ds_mcspp_cdr_run(ctypes.byref(cp), one, one, one, one, 0, null, None, null) == EUNSUP
-    assert b"n_mics must be 4" in lib.ds_last_error()
+    assert b"n_mics must be 4..8" in lib.ds_last_error()
+    assert lib.ds_wpe_run(1, 257, 4, 8, 3, 2, 0.998, 0.98, one, one, 0, one, null) == EINVAL      # 8 channels x 3 taps > 16
+    assert lib.ds_wpe_state_bytes(1, 257, 0, 2, 2) == 0
     gp = _lib.GscParams()
     lib.ds_gsc_default_params(ctypes.byref(gp), 256, 1, 4, 4)
     assert lib.ds_gsc_run(ctypes.byref(gp), one, null, one, 0, one, None, null) == EINVAL     # output without propagation vectors

@@ -365,7 +365,10 @@ def test_fdgsc_golden(cuda, precision):
     x = g["x"].copy()
     res = fd.process(x, postfilter=False, dc_notch=True)
     assert len(res) == 9
-    assert np.array_equal(x, g["x_notched"])                                  # in-place DC notch, bit exact (quirk 11)
+    # in-place DC notch (quirk 11): the time-parallel kernel reproduces the sequential filter to the last bit of float32
+    # except where a double-precision last-bit difference of its carried state crosses a rounding boundary
+    dn = np.abs(x - g["x_notched"])
+    assert np.max(dn) <= 2 * np.spacing(np.abs(g["x_notched"]).max()) and np.mean(dn > 0) < 1e-4
     err, s = assert_wave_parity(g["y"], res[0], "FDGSC %s" % precision)
     print("FDGSC %s: max-abs %.2e SNR %.1f dB" % (precision, err, s))
     assert np.max(np.abs(res[2] - g["fix_output"])) < 2e-6

@@ -195,3 +195,69 @@ def test_mcspp_8_mics_matches_the_oracle_gpu(cuda):
     for k in taps:
         assert np.allclose(res[k], np.array(taps[k]).T, rtol=1e-6, atol=1e-10), (k, np.max(np.abs(res[k] - np.array(taps[k]).T)))
     assert np.max(np.abs(est.w - ref.w)) <= 1e-7 * np.max(np.abs(ref.w))
+
+
+# ---------------------------------------------------------------- f4: adaptive WPE
+def test_wpe_golden_gpu(cuda):
+    """Wpe (dereverberation/awpe.py:128-191) against the filter state of the reference's own update body (ref_harness.make_wpe)
+    and against the oracle's dereverberated waveform; block by block == one call; batch == singles."""
+    from distantspeech_b200.dereverberation.awpe import Wpe
+    g = golden("wpe.npz")
+    C, Lf, nb, hop, D = (int(v) for v in g["params"])
+    x = g["x"]
+    w = Wpe(channels=C, filter_len=Lf, num_bands=nb, delay=D, hop_length=hop)
+    outs = []
+    for n in range(60):
+        y0, W = w.update(x[n * hop:(n + 1) * hop])
+        outs.append(y0)
+        if n + 1 in (30, 60):
+            for nm, a in (("W", w.W), ("P", w.P), ("var", w.var)):
+                ref = g["%s%d" % (nm, n + 1)]
+                assert a.shape == ref.shape, (nm, a.shape, ref.shape)
+                assert np.max(np.abs(a - ref)) <= 2e-5 * np.max(np.abs(ref)), (nm, n + 1, np.max(np.abs(a - ref)) / np.max(np.abs(ref)))
+    ref_y = O.WpeOracle(channels=C, filter_len=Lf, num_bands=nb, delay=D, hop_length=hop).process(x.astype(np.float64))
+    assert_wave_parity(ref_y[:, 0], np.concatenate(outs), "WPE, block by block")
+    w2 = Wpe(channels=C, filter_len=Lf, num_bands=nb, delay=D, hop_length=hop)
+    y = w2.process(x)
+    assert y.shape == x.shape
+    for c in range(C):
+        assert_wave_parity(ref_y[:, c], y[:, c], "WPE channel %d" % c)
+    assert np.max(np.abs(y[:, 0] - np.concatenate(outs))) < 1e-6
+    # fed the reference's spectrum (complex128) the recursion itself agrees to rounding
+    import torch
+    from distantspeech_b200 import _lib as L
+    Dspec = O.Transform(n_fft=nb, hop_length=hop, channel=C).stft(x.astype(np.float64))              # [K, T, C]
+    w3 = Wpe(channels=C, filter_len=Lf, num_bands=nb, delay=D, hop_length=hop)
+    w3._ensure(1)
+    X = torch.as_tensor(np.ascontiguousarray(Dspec.transpose(1, 2, 0)[None])).cuda()                 # [1, T, C, K] c128
+    Err = torch.empty_like(X)
+    L.check(L.lib().ds_wpe_run(1, nb // 2 + 1, X.shape[1], C, Lf, D, 0.998, 0.98, L.ptr(w3._state), L.ptr(X), 1, L.ptr(Err), L.stream_ptr()))
+    assert np.max(np.abs(w3.W - g["W60"])) <= 1e-9 * np.max(np.abs(g["W60"]))
+    assert np.max(np.abs(w3.P - g["P60"])) <= 1e-9 * np.max(np.abs(g["P60"]))
+    yb = Wpe(channels=C, filter_len=Lf, num_bands=nb, delay=D, hop_length=hop).process(np.stack([x, x[::-1].copy()]))
+    assert np.max(np.abs(yb[0] - y)) < 1e-7
+
+
+def test_realtime_chunks_equal_one_call_gpu(cuda):
+    """8f.2 chunk API: 1024-frame int16 capture buffers through realtime_processing.process_pcm with the GSC pipeline as the
+    enhancement method == the same signal processed in one call (state carries over from chunk to chunk)."""
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.GSC import GSC
+    from distantspeech_b200.realtime.realtime_processing import realtime_processing
+    geo = O.MicGeometry("circular", r=0.032, M=4, n_fft=256)
+    x4 = O.synth_streams(1, geo, 1024 * 12, seed0=0x77)[0]                                # [4, N] float32
+    pcm = np.zeros((1024 * 12, 6), dtype=np.int16)
+    pcm[:, 1:5] = np.round(x4.T * 32768).astype(np.int16)
+    ang = np.array([30, 0]) / 180 * np.pi
+
+    class Wrap(object):                                  # the reference calls EnhancementMethod.process(data) with one argument
+        def __init__(self):
+            self.g = GSC(MicArray(arrayType="circular", r=0.032, M=4), 256)
+
+        def process(self, data):
+            return self.g.process(np.ascontiguousarray(data.T), ang, method=2)
+    rt = realtime_processing(EnhancementMehtod=Wrap(), chunk=1024, channels=6)
+    chunks = [np.frombuffer(rt.process_pcm(pcm[i * 1024:(i + 1) * 1024].tobytes()), dtype='<i2') for i in range(12)]
+    whole = Wrap().process(pcm[:, 1:5].astype(np.float32) / 32768.0)["data"]
+    ref = (whole.astype(np.float32) * 32768).astype('<i2')
+    assert np.max(np.abs(np.concatenate(chunks).astype(np.int32) - ref.astype(np.int32))) <= 1

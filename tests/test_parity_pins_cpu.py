@@ -92,3 +92,41 @@ def test_mcspp_more_than_4_mics_golden():
                 assert np.array_equal(est.q, g[tag + "_q"][:, n]) and np.array_equal(est.gamma, g[tag + "_gamma"][:, n]), (tag, n)
         assert np.array_equal(est.w, g[tag + "_w_last"]) and np.array_equal(est.Phi_vv_inv, g[tag + "_Phi_vv_inv_last"])
         assert np.array_equal(est.mccdr.Pxii, g[tag + "_Pxii_last"])
+
+
+def test_wpe_golden():
+    """8f.4: the WPE oracle reproduces the filter state of the reference's own update body (awpe.py:152-187) bit for bit."""
+    g = golden("wpe.npz")
+    C, Lf, nb, hop, D = (int(v) for v in g["params"])
+    o = O.WpeOracle(channels=C, filter_len=Lf, num_bands=nb, delay=D, hop_length=hop)
+    tx = O.Transform(n_fft=nb, hop_length=hop, channel=C)
+    x = g["x"].astype(np.float64)
+    for n in range(60):
+        o.update_spec(tx.stft(x[n * hop:(n + 1) * hop])[:, 0, :])
+        if n + 1 in (30, 60):
+            assert np.array_equal(o.W, g["W%d" % (n + 1)]) and np.array_equal(o.P, g["P%d" % (n + 1)])
+            assert np.array_equal(o.var, g["var%d" % (n + 1)])
+    # the error signal is a dereverberated version of the input: energy drops once the filter has adapted
+    y = O.WpeOracle(channels=C, filter_len=Lf, num_bands=nb, delay=D, hop_length=hop).process(x)
+    assert y.shape == x.shape and np.sum(y[hop * 30:] ** 2) < np.sum(x[hop * 29:-hop] ** 2)
+
+
+def test_realtime_chunk_api_host_logic():
+    """8f.2: the chunk API mirrors realtime_processing.process / the capture loop's arithmetic (realtime_processing.py:78-84,
+    :113-131): / 32768 scaling, channels 1..4 in, channel 5 out, int16 bytes back."""
+    from distantspeech_b200.realtime.realtime_processing import realtime_processing
+    rng = np.random.default_rng(2)
+    pcm = rng.integers(-20000, 20000, size=(1024, 6), dtype=np.int16)
+
+    class Mean(object):
+        def process(self, data):
+            return {"data": data.mean(axis=1)}
+    rt = realtime_processing(EnhancementMehtod=Mean(), chunk=1024, channels=6)
+    out = np.frombuffer(rt.process_pcm(pcm.tobytes()), dtype='<i2')
+    f = pcm.astype(np.float32) / 32768.0
+    assert np.array_equal(out, (f[:, 1:5].mean(axis=1) * 32768).astype('<i2'))
+    passthrough = realtime_processing(EnhancementMehtod=None, chunk=1024, channels=6)
+    assert np.array_equal(np.frombuffer(passthrough.process_pcm(pcm.tobytes()), dtype='<i2'), pcm[:, 2])      # data[:, 1] of channels 1..4
+    rec = realtime_processing(EnhancementMehtod=None, chunk=1024, channels=6, save_rec_to_file=True)
+    allch = np.frombuffer(rec.process_pcm(pcm.tobytes()), dtype='<i2').reshape(1024, 6)
+    assert np.array_equal(allch[:, :5], pcm[:, :5]) and np.array_equal(allch[:, 5], pcm[:, 2])
