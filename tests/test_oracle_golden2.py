@@ -63,7 +63,7 @@ def test_mcspp_cdr_golden():
     assert np.array_equal(est.Phi_vv_inv, g["Phi_vv_inv_last"]) and np.array_equal(est.Phi_xx, g["Phi_xx_last"])
     assert np.array_equal(est.mccdr.mcra.p, g["mcra_p_last"])
     with pytest.raises(ValueError):
-        O.McSpp(nfft=512, channels=6)                     # the reference raises IndexError above 4 channels
+        O.McSpp(nfft=512, channels=3)                     # pair (1, 2) of the CDR prior is undefined below 4 channels
 
 
 def test_gsc_mcmcra_golden():
