@@ -177,6 +177,9 @@ def _declare(lib):
     lib.ds_fdgsc_state_bytes.argtypes = [C.POINTER(FdgscParams)]
     lib.ds_fdgsc_state_bytes.restype = C.c_size_t
     lib.ds_fdgsc_run.argtypes = [C.POINTER(FdgscParams), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ds_fdgsc_workspace_bytes.argtypes = [C.POINTER(FdgscParams)]
+    lib.ds_fdgsc_workspace_bytes.restype = C.c_size_t
+    lib.ds_fdgsc_run_ws.argtypes = [C.POINTER(FdgscParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ds_fir_run.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.ds_omlsa_multi_default_params.argtypes = [C.POINTER(OmlsaMultiParams), i32, i32, i32, i32]
     lib.ds_omlsa_multi_default_params.restype = None

@@ -2,8 +2,10 @@
 (FDGSC :37, process :201) with its building blocks ``TimeAlignment``
 (fixedbeamformer.py:51-93), ``AdaptiveBlockingMatrixFilter`` (gsc_bm.py),
 ``AdaptiveInterferenceCancellation`` (gsc_aic.py), ``FilterDcNotch16`` (feature.py:32-49)
-and the delay lines, all fused into ds_fdgsc_run: one CTA per stream, every filter
-state resident in shared memory for the whole utterance.
+and the delay lines.  Two device implementations with identical results and state: ``impl="pipeline"`` (default;
+ds_fdgsc_run_ws: feed-forward alignment / spectra / detector kernels, one warp per blocking filter, one CTA per
+canceller, intermediate signals through a scratch workspace) and ``impl="fused"`` (ds_fdgsc_run: one CTA per stream,
+every filter state resident in shared memory for the whole utterance, no workspace).
 
 ``process(x[N, M])`` returns the reference's 9-tuple; ``x`` is overwritten with the
 DC-notched signal like the reference does (FDGSC.py:213).  A leading stream axis
@@ -71,7 +73,7 @@ class _McraView(object):
 
 
 class FDGSC(object):
-    def __init__(self, mic_array: MicArray, frameLen=256, angle=[197, 0], precision="fp32"):
+    def __init__(self, mic_array: MicArray, frameLen=256, angle=[197, 0], precision="fp32", impl="pipeline"):
         if frameLen != 256:
             raise L.DsError("the CUDA FDGSC is compiled for frameLen = 256 (reference default)")
         self.MicArray = mic_array
@@ -85,6 +87,11 @@ class FDGSC(object):
         self.gamma = mic_array.gamma
         self.spp = _McraView()
         self.precision = precision
+        if impl not in ("pipeline", "fused"):
+            raise ValueError("impl must be 'pipeline' (kernels cut along the data dependences, needs a workspace) or "
+                             "'fused' (one CTA per stream, no workspace)")
+        self.impl = impl
+        self._ws = None
         self.mu_bm, self.mu_aic, self.alpha = 0.1, 0.1, 0.9
         self.phi, self.psi = None, None          # ccafbounds: computed by the reference ctor but never used
         self._state = None
@@ -102,6 +109,21 @@ class FDGSC(object):
         p.fp64 = int(self.precision == "fp64")
         p.mu_bm, p.mu_aic, p.alpha = float(self.mu_bm), float(self.mu_aic), float(self.alpha)
         return p
+
+    def _launch(self, prm, h, xrun, yrun, bm_out, fix_out, p_out):
+        """ds_fdgsc_run_ws (pipeline of kernels, scratch workspace kept between calls) or ds_fdgsc_run (fused kernel)."""
+        t = L.require_cuda()
+        win = L.device_window(_sqrt_hann(512), 512)
+        if self.impl == "fused":
+            L.check(L.lib().ds_fdgsc_run(C.byref(prm), L.ptr(h), L.ptr(win), L.ptr(self._state), L.ptr(xrun), L.ptr(yrun),
+                                         L.ptr(bm_out), L.ptr(fix_out), L.ptr(p_out), L.stream_ptr()), "ds_fdgsc_run")
+            return
+        need = L.lib().ds_fdgsc_workspace_bytes(C.byref(prm))
+        if self._ws is None or self._ws.numel() < need or self._ws.device.index != t.cuda.current_device():
+            self._ws = None
+            self._ws = t.empty(need, dtype=t.uint8, device="cuda")
+        L.check(L.lib().ds_fdgsc_run_ws(C.byref(prm), L.ptr(h), L.ptr(win), L.ptr(self._state), L.ptr(self._ws), L.ptr(xrun),
+                                        L.ptr(yrun), L.ptr(bm_out), L.ptr(fix_out), L.ptr(p_out), L.stream_ptr()), "ds_fdgsc_run_ws")
 
     def reset_state(self):
         """Zero the recursive state in place (a fresh utterance for the same batch size, no reallocation)."""
@@ -204,8 +226,7 @@ class FDGSC(object):
         key = (t.cuda.current_device(),)
         if getattr(self, "_h_dev", None) is None or self._h_dev[0] != key:
             self._h_dev = (key, t.as_tensor(np.ascontiguousarray(self.time_alignment.delay_filter.T)).to("cuda"))     # [M, FL]
-        L.check(L.lib().ds_fdgsc_run(C.byref(prm), L.ptr(self._h_dev[1]), L.ptr(L.device_window(_sqrt_hann(512), 512)),
-                                     L.ptr(self._state), L.ptr(xs), L.ptr(y), None, None, None, L.stream_ptr()), "ds_fdgsc_run")
+        self._launch(prm, self._h_dev[1], xs, y, None, None, None)
         f, e = C.c_int32(self.spp.frm_cnt), C.c_int32(self.spp.ell)
         L.lib().ds_mcra_advance(int(self.spp.L), N // self.frameLen, C.byref(f), C.byref(e))
         self.spp.frm_cnt, self.spp.ell = f.value, e.value
@@ -243,9 +264,7 @@ class FDGSC(object):
         fix_out = t.zeros((S, Nb), dtype=t.float32, device="cuda")
         p_out = t.empty((S, nblk, 257), dtype=t.float64, device="cuda")
         h = t.as_tensor(np.ascontiguousarray(self.time_alignment.delay_filter.T)).to("cuda")       # [M, FL]
-        L.check(L.lib().ds_fdgsc_run(C.byref(prm), L.ptr(h), L.ptr(L.device_window(_sqrt_hann(512), 512)), L.ptr(self._state),
-                                     L.ptr(xrun), L.ptr(yrun), L.ptr(bm_out), L.ptr(fix_out), L.ptr(p_out), L.stream_ptr()),
-                "ds_fdgsc_run")
+        self._launch(prm, h, xrun, yrun, bm_out, fix_out, p_out)
         f, e = C.c_int32(self.spp.frm_cnt), C.c_int32(self.spp.ell)
         L.lib().ds_mcra_advance(int(self.spp.L), nblk, C.byref(f), C.byref(e))
         self.spp.frm_cnt, self.spp.ell = f.value, e.value

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NOTCH_WARPS * 32) dcnotch_scan_kernel(float *x
   if (lane == 0) { mem[0] = c0; mem[1] = c1; }
 }
 
-static int launch_dcnotch(float *x, double *state, int S, int M, int Ns, double r, cudaStream_t st) {
+int fdgsc_notch_launch(float *x, double *state, int S, int M, int Ns, double r, cudaStream_t st) {
   const double den2 = r * r + 0.7 * (1 - r) * (1 - r);
   const long long rows = (long long)S * M;
   if (Ns % NOTCH_SEG == 0 && ((reinterpret_cast<size_t>(x) & 15) == 0)) {
@@ -630,7 +630,7 @@ int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const dou
   if (rc != DS_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->dc_notch) {
-    rc = launch_dcnotch(x, (double *)state, p->n_streams, p->n_mics, p->n_samples, p->notch_radius, st);
+    rc = fdgsc_notch_launch(x, (double *)state, p->n_streams, p->n_mics, p->n_samples, p->notch_radius, st);
     if (rc != DS_OK) return rc;
   }
   FdgscArgs a;
@@ -645,7 +645,7 @@ int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const dou
 
 int ds_fdgsc_notch_run(const ds_fdgsc_params *p, void *state, float *x, int n_samples, void *stream) {
   DS_CHECK_ARG(p && state && x && n_samples >= 1, "ds_fdgsc_notch_run: bad argument");
-  return launch_dcnotch(x, (double *)state, p->n_streams, p->n_mics, n_samples, p->notch_radius, (cudaStream_t)stream);
+  return fdgsc_notch_launch(x, (double *)state, p->n_streams, p->n_mics, n_samples, p->notch_radius, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -507,6 +507,13 @@ size_t ds_fdgsc_state_bytes(const ds_fdgsc_params *p);
 int ds_fdgsc_run(const ds_fdgsc_params *p, const double *delay_filter, const double *window,
                  void *state, float *x, float *y, float *bm_out, float *fix_out, double *p_out,
                  void *stream);
+/* The same computation as a pipeline of kernels cut along the algorithm's data dependences (feed-forward alignment /
+ * spectra / detector, one warp per blocking filter, one CTA per canceller): several times faster for large batches, at
+ * the price of a caller-provided scratch `workspace` of ds_fdgsc_workspace_bytes(p) bytes (about 3x the input).
+ * Same arguments, state blob and results as ds_fdgsc_run.                                                      */
+size_t ds_fdgsc_workspace_bytes(const ds_fdgsc_params *p);
+int ds_fdgsc_run_ws(const ds_fdgsc_params *p, const double *delay_filter, const double *window, void *state,
+                    void *workspace, float *x, float *y, float *bm_out, float *fix_out, double *p_out, void *stream);
 
 /* The DC notch of FDGSC.process on its own (FDGSC.py:211-213, feature.py:37-49), in place on
  * x [S][M][n_samples] with the notch memories of `state`: the reference filters the WHOLE input,

@@ -261,3 +261,57 @@ def test_realtime_chunks_equal_one_call_gpu(cuda):
     whole = Wrap().process(pcm[:, 1:5].astype(np.float32) / 32768.0)["data"]
     ref = (whole.astype(np.float32) * 32768).astype('<i2')
     assert np.max(np.abs(np.concatenate(chunks).astype(np.int32) - ref.astype(np.int32))) <= 1
+
+
+# ---------------------------------------------------------------- a17: the FDGSC kernel pipeline against the fused kernel and the goldens
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_fdgsc_pipeline_equals_fused_and_golden_gpu(cuda, precision):
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.FDGSC import FDGSC
+    g = golden("fdgsc.npz")
+    mic = MicArray(arrayType="linear", r=0.05, M=6, n_fft=256)
+    ang = [int(g["angle_deg"][0]), int(g["angle_deg"][1])]
+    res = {}
+    for impl in ("pipeline", "fused"):
+        fd = FDGSC(mic, frameLen=256, angle=ang, precision=precision, impl=impl)
+        r = fd.process(g["x"].copy(), postfilter=False, dc_notch=True)
+        err, s = assert_wave_parity(g["y"], r[0], "FDGSC %s %s" % (impl, precision))
+        print("FDGSC %s %s: max-abs %.2e SNR %.1f dB" % (impl, precision, err, s))
+        res[impl] = (r, fd.aic_filter.W.copy(), np.stack([f.W[:, 0] for f in fd.bm]))
+    tol = 2e-6 if precision == "fp32" else 1e-10
+    a, b = res["pipeline"], res["fused"]
+    assert np.max(np.abs(a[0][0] - b[0][0])) < tol                      # output
+    assert np.max(np.abs(a[0][2] - b[0][2])) < tol and np.max(np.abs(a[0][4] - b[0][4])) < tol        # fixed beam, blocking outputs
+    assert np.array_equal(a[0][1], b[0][1])                              # adaptation-control p: same decisions
+    assert np.linalg.norm(a[1] - b[1]) <= (1e-4 if precision == "fp32" else 1e-9) * np.linalg.norm(b[1])
+    assert np.linalg.norm(a[2] - b[2]) <= (1e-4 if precision == "fp32" else 1e-9) * np.linalg.norm(b[2])
+    # same state blob: a stream may switch implementation between calls
+    n1 = 256 * 25
+    fd = FDGSC(mic, frameLen=256, angle=ang, precision=precision, impl="pipeline")
+    ya = fd.process(g["x"][:n1].copy())[0]
+    fd.impl = "fused"
+    yb = fd.process(g["x"][n1:].copy())[0]
+    assert np.max(np.abs(np.concatenate([ya, yb]) - a[0][0])) < 10 * tol
+    fd2 = FDGSC(mic, frameLen=256, angle=ang, precision=precision, impl="fused")
+    ya = fd2.process(g["x"][:n1].copy())[0]
+    fd2.impl = "pipeline"
+    yb = fd2.process(g["x"][n1:].copy())[0]
+    assert np.max(np.abs(np.concatenate([ya, yb]) - a[0][0])) < 10 * tol
+
+
+def test_fdgsc_pipeline_batch_device_entry_gpu(cuda):
+    """process_device (output only) on a batch with 4, 6 and 8 microphones and a look direction with non-zero alignment delays."""
+    import torch
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.FDGSC import FDGSC
+    for M, look in ((4, 75.0), (6, 20.0), (8, 140.0)):
+        geo = O.MicGeometry("linear", r=0.05, M=M, n_fft=256)
+        xs = O.synth_streams(3, geo, 256 * 40, look_deg=(look, 0.0), interf_deg=(look + 70.0, 0.0), seed0=60 + M)   # [S, M, N]
+        mic = MicArray(arrayType="linear", r=0.05, M=M, n_fft=256)
+        fd = FDGSC(mic, frameLen=256, angle=[int(look), 0])
+        xd = torch.from_numpy(xs).cuda()
+        y = fd.process_device(xd).cpu().numpy()
+        for s in (0, 2):
+            ref = O.FdgscOracle(geo, 256, np.array([look, 0]) / 180 * np.pi).process(xs[s].T.astype(np.float64))
+            assert_wave_parity(ref[0], y[s], "FDGSC pipeline M=%d stream %d" % (M, s))
+            assert np.max(np.abs(xd[s].cpu().numpy().T - ref[4])) < 1e-6      # the caller's tensor holds the notched signal
