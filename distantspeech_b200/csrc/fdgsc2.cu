@@ -338,7 +338,16 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
   const T invN = (T)1 / (T)N, step_bm = (T)(1.0 * a.mu_bm);                  // p = 1.0 (gsc_bm.py:90, FDGSC.py:260)
 #define FIDX(n) (2 * FPAD<T>((n) >> 1) + ((n) & 1))
   for (int b = 0; b < a.nblk; ++b) {
-    for (int k = lane; k < K; k += 32) buf[FPAD<T>(k)] = cmul(Xf[(size_t)b * K + k], W[k]);
+    if (b + 1 < a.nblk) {
+      // next block's operands towards L2 now (ncu: 3.4 long-scoreboard stalls per issue without it): 128-byte lines
+      const char *px = reinterpret_cast<const char *>(Xf + (size_t)(b + 1) * K), *pp = reinterpret_cast<const char *>(Pf + (size_t)(b + 1) * K);
+      const char *pd = reinterpret_cast<const char *>(xad + (size_t)(b + 1) * L);
+      if (lane * 128 < (int)(K * sizeof(C2))) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + lane * 128));
+      if (lane * 128 < (int)(K * sizeof(T))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + lane * 128));
+      if (lane * 128 < (int)(L * sizeof(T))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + lane * 128));
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) buf[FPAD<T>(k)] = cmul(Xf[(size_t)b * K + k], W[k]); }
     __syncwarp();
     warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
     T e[L / 32];
@@ -354,16 +363,22 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
     for (int j = 0; j < L / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = (T)0; fb[FIDX(L + n)] = e[j]; }     // e_pad (:185)
     __syncwarp();
     warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-    for (int k = lane; k < K; k += 32) {                                     // X_f / P_f again from L2: cheaper than 27 live registers
-      const C2 g = cmulc(buf[FPAD<T>(k)], Xf[(size_t)b * K + k]);           // conj(X) * E
-      const T ip = (T)1 / Pf[(size_t)b * K + k];
-      C2 wv = W[k];
-      wv.x += step_bm * (g.x * ip); wv.y += step_bm * (g.y * ip);
-      buf[FPAD<T>(k)] = wv;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {                                            // X_f / P_f again from L2: cheaper than 27 live registers
+      const int k = lane + 32 * i;
+      if (k < K) {
+        const C2 g = cmulc(buf[FPAD<T>(k)], Xf[(size_t)b * K + k]);         // conj(X) * E
+        const T ip = (T)1 / Pf[(size_t)b * K + k];
+        C2 wv = W[k];
+        wv.x += step_bm * (g.x * ip); wv.y += step_bm * (g.y * ip);
+        buf[FPAD<T>(k)] = wv;
+      }
     }
     __syncwarp();
     warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
-    for (int n = lane; n < N; n += 32) {
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) {
+      const int n = lane + 32 * j;
       T v = fb[FIDX(n)] * invN;
       if (n >= L) {
         v = (T)0;                                                           // w[-hop_len:] = 0 (:94)
@@ -377,14 +392,18 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
     }
     __syncwarp();
     warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-    for (int k = lane; k < K; k += 32) W[k] = buf[FPAD<T>(k)];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) W[k] = buf[FPAD<T>(k)]; }
     __syncwarp();
   }
 #undef FIDX
   for (int k = lane; k < K; k += 32) { st[2 * k] = (double)W[k].x; st[2 * k + 1] = (double)W[k].y; }
 }
 
-// interference canceller: CTA per stream, warp per channel
+// interference canceller: CTA per stream, warp per channel.  The reference spectra X_a of block b + 1 depend only on the
+// blocking outputs, so they are computed by the otherwise idle warps WHILE warp 0 runs the serial output / error-spectrum
+// step of block b (ncu on the unpipelined version: 3.8 barrier stalls per issue): 4 transform times per block on the
+// critical path instead of 5, X_a double-buffered in shared memory.
 template <typename T>
 __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, const typename V2<T>::type *__restrict__ tw_h_g,
                                                      const typename V2<T>::type *__restrict__ tw_n_g) {
@@ -398,8 +417,8 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
   C2 *tw_n = tw_h + H;
   C2 *bufs = tw_n + (H / 2 + 2);                       // [M][BE]
   C2 *Waic = bufs + (size_t)M * BE;                    // [M][K]
-  C2 *Xa = Waic + (size_t)M * K;                       // [M][K]
-  C2 *Ef = Xa + (size_t)M * K;                         // [K]
+  C2 *XaBuf = Waic + (size_t)M * K;                    // [2][M][K]
+  C2 *Ef = XaBuf + (size_t)2 * M * K;                  // [K]
   T *Pa = reinterpret_cast<T *>(Ef + K + 1);           // [K]
   double *red = reinterpret_cast<double *>((reinterpret_cast<size_t>(Pa + K) + 15) & ~(size_t)15);    // [8]
   double *st = a.state + (size_t)s * so.total;
@@ -410,18 +429,28 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
   __syncthreads();
   C2 *buf = bufs + (size_t)warp * BE;
   T *fb = reinterpret_cast<T *>(buf);
-  const T *Bx = reinterpret_cast<const T *>(a.ws + w.B) + ((size_t)s * M + warp) * (L + a.Ns);      // [bm_prev | bm ...] of this warp's channel
+  const T *Bs = reinterpret_cast<const T *>(a.ws + w.B) + (size_t)s * M * (L + a.Ns);               // [M][L + Ns]: [bm_prev | bm ...]
   const T *Fd = reinterpret_cast<const T *>(a.ws + w.F) + (size_t)s * (L + a.Ns);                   // fbf delayed by one block
   const T *stepv = reinterpret_cast<const T *>(a.ws + w.step) + (size_t)s * a.nblk;
   const T invN = (T)1 / (T)N;
 #define FIDX(n) (2 * FPAD<T>((n) >> 1) + ((n) & 1))
-  for (int b = 0; b < a.nblk; ++b) {
-    // (a) X_a = rfft([bm_prev | bm]) per channel
-    for (int n = lane; n < N; n += 32) fb[FIDX(n)] = Bx[(size_t)b * L + n];
+  // X_a = rfft([bm_prev | bm]) of channel m for block b into plane `pl`
+  auto spectrum = [&](int m, int b, int pl) {
+    const T *src = Bs + (size_t)m * (L + a.Ns) + (size_t)b * L;
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = src[n]; }
     __syncwarp();
     warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-    for (int k = lane; k < K; k += 32) Xa[(size_t)warp * K + k] = buf[FPAD<T>(k)];
-    __syncthreads();
+    C2 *dst = XaBuf + ((size_t)pl * M + m) * K;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) dst[k] = buf[FPAD<T>(k)]; }
+    __syncwarp();
+  };
+  spectrum(warp, 0, 0);
+  __syncthreads();
+  for (int b = 0; b < a.nblk; ++b) {
+    const int cur = b & 1;
+    const C2 *Xa = XaBuf + (size_t)cur * M * K;
     // (b) power, sum_ch X W
     for (int k = tid; k < K; k += NT) {
       T pw = (T)0;
@@ -437,9 +466,10 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
       Ef[k] = acc;                                                          // sum_ch X W  (:161)
     }
     __syncthreads();
-    // (c) output block and error spectrum: warp 0
     if (warp == 0) {
-      for (int k = lane; k < K; k += 32) buf[FPAD<T>(k)] = Ef[k];
+      // (c) output block and error spectrum
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) buf[FPAD<T>(k)] = Ef[k]; }
       __syncwarp();
       warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
       T ev[L / 32];
@@ -454,7 +484,12 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
       for (int i = 0; i < L / 32; ++i) { const int n = lane + 32 * i; fb[FIDX(n)] = (T)0; fb[FIDX(L + n)] = ev[i]; }
       __syncwarp();
       warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-      for (int k = lane; k < K; k += 32) Ef[k] = buf[FPAD<T>(k)];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) Ef[k] = buf[FPAD<T>(k)]; }
+    } else if (b + 1 < a.nblk) {
+      // meanwhile: reference spectra of the next block (warp 1 also takes channel 0)
+      spectrum(warp, b + 1, cur ^ 1);
+      if (warp == 1) spectrum(0, b + 1, cur ^ 1);
     }
     __syncthreads();
     // (d) weight update, norm of the updated weights
@@ -479,13 +514,16 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
     const T sc = (nrm > a.maxnorm) ? (T)sqrt(a.maxnorm / nrm) : (T)1;
     // (e) constraint per channel: irfft, scale, zero the second half, rfft (:92-97)
     C2 *Wm = Waic + (size_t)warp * K;
-    for (int k = lane; k < K; k += 32) buf[FPAD<T>(k)] = Wm[k];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) buf[FPAD<T>(k)] = Wm[k]; }
     __syncwarp();
     warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
-    for (int n = lane; n < N; n += 32) fb[FIDX(n)] = (n >= L) ? (T)0 : fb[FIDX(n)] * invN * sc;
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = (n >= L) ? (T)0 : fb[FIDX(n)] * invN * sc; }
     __syncwarp();
     warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-    for (int k = lane; k < K; k += 32) Wm[k] = buf[FPAD<T>(k)];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) Wm[k] = buf[FPAD<T>(k)]; }
     __syncthreads();
   }
 #undef FIDX
@@ -562,7 +600,7 @@ static int launch_fdgsc2(const Fd2Args &a, const TwiddleSet &tw, cudaStream_t st
     DS_LAUNCH_CHECK();
   }
   {
-    const size_t smem = tw_bytes + ((size_t)M * BE + (size_t)2 * M * F2_K + F2_K + 1) * sizeof(C2) + (size_t)F2_K * sizeof(T) + 16 + 8 * sizeof(double);
+    const size_t smem = tw_bytes + ((size_t)M * BE + (size_t)3 * M * F2_K + F2_K + 1) * sizeof(C2) + (size_t)F2_K * sizeof(T) + 16 + 8 * sizeof(double);
     auto k = fd_aic_kernel<T>;
     DS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<a.S, 32 * M, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw));
