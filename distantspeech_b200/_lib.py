@@ -261,6 +261,9 @@ def _declare(lib):
     lib.ds_chain_run_io.argtypes = [C.POINTER(ChainParams), vp, vp, vp, vp, vp, i32, vp, i32, vp]
     lib.ds_stft_pcm16_run.argtypes = [C.POINTER(StftParams), vp, vp, vp, vp, vp]
     lib.ds_istft_pcm16_run.argtypes = [C.POINTER(IstftParams), vp, vp, vp, vp, vp]
+    lib.ds_multibeam_tc_layout.argtypes = [i32, i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.ds_multibeam_tc_run.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.ds_istft_frames_inner_run.argtypes = [C.POINTER(IstftParams), vp, vp, vp, C.c_longlong, vp, vp]
     lib.ds_wpe_state_bytes.argtypes = [i32, i32, i32, i32, i32]
     lib.ds_wpe_state_bytes.restype = C.c_size_t
     lib.ds_wpe_run.argtypes = [i32, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, i32, vp, vp]

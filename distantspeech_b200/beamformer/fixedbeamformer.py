@@ -61,6 +61,7 @@ class FixedBeamformer(beamformer):
     def reset(self):
         """Drop the streaming state (input history / output tail)."""
         self._state = None
+        self._tc_key = None
 
     def process(self, x, angle=(0, 0), weightType=None):
         """x [samples, channel] (or [S, samples, channel]) -> [samples] (or [S, samples]).
@@ -85,10 +86,59 @@ class FixedBeamformer(beamformer):
             return y
         return y.double().cpu().numpy().squeeze()
 
-    def process_multibeam(self, x, angles, weightType="SD"):
-        """Extension: x [S, N, M], ``angles`` list of (az, el) -> [S, B, N], all beams in one pass."""
+    def _run_tensor(self, x, W):
+        """The multi-beam path on the tensor cores: device STFT -> ds_multibeam_tc_run (per-bin [beams x 6M] . [6M x frames]
+        GEMMs on tcgen05, tf32 head + tail operands) -> per-beam ISTFT of the frames-innermost spectrum.
+        x [S, N, M], W [B, K, M] complex -> y [S, B, N] float32 CUDA.  Streaming state (input history, per-beam output
+        tail) is kept between calls like the fused kernel's."""
+        from ..transform.transform import stft_device
         t = L.require_cuda()
-        W = np.stack([self.compute_weights(look_angle=list(a), weightType=weightType) for a in angles])
+        L.ensure_init()
+        xd = L.to_device(x, t.float32)
+        S, N, M = xd.shape
+        if N % self.hop != 0:
+            raise AssertionError('output:{}, x:{}'.format((N // self.hop) * self.hop, tuple(xd.shape)))
+        xs = xd.permute(0, 2, 1).contiguous()                                   # [S, M, N]
+        Wd = L.to_device(np.asarray(W, dtype=np.complex64), t.complex64).contiguous()
+        B, K = Wd.shape[0], self.half_bin
+        tf = self.transform
+        ov = self.nfft - self.hop
+        key = (S, M, B, self.nfft, self.hop)
+        if getattr(self, "_tc_key", None) != key:
+            self._tc_key = key
+            self._tc_hist = t.zeros((S, M, max(ov, 1)), dtype=t.float32, device="cuda")
+            self._tc_tail = t.zeros((S, B, max(ov, 1)), dtype=t.float32, device="cuda")
+        win = L.device_window(tf.window, self.nfft)
+        X = stft_device(xs, self.nfft, self.hop, win, L.DS_STFT_STREAMING, history=self._tc_hist)     # [S, T, M, K] c64
+        T = X.shape[1]
+        pitch, wsb, yb = C.c_int32(), C.c_size_t(), C.c_size_t()
+        L.check(L.lib().ds_multibeam_tc_layout(S, T, M, K, B, C.byref(pitch), C.byref(wsb), C.byref(yb)), "ds_multibeam_tc_layout")
+        ws = t.empty(wsb.value, dtype=t.uint8, device="cuda")
+        Y = t.empty((S, B, K, pitch.value), dtype=t.complex64, device="cuda")
+        L.check(L.lib().ds_multibeam_tc_run(S, T, M, K, B, L.ptr(Wd), L.ptr(X), L.ptr(ws), L.ptr(Y), L.stream_ptr()),
+                "ds_multibeam_tc_run")
+        ip = L.IstftParams(self.nfft, self.hop, S, B, T, L.DS_STFT_STREAMING, 0, 0, float(self.hop / tf.W0))
+        y = t.empty((S, B, T * self.hop), dtype=t.float32, device="cuda")
+        L.check(L.lib().ds_istft_frames_inner_run(C.byref(ip), L.ptr(win), L.ptr(self._tc_tail), L.ptr(Y), pitch.value, L.ptr(y),
+                                                  L.stream_ptr()), "ds_istft_frames_inner_run")
+        return y
+
+    def process_multibeam(self, x, angles, weightType="SD", engine="auto"):
+        """Extension: x [S, N, M], ``angles`` list of (az, el) -> [S, B, N], all beams in one pass.
+        ``engine``: "tensor" = per-bin GEMMs on the tensor cores (tcgen05; 4, 8 or 16 microphones), "simt" = the fused
+        CUDA-core kernels, "auto" = tensor cores from 16 beams up (below that the fused kernel, whose spectrum never
+        leaves the SM, is faster)."""
+        t = L.require_cuda()
+        wkey = (tuple(tuple(float(v) for v in a) for a in angles), weightType)
+        if getattr(self, "_mb_wkey", None) != wkey:                          # one-off design per set of look directions (host)
+            self._mb_W = np.stack([self.compute_weights(look_angle=list(a), weightType=weightType) for a in angles])
+            self._mb_wkey = wkey
+        W = self._mb_W
         as_torch = isinstance(x, t.Tensor)
-        y = self._run(x, W)
+        if engine not in ("auto", "tensor", "simt"):
+            raise ValueError("engine must be 'auto', 'tensor' or 'simt'")
+        use_tc = engine == "tensor" or (engine == "auto" and len(angles) >= 16 and self.M in (4, 8, 16))
+        if use_tc and self.M not in (4, 8, 16):
+            raise ValueError("the tensor-core multi-beam path is compiled for 4, 8 or 16 microphones")
+        y = self._run_tensor(x, W) if use_tc else self._run(x, W)
         return y if as_torch else y.double().cpu().numpy()

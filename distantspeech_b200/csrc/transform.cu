@@ -179,6 +179,7 @@ struct IstftArgs {
   int S, C, T, hop, mode, n_out, in_c128;  // n_out = samples written per (s,c)
   double scale;
   short *y16;       // int16 PCM output instead of y (fused save_audio scaling, beamformer/utils.py:193)
+  long long sS, sT, sC, sK;   // element strides of Y over (stream, frame, channel, bin); default [S][T][C][K] contiguous
 };
 
 // save_audio on the float32 sample the float path would have stored: (audio * 32767).astype(int16) with the product in
@@ -200,13 +201,13 @@ __device__ __forceinline__ void istft_frame(const IstftArgs &a, int s, int c, in
                                             float *dst, int lane) {
   typedef typename V2<T>::type C2;
   constexpr int H = N / 2, K = H + 1;
-  const long long ibase = (((long long)s * a.T + t) * a.C + c) * K;
+  const long long ibase = (long long)s * a.sS + (long long)t * a.sT + (long long)c * a.sC;
   if (a.in_c128) {
     const double2 *in = reinterpret_cast<const double2 *>(a.Y) + ibase;
-    for (int k = lane; k < K; k += 32) { double2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
+    for (int k = lane; k < K; k += 32) { double2 v = in[k * a.sK]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
   } else {
     const float2 *in = reinterpret_cast<const float2 *>(a.Y) + ibase;
-    for (int k = lane; k < K; k += 32) { float2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
+    for (int k = lane; k < K; k += 32) { float2 v = in[k * a.sK]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
   }
   __syncwarp();
   warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
@@ -315,13 +316,13 @@ __global__ void __launch_bounds__(ISEQ_WARPS * 32) istft_seq_kernel(IstftArgs a,
   const bool streaming = a.mode == DS_STFT_STREAMING;
 
   auto inverse = [&](int t) {          // frame t -> buf holds irfft * N
-    const long long ibase = (((long long)s * a.T + t) * a.C + c) * K;
+    const long long ibase = (long long)s * a.sS + (long long)t * a.sT + (long long)c * a.sC;
     if (a.in_c128) {
       const double2 *in = reinterpret_cast<const double2 *>(a.Y) + ibase;
-      for (int k = lane; k < K; k += 32) { const double2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
+      for (int k = lane; k < K; k += 32) { const double2 v = in[k * a.sK]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
     } else {
       const float2 *in = reinterpret_cast<const float2 *>(a.Y) + ibase;
-      for (int k = lane; k < K; k += 32) { const float2 v = in[k]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
+      for (int k = lane; k < K; k += 32) { const float2 v = in[k * a.sK]; buf[FPAD<T>(k)] = mk2<T>((T)v.x, (T)v.y); }
     }
     __syncwarp();
     warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
@@ -870,7 +871,7 @@ int ds_stft_pcm16_run(const ds_stft_params *p, const double *window, float *hist
 }
 
 static int istft_run_impl(const ds_istft_params *p, const double *window, float *tail, const void *Y, float *y, short *y16,
-                          void *stream) {
+                          void *stream, long long frame_pitch = 0) {
   DS_CHECK_ARG(p && window && Y && (y || y16), "ds_istft_run: null argument");
   DS_CHECK_ARG(p->hop >= 1 && p->hop <= p->n_fft, "ds_istft_run: hop %d out of range", p->hop);
   DS_CHECK_ARG(p->n_streams >= 1 && p->n_ch >= 1 && p->n_frames >= 1, "ds_istft_run: bad shape");
@@ -884,8 +885,20 @@ static int istft_run_impl(const ds_istft_params *p, const double *window, float 
   a.S = p->n_streams; a.C = p->n_ch; a.T = p->n_frames; a.hop = p->hop; a.mode = p->mode;
   a.n_out = (p->mode == DS_STFT_STREAMING) ? p->n_frames * p->hop : p->n_fft + p->hop * (p->n_frames - 1);
   a.scale = p->scale;
+  const long long K = p->n_fft / 2 + 1;
+  if (frame_pitch > 0) {       // [S][C][K][frame_pitch]: frames innermost (the tensor-core multi-beam kernel's output)
+    a.sK = frame_pitch; a.sT = 1; a.sC = K * frame_pitch; a.sS = (long long)a.C * K * frame_pitch;
+  } else {                     // [S][T][C][K]
+    a.sK = 1; a.sC = K; a.sT = (long long)a.C * K; a.sS = (long long)a.T * a.C * K;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   return p->fft_fp64 ? dispatch_istft<double>(p->n_fft, a, tw, st) : dispatch_istft<float>(p->n_fft, a, tw, st);
+}
+
+int ds_istft_frames_inner_run(const ds_istft_params *p, const double *window, float *tail, const void *Y, long long frame_pitch,
+                              float *y, void *stream) {
+  DS_CHECK_ARG(y && p && frame_pitch >= p->n_frames, "ds_istft_frames_inner_run: bad argument");
+  return istft_run_impl(p, window, tail, Y, y, nullptr, stream, frame_pitch);
 }
 
 int ds_istft_run(const ds_istft_params *p, const double *window, float *tail, const void *Y, float *y, void *stream) {

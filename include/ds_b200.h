@@ -125,6 +125,10 @@ int ds_istft_run(const ds_istft_params *p, const double *window, float *tail,
  * into the synthesis kernel's store.                                             */
 int ds_istft_pcm16_run(const ds_istft_params *p, const double *window, float *tail,
                        const void *Y, int16_t *y_pcm, void *stream);
+/* Same synthesis reading Y in the layout [S][C][K][frame_pitch] (frame index innermost, frame_pitch >= T) -- what the
+ * tensor-core multi-beam kernel (ds_multibeam_tc_run) writes.                                                    */
+int ds_istft_frames_inner_run(const ds_istft_params *p, const double *window, float *tail,
+                              const void *Y, long long frame_pitch, float *y, void *stream);
 
 /* ---- fixed beamformer (beamformer/fixedbeamformer.py) ----------------- */
 typedef struct ds_fixedbf_params {
@@ -307,6 +311,20 @@ int ds_mcspp_cdr_run(const ds_mcspp_cdr_params *p, void *state, void *workspace,
  * Pxii[M] Re Pxij[NQ] Im Pxij[NQ] (NQ = M(M-1)/2 pairs, i < j row-major); 7 [S][6][K] MCRA S Smin Stmp p
  * lambda_d, posterior p                                                             */
 int ds_mcspp_cdr_export(const ds_mcspp_cdr_params *p, const void *state, int field, void *out, void *stream);
+
+/* ---- multi-beam fixed / superdirective weighting on the tensor cores (beamformer/fixedbeamformer.py) ---------- */
+/* replaces, for n_beams look directions at once, the per-frame weighting of FixedBeamformer.process_freframe
+ * (fixedbeamformer.py:147-165, einsum 'ij,ij->i' of conj(W) and X; weights from compute_weights :109-145):
+ *   Y[s][b][k][t] = sum_m conj(W[b][k][m]) X[s][t][m][k]
+ * as per-bin real GEMMs [128 beams x 6M] . [6M x 2*64 frames] on tcgen05 (kind::tf32, operands split into tf32 head +
+ * tail so the result is fp32-accurate), accumulators in tensor memory, operand tiles streamed with cp.async.bulk.
+ *   W [n_beams][K][M] c64, X [S][T][M][K] c64 (ds_stft_run's layout), n_mics in {4, 8, 16}
+ *   Y [S][n_beams][K][frame_pitch] c64 (frame index innermost; feed it to ds_istft_frames_inner_run)
+ *   workspace: scratch for the packed operand tiles, 128-byte aligned; sizes from ds_multibeam_tc_layout.        */
+int ds_multibeam_tc_layout(int n_streams, int n_frames, int n_mics, int n_bins, int n_beams, int *frame_pitch,
+                           size_t *workspace_bytes, size_t *y_bytes);
+int ds_multibeam_tc_run(int n_streams, int n_frames, int n_mics, int n_bins, int n_beams, const void *W, const void *X,
+                        void *workspace, void *Y, void *stream);
 
 /* ---- adaptive (RLS) WPE dereverberation (dereverberation/awpe.py) ----------------------------- */
 /* state blob [S][NE][K] float64 (NE from ds_wpe_state_bytes): W re/im [C][C L], P re/im [C L][C L], the last

@@ -315,3 +315,38 @@ def test_fdgsc_pipeline_batch_device_entry_gpu(cuda):
             ref = O.FdgscOracle(geo, 256, np.array([look, 0]) / 180 * np.pi).process(xs[s].T.astype(np.float64))
             assert_wave_parity(ref[0], y[s], "FDGSC pipeline M=%d stream %d" % (M, s))
             assert np.max(np.abs(xd[s].cpu().numpy().T - ref[4])) < 1e-6      # the caller's tensor holds the notched signal
+
+
+# ---------------------------------------------------------------- n1: multi-beam weighting on the tensor cores
+@pytest.mark.parametrize("M,B,weight", [(8, 64, "SD"), (4, 16, "DS"), (16, 130, "SD")])
+def test_multibeam_tensor_core_gpu(cuda, M, B, weight):
+    """FixedBeamformer.process_multibeam(engine="tensor"): per-bin GEMMs on tcgen05 (tf32 head + tail operands) against
+    O.fixed_beamform per beam (fixedbeamformer.py:109-165), against the CUDA-core path, and chunked == one call."""
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.fixedbeamformer import FixedBeamformer
+    geo = O.MicGeometry("circular", r=0.05, M=M, n_fft=512)
+    xs = O.synth_streams(3, geo, 256 * 70, seed0=0x4B + M)
+    x_nm = np.ascontiguousarray(xs.transpose(0, 2, 1))                    # [S, N, M]
+    mic = MicArray(arrayType="circular", r=0.05, M=M, n_fft=512)
+    angles = [(int(a), 0) for a in np.linspace(0, 359, B)]
+    fb = FixedBeamformer(mic, 512, 256, 512)
+    y = fb.process_multibeam(x_nm, angles, weightType=weight, engine="tensor")
+    assert y.shape == (3, B, 256 * 70)
+    worst = 1e9
+    for s, b in ((0, 0), (1, B // 2), (2, B - 1), (0, B // 3)):
+        W = O.fixed_weights(geo, 512, angles[b], weight)
+        ref = O.fixed_beamform(x_nm[s].astype(np.float64), W, 512, 256)
+        err, snr = assert_wave_parity(ref, y[s, b], "tensor-core beam %d of stream %d" % (b, s))
+        worst = min(worst, snr)
+    print("multi-beam tcgen05 M=%d B=%d: worst SNR vs oracle %.1f dB" % (M, B, worst))
+    assert worst >= 100.0                                                 # head + tail operands: fp32-level accuracy, not tf32's ~70 dB
+    if B <= 16:                                                           # the fused CUDA-core kernel holds every beam in shared memory
+        ys = FixedBeamformer(mic, 512, 256, 512).process_multibeam(x_nm, angles, weightType=weight, engine="simt")
+        assert np.max(np.abs(ys - y)) < 2e-6
+    fb2 = FixedBeamformer(mic, 512, 256, 512)
+    ya = fb2.process_multibeam(x_nm[:, :256 * 30], angles, weightType=weight, engine="tensor")
+    yb = fb2.process_multibeam(x_nm[:, 256 * 30:], angles, weightType=weight, engine="tensor")
+    assert np.max(np.abs(np.concatenate([ya, yb], axis=2) - y)) < 1e-6
+    with pytest.raises(ValueError):
+        FixedBeamformer(MicArray(arrayType="circular", r=0.05, M=6, n_fft=512), 512, 256, 512).process_multibeam(
+            x_nm[:, :, :6], angles, engine="tensor")
