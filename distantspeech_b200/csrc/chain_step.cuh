@@ -140,7 +140,14 @@ __device__ __forceinline__ void mcra_step_sel(McraRegs &m, double Ym1, double Y0
 // A but not u, pass Z needs u but not A, the updated Phi_yy' takes over A's registers element by
 // element, and Phi_vv is read once per frame less -- the fused loop this replaces had ~200 live
 // registers and ran its nine-operation chain per element almost serially (8-cycle DFMA latency).
-template <int M, int NT, bool USE_C>
+// MIXED (A/B experiment, compiled in only with -DDS_CHAIN_MIXED): u = A y, tr(A Phi_yy') and the quadratic form of gamma on
+// the otherwise idle fp32 pipe from float copies of A and Phi_yy' (288 fewer fp64 instructions per bin and frame); the sweep
+// inverse, both covariance recursions, the MCRA / SPP chain and the MVDR numerator / denominator stay in fp64.  MEASURED
+// (round 2, B200, 1024 streams x 10 s): 22.67 ms per step against 22.25 ms -- SLOWER: the 88 float<->double conversions
+// it needs cost more than the 288 DFMA it saves -- and less accurate: 100 dB instead of 108 dB on the synthetic streams,
+// 46 dB (below the 60 dB contract) when Phi_vv is close to singular, because xi and gamma are differences of nearly equal
+// sums (tools/mixed_precision_study.py).  Kept only so the measurement can be repeated.
+template <int M, int NT, bool USE_C, bool MIXED = false>
 __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 ynb0, float2 ynb1, int k, int K, int frm,
                                                  bool reset, McraRegs &mc, double *smy, double *smv, const double *smc,
                                                  const double *a0, const McsppArgs &a, double &p_post) {
@@ -205,6 +212,24 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
 #pragma unroll
     for (int m = 0; m < M; ++m) { a0r[m] = ld_f64_once(a0 + 2 * m * K); a0i[m] = ld_f64_once(a0 + 2 * m * K + 1); }
 #endif
+    float Af[MIXED ? NP : 1], urf[MIXED ? M : 1], uif[MIXED ? M : 1];
+    if constexpr (MIXED) {
+#pragma unroll
+      for (int e = 0; e < NP; ++e) Af[e] = (float)A[e];
+#define ASF(i, j) (((i) <= (j)) ? Af[pidx<M>(i, j)] : Af[pidx<M>(j, i)])
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        float sr = 0.f, sr2 = 0.f, si = 0.f, si2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          if (j & 1) { sr2 = fmaf(ASF(i, j), yf[j].x, sr2); si2 = fmaf(ASF(i, j), yf[j].y, si2); }
+          else { sr = fmaf(ASF(i, j), yf[j].x, sr); si = fmaf(ASF(i, j), yf[j].y, si); }
+        }
+        urf[i] = sr + sr2; uif[i] = si + si2;
+        ur[i] = (double)urf[i]; ui[i] = (double)uif[i];
+      }
+#undef ASF
+    } else {
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       double sr = 0.0, sr2 = 0.0, si = 0.0, si2 = 0.0;
@@ -215,6 +240,7 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
       }
       ur[i] = sr + sr2;
       ui[i] = si + si2;
+    }
     }
     double Yr = 0.0, Yi = 0.0, Yr2 = 0.0, Yi2 = 0.0, syu = 0.0, syu2 = 0.0, uu = 0.0, uu2 = 0.0;
 #pragma unroll
@@ -234,6 +260,7 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
     // ---- pass X: Phi_yy' = alpha Phi_yy + (1 - alpha) Re(y y^H), tr(A Phi_yy'); Phi_yy' replaces A   :84-90, :280
     const double alpha = a.alpha, one_m_alpha = 1.0 - a.alpha;
     double trd[2] = {0.0, 0.0}, tro[4] = {0.0, 0.0, 0.0, 0.0};
+    float trdf[2] = {0.f, 0.f}, trof[4] = {0.f, 0.f, 0.f, 0.f}, gmdf[2] = {0.f, 0.f}, gmof[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       const double tr_i = one_m_alpha * yr[i], ti_i = one_m_alpha * yi[i];
@@ -242,14 +269,28 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
         const int e = pidx<M>(i, j);
         const double pyy = fma(tr_i, yr[j], fma(ti_i, yi[j], alpha * smy[e * NT]));
         smy[e * NT] = pyy;
-        if (i == j) trd[i & 1] = fma(A[e], pyy, trd[i & 1]);
-        else tro[e & 3] = fma(A[e], pyy, tro[e & 3]);
-        A[e] = pyy;
+        if constexpr (MIXED) {
+          // trace term and (pass Z fused here) the quadratic-form term of gamma, both on the fp32 pipe
+          const float pf32 = (float)pyy;
+          const float z = fmaf(uif[i], uif[j], urf[i] * urf[j]);
+          if (i == j) { trdf[i & 1] = fmaf(Af[e], pf32, trdf[i & 1]); gmdf[i & 1] = fmaf(pf32, z, gmdf[i & 1]); }
+          else { trof[e & 3] = fmaf(Af[e], pf32, trof[e & 3]); gmof[e & 3] = fmaf(pf32, z, gmof[e & 3]); }
+        } else {
+          if (i == j) trd[i & 1] = fma(A[e], pyy, trd[i & 1]);
+          else tro[e & 3] = fma(A[e], pyy, tro[e & 3]);
+          A[e] = pyy;
+        }
       }
     }
 #undef AS
     // ---- pass Z: sum_ij Phi_yy'_ij Re(conj(u_i) u_j)
     double gmd[2] = {0.0, 0.0}, gmo[4] = {0.0, 0.0, 0.0, 0.0};
+    if constexpr (MIXED) {
+      trd[0] = (double)(trdf[0] + trdf[1]); trd[1] = 0.0;
+      tro[0] = (double)((trof[0] + trof[1]) + (trof[2] + trof[3])); tro[1] = tro[2] = tro[3] = 0.0;
+      gmd[0] = (double)(gmdf[0] + gmdf[1]);
+      gmo[0] = (double)((gmof[0] + gmof[1]) + (gmof[2] + gmof[3]));
+    } else {
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -259,6 +300,7 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
         if (i == j) gmd[i & 1] = fma(A[e], z, gmd[i & 1]);
         else gmo[e & 3] = fma(A[e], z, gmo[e & 3]);
       }
+    }
     double xi = fma(2.0, (tro[0] + tro[1]) + (tro[2] + tro[3]), trd[0] + trd[1]);
     xi = fma(a.eps, trA, xi - (double)M);
     double gam = fma(2.0, (gmo[0] + gmo[1]) + (gmo[2] + gmo[3]), gmd[0] + gmd[1]);

@@ -372,11 +372,12 @@ int mcspp_run_impl(const ds_mcspp_params *p, void *state, const void *a0, const 
   a.tAinv = taps ? taps->Phi_vv_inv_last : nullptr;
   const bool any_tap = a.tp || a.txi || a.tgamma || a.tq || a.tG || a.tw_mvdr || a.tw_pmwf || a.tAinv;
   // output-only mode may skip bins 0 and 1 (their gain is identically 0)
-  a.k_first = (!p->full_state && apply_gain && a0 && Yout && !any_tap) ? 2 : 0;
+  const bool full = p->full_state != 0;
+  a.k_first = (!full && apply_gain && a0 && Yout && !any_tap) ? 2 : 0;
   // the output-only kernel also serves the p tap alone (it then has to visit every bin)
   const bool only_p = a.tp && !(a.txi || a.tgamma || a.tq || a.tG || a.tw_mvdr || a.tw_pmwf || a.tAinv);
-  if (!p->full_state && a0 && Yout && (!any_tap || only_p) && !x_is_c128) return launch_mcspp_fast(p->n_mics, a, st);
-  return launch_mcspp(p->n_mics, a, p->full_state != 0, x_is_c128 != 0, st);
+  if (!full && a0 && Yout && (!any_tap || only_p) && !x_is_c128) return launch_mcspp_fast(p->n_mics, a, st);
+  return launch_mcspp(p->n_mics, a, full, x_is_c128 != 0, st);
 }
 
 }  // namespace ds

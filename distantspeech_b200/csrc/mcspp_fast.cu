@@ -29,7 +29,7 @@ namespace ds {
 
 // TAP_P: also write the posterior p per frame (the mask of the mask-based beamformers); a separate instantiation,
 // because even a predicated-off store costs the headline kernel 2 % (registers: 16.84 -> 17.17 ms measured)
-template <int M, int NT, int MINB, bool TAP_P>
+template <int M, int NT, int MINB, bool TAP_P, bool MIXED = false>
 __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
   constexpr bool USE_C = DS_FAST_USE_C != 0;
   constexpr int NP = M * (M + 1) / 2;
@@ -103,7 +103,7 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
     }
     const bool reset = (frm > 0) && (ell_mod == 0);
     double p_post;
-    *Yp = chain_bin_step<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
+    *Yp = chain_bin_step<M, NT, USE_C, MIXED>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
     if constexpr (TAP_P) a.tp[((long long)s * a.T + t) * K + k] = p_post;     // the only tap this kernel serves
     if (reset) ell = 0;
     ++ell; ++frm;
@@ -128,7 +128,11 @@ static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
   constexpr int NP = M * (M + 1) / 2;
   constexpr int MINB = DS_FAST_MINB; // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
   const size_t smem = (size_t)(DS_FAST_USE_C ? 3 : 2) * NP * NT * sizeof(double);
+#ifdef DS_CHAIN_MIXED      // A/B build only (tools/build_variant.sh x mcspp_fast.cu -DDS_CHAIN_MIXED): see chain_step.cuh
+  auto kern = a.tp ? mcspp_fast_kernel<M, NT, MINB, true> : mcspp_fast_kernel<M, NT, MINB, false, true>;
+#else
   auto kern = a.tp ? mcspp_fast_kernel<M, NT, MINB, true> : mcspp_fast_kernel<M, NT, MINB, false>;
+#endif
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)a.S * (a.K - a.k_first);
   kern<<<(unsigned)((items + NT - 1) / NT), NT, smem, st>>>(a);

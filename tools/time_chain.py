@@ -21,4 +21,4 @@ for _ in range(4):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); ch.process_device(x, out=y); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
-print(os.environ.get("DS_B200_LIB", "default"), os.environ.get("DS_CHAIN_FUSED", "-"), "ms:", " ".join("%.2f" % t for t in ts), "finite" if torch.isfinite(y).all().item() else "nonfinite")
+print(os.environ.get("DS_B200_LIB", "default"), os.environ.get("PRECISION", "f64"), "ms:", " ".join("%.2f" % t for t in ts), "finite" if torch.isfinite(y).all().item() else "nonfinite")
