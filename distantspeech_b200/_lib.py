@@ -267,6 +267,7 @@ def _declare(lib):
     lib.ds_wpe_state_bytes.argtypes = [i32, i32, i32, i32, i32]
     lib.ds_wpe_state_bytes.restype = C.c_size_t
     lib.ds_wpe_run.argtypes = [i32, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, i32, vp, vp]
+    lib.ds_memcpy2d_async.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, i32, vp]
     lib.ds_fp64_peak_run.argtypes = [i32, vp, vp]
     lib.ds_fp64_peak_run.restype = C.c_double
     lib.ds_double_to_pcm16_run.argtypes = [C.c_size_t, vp, vp, vp]

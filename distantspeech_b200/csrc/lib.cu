@@ -111,6 +111,17 @@ double ds_fp64_peak_run(int iters, double *scratch, void *stream) {
   return 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
 }
 
+// Strided host <-> device copy on `stream` (cudaMemcpy2DAsync): `height` rows of `width` bytes, pitches in bytes.
+// kind: 0 host -> device, 1 device -> host.  Used by the host-buffer pipelines to move a TIME SLICE of every stream
+// ([S][M][N] rows) with one DMA request.
+int ds_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int kind, void *stream) {
+  DS_CHECK_ARG(dst && src && width <= dpitch && width <= spitch && (kind == 0 || kind == 1), "ds_memcpy2d_async: bad argument");
+  if (width == 0 || height == 0) return DS_OK;
+  DS_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                            (cudaStream_t)stream));
+  return DS_OK;
+}
+
 int ds_version(void) { return DS_VERSION; }
 
 const char *ds_last_error(void) { return ds::g_err; }

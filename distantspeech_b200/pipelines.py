@@ -65,9 +65,10 @@ class MvdrMcsppChain(object):
             self._state = t.zeros(L.lib().ds_chain_state_bytes(C.byref(p)), dtype=t.uint8, device="cuda")
             self.frm_cnt, self.ell = 0, 1
             p = self._params(S, N)
-        if self._ws is None or self._key != (S, N):
+        need = L.lib().ds_chain_workspace_bytes(C.byref(p))
+        if self._ws is None or self._ws.numel() < need or self._ws.device.index != t.cuda.current_device():
             self._ws = None
-            self._ws = t.empty(L.lib().ds_chain_workspace_bytes(C.byref(p)), dtype=t.uint8, device="cuda")
+            self._ws = t.empty(need, dtype=t.uint8, device="cuda")
         self._key = (S, N)
         if self._a0_dev is None or self._a0_dev.device.index != t.cuda.current_device():
             self._a0_dev = t.as_tensor(np.ascontiguousarray(self.a0.T)).to("cuda")     # [M, K] complex128
@@ -139,75 +140,90 @@ class MvdrMcsppChain(object):
         return y if as_torch else y.double().cpu().numpy()
 
     # ------------------------------------------------------------------
-    def _host_pipeline(self, cs, M, N, in_dtype, out_dtype):
-        """Streams, events, staging buffers and per-slot chain objects of process_host, created once per
-        (group size, shape, dtypes) and kept for the life of the object."""
+    def _host_pipeline(self, S, M, n_slice, in_dtype, out_dtype):
+        """Streams, events, staging buffers and the chain object that owns the batch's recursive state for process_host,
+        created once per (batch, slice, dtypes) and kept for the life of the object."""
         t = L.require_cuda()
-        key = (cs, M, N, in_dtype, out_dtype, t.cuda.current_device())
+        key = (S, M, n_slice, in_dtype, out_dtype, t.cuda.current_device())
         hp = getattr(self, "_hp", None)
         if hp is not None and hp["key"] == key:
             return hp
-        sub = MvdrMcsppChain.__new__(MvdrMcsppChain)        # the groups' own recursive state, separate from process()'s
+        sub = MvdrMcsppChain.__new__(MvdrMcsppChain)        # the batch's own recursive state, separate from process()'s
         sub.__dict__.update(self.__dict__)
         sub._state = sub._ws = sub._key = sub._hp = None
         hp = {"key": key, "s_in": t.cuda.Stream(), "s_out": t.cuda.Stream(),
-              "xbuf": [t.empty((cs, M, N), dtype=in_dtype, device="cuda") for _ in range(2)],
-              "ybuf": [t.empty((cs, N), dtype=out_dtype, device="cuda") for _ in range(2)],
+              "xbuf": [t.empty((S, M, n_slice), dtype=in_dtype, device="cuda") for _ in range(2)],
+              "ybuf": [t.empty((S, n_slice), dtype=out_dtype, device="cuda") for _ in range(2)],
               "ev_in": [t.cuda.Event() for _ in range(2)], "ev_done": [t.cuda.Event() for _ in range(2)],
               "ev_out": [t.cuda.Event() for _ in range(2)], "sub": sub}
         self._hp = hp
         return hp
 
-    def process_host(self, x_host, y_host=None, chunk_streams=128):
+    @staticmethod
+    def _slices(T, slice_frames):
+        """Frame ranges of the time slices: equal slices, then a short last one so that the pipeline drains quickly."""
+        out, lo = [], 0
+        while lo < T:
+            n = min(slice_frames, T - lo)
+            if T - lo - n == 0 and n > max(4, slice_frames // 4) and len(out) > 0:
+                n = n - max(4, slice_frames // 4)          # split the final slice: big part + short tail
+            out.append((lo, lo + n))
+            lo += n
+        return out
+
+    def process_host(self, x_host, y_host=None, slice_frames=16):
         """End-to-end call with HOST buffers: x_host [S, M, N] float32 or int16 PCM (the reference's on-disk
         format; scaled exactly like load_audio, float32(pcm) / 32767, utils.py:184-185) -> y_host [S, N] float32,
         or int16 PCM when an int16 ``y_host`` is handed in (save_audio's (audio * 32767).astype(int16), utils.py:193).
         Pinned buffers for speed.  Both conversions run inside the analysis / synthesis kernels: int16 samples are
-        what crosses PCIe and what the kernels read and write.  Streams are independent, so the batch is cut into
-        groups of ``chunk_streams`` and H2D copy / kernels / D2H copy of consecutive groups overlap on three CUDA
-        streams (staging buffers, streams and events are created once per object).  Each group is a fresh utterance
-        (state reset)."""
+        what crosses PCIe and what the kernels read and write.
+
+        The batch is cut along TIME: slice j of every stream ([S, M, slice] -- one strided DMA request) is copied in
+        while the kernels work on slice j - 1 with the recursive state carried on the device (chunked streaming is
+        bit-identical to one call) and slice j - 2 is copied out, on three CUDA streams.  Every kernel launch sees the
+        whole batch (full occupancy) and the pipeline drains in the time of one short last slice, so the call runs at
+        the pace of the host-to-device copy.  Each call is a fresh utterance (state reset)."""
         t = L.require_cuda()
-        if x_host.dim() != 3 or x_host.dtype not in (t.float32, t.int16):
-            raise ValueError("x_host must be [S, M, N] float32 or int16")
+        if x_host.dim() != 3 or x_host.dtype not in (t.float32, t.int16) or not x_host.is_contiguous():
+            raise ValueError("x_host must be a contiguous [S, M, N] float32 or int16 tensor")
         S, M, N = x_host.shape
         if M != self.M or N % self.hop != 0 or N < self.hop:
             raise ValueError("expected [S, %d, N] with N a positive multiple of hop=%d" % (self.M, self.hop))
         if y_host is None:
             y_host = t.empty((S, N), dtype=t.float32, pin_memory=True)
-        if tuple(y_host.shape) != (S, N) or y_host.dtype not in (t.float32, t.int16):
-            raise ValueError("y_host must be [S, N] float32 or int16")
-        cs = min(chunk_streams, S)
-        n_chunks = (S + cs - 1) // cs
-        hp = self._host_pipeline(cs, M, N, x_host.dtype, y_host.dtype)
+        if tuple(y_host.shape) != (S, N) or y_host.dtype not in (t.float32, t.int16) or not y_host.is_contiguous():
+            raise ValueError("y_host must be a contiguous [S, N] float32 or int16 tensor")
+        slices = self._slices(N // self.hop, max(1, int(slice_frames)))
+        n_max = max(b - a for a, b in slices) * self.hop
+        hp = self._host_pipeline(S, M, n_max, x_host.dtype, y_host.dtype)
         cur = t.cuda.current_stream()
         s_in, s_out, xbuf, ybuf = hp["s_in"], hp["s_out"], hp["xbuf"], hp["ybuf"]
         ev_in, ev_done, ev_out, sub = hp["ev_in"], hp["ev_done"], hp["ev_out"], hp["sub"]
+        xe, ye = x_host.element_size(), y_host.element_size()
+        lib = L.lib()
         s_in.wait_stream(cur)
-        for c in range(n_chunks):
+        sub.reset_counters()
+        if sub._state is not None:
+            sub._state.zero_()
+        for c, (f0, f1) in enumerate(slices):
             b = c & 1
-            lo, hi = c * cs, min(S, (c + 1) * cs)
-            n = hi - lo
-            with t.cuda.stream(s_in):
-                if c >= 2:
-                    s_in.wait_event(ev_done[b])          # kernels of chunk c-2 finished reading xbuf[b]
-                xbuf[b][:n].copy_(x_host[lo:hi], non_blocking=True)
-                ev_in[b].record(s_in)
+            n0, n = f0 * self.hop, (f1 - f0) * self.hop
+            xs = xbuf[b].view(-1)[:S * M * n].view(S, M, n)          # a dense [S, M, n] view of the staging buffer
+            ys = ybuf[b].view(-1)[:S * n].view(S, n)
+            if c >= 2:
+                s_in.wait_event(ev_done[b])              # kernels of slice c-2 finished reading xbuf[b]
+            L.check(lib.ds_memcpy2d_async(xs.data_ptr(), n * xe, x_host.data_ptr() + n0 * xe, N * xe, n * xe, S * M, 0,
+                                          s_in.cuda_stream), "ds_memcpy2d_async")
+            ev_in[b].record(s_in)
             cur.wait_event(ev_in[b])
             if c >= 2:
-                cur.wait_event(ev_out[b])                # D2H of chunk c-2 finished reading ybuf[b]
-            if sub._key is not None and sub._key[0] != n:
-                sub._state = None                        # ragged last group: state blob of its own size
-                sub._key = None
-            sub.reset_counters()
-            if sub._state is not None:
-                sub._state.zero_()
-            sub.process_device(xbuf[b][:n], out=ybuf[b][:n])
+                cur.wait_event(ev_out[b])                # D2H of slice c-2 finished reading ybuf[b]
+            sub.process_device(xs, out=ys)               # state carries over from slice to slice
             ev_done[b].record(cur)
-            with t.cuda.stream(s_out):
-                s_out.wait_event(ev_done[b])
-                y_host[lo:hi].copy_(ybuf[b][:n], non_blocking=True)
-                ev_out[b].record(s_out)
+            s_out.wait_event(ev_done[b])
+            L.check(lib.ds_memcpy2d_async(y_host.data_ptr() + n0 * ye, N * ye, ys.data_ptr(), n * ye, n * ye, S, 1,
+                                          s_out.cuda_stream), "ds_memcpy2d_async")
+            ev_out[b].record(s_out)
         s_out.synchronize()
         cur.synchronize()
         return y_host

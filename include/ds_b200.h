@@ -57,6 +57,11 @@ const char *ds_last_error(void);
 int ds_init(void);
 /* SM count and compute capability of the current device. */
 int ds_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* Strided host <-> device copy on `stream` (cudaMemcpy2DAsync): `height` rows of `width` bytes; kind 0 = host to device,
+ * 1 = device to host.  The host-buffer pipelines move a time slice of every stream with it (no reference counterpart:
+ * the reference has no device).                                                                                  */
+int ds_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int kind,
+                      void *stream);
 /* fp64-pipe microbenchmark (8 independent DFMA chains per thread, 2 x 1024 threads per SM): launches on `stream`
  * and returns the floating-point operations executed (0 on error); the caller times it with CUDA events.  It is the
  * measured denominator of roofline.fp64_pipe in bench.py (no reference counterpart: measurement infrastructure). */

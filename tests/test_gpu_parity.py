@@ -277,7 +277,7 @@ def test_chain_batch_and_streaming(cuda):
     assert np.array_equal(yc, y)
     # host-buffer pipeline == device path
     import torch
-    yh = ch.process_host(torch.from_numpy(xs).pin_memory(), chunk_streams=3)
+    yh = ch.process_host(torch.from_numpy(xs).pin_memory(), slice_frames=7)
     assert np.max(np.abs(yh.numpy() - y)) < 1e-6
 
 
@@ -569,7 +569,7 @@ def test_pcm16_ingest_matches_load_audio(cuda):
     xi = np.round(xs * 32767).astype(np.int16)
     mic = MicArray(arrayType="circular", r=0.05, M=8, n_fft=512)
     ch = MvdrMcsppChain(mic, look_angle=(30, 0))
-    y_pcm = ch.process_host(torch.from_numpy(xi).pin_memory(), chunk_streams=2).numpy().copy()
+    y_pcm = ch.process_host(torch.from_numpy(xi).pin_memory(), slice_frames=9).numpy().copy()
     xf = xi.astype(np.float32) / 32767.0
     ref0 = O.mvdr_mcspp_chain(xf[0].T.astype(np.float64), geo, (30, 0), 512, 256)
     assert_wave_parity(ref0, y_pcm[0], "pcm16 chain")

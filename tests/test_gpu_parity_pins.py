@@ -139,9 +139,9 @@ def test_chain_pcm16_in_and_out(cuda):
     ch = MvdrMcsppChain(mic, look_angle=(30, 0))
     y_host = torch.empty((5, 256 * 40), dtype=torch.int16).pin_memory()
     for _ in range(2):                                                   # second call reuses the staging pipeline
-        ch.process_host(torch.from_numpy(xi).pin_memory(), y_host, chunk_streams=2)
+        ch.process_host(torch.from_numpy(xi).pin_memory(), y_host, slice_frames=11)
         assert np.array_equal(y_host.numpy(), q)
-    yh32 = ch.process_host(torch.from_numpy(xi).pin_memory(), chunk_streams=2)         # int16 in, float32 out
+    yh32 = ch.process_host(torch.from_numpy(xi).pin_memory(), slice_frames=40)         # int16 in, float32 out
     assert np.array_equal(yh32.numpy(), yf.cpu().numpy())
     ref0 = O.mvdr_mcspp_chain(xf[3].T.astype(np.float64), geo, (30, 0), 512, 256)
     assert_wave_parity(ref0, yf[3].cpu().numpy(), "pcm16 chain (float out)")
