@@ -208,29 +208,75 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32) fd_spec_kernel(Fd2Args a, con
   if (item >= (long long)a.S * a.nblk) return;
   const int s = (int)(item / a.nblk), b = (int)(item % a.nblk);
 #define FIDX(n) (2 * FPAD<T>((n) >> 1) + ((n) & 1))
+  typedef FftFirst<H, T> F1;                           // first radix-8 pass fed from registers (coalesced 8-byte global loads)
   // X_f = rfft([fbf_prev | fbf]): 512 contiguous samples of the extended buffer
   const T *F = reinterpret_cast<const T *>(a.ws + w.F) + (size_t)s * (L + a.Ns) + (size_t)b * L;
-  for (int n = lane; n < N; n += 32) fb[FIDX(n)] = F[n];
-  __syncwarp();
-  warp_rfft<N, T>(buf, tw_h, tw_n, lane);
+  {
+    C2 v[F1::PER][F1::R];
+    const C2 *src = reinterpret_cast<const C2 *>(F);
+#pragma unroll
+    for (int i = 0; i < F1::PER; ++i)
+#pragma unroll
+      for (int r = 0; r < F1::R; ++r) v[i][r] = src[lane + 32 * i + r * F1::NB];
+    F1::run(v, buf, tw_h, lane);
+  }
   C2 *Xf = reinterpret_cast<C2 *>(a.ws + w.Xf) + ((size_t)s * a.nblk + b) * K;
-  for (int k = lane; k < K; k += 32) Xf[k] = buf[FPAD<T>(k)];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {                        // real-FFT split straight to global memory
+    const int k = lane + 32 * i;
+    if (k <= H / 2) {
+      if (k == 0) {
+        const C2 z = buf[FPAD<T>(0)];
+        Xf[0] = mk2<T>(z.x + z.y, (T)0); Xf[H] = mk2<T>(z.x - z.y, (T)0);
+      } else {
+        C2 x1, x2;
+        rfft_split_pair<T, C2>(buf[FPAD<T>(k)], buf[FPAD<T>(H - k)], tw_n[k], x1, x2);
+        Xf[k] = x1; Xf[H - k] = x2;
+      }
+    }
+  }
   __syncwarp();
   // |rfft(window * [x0_prev | x0])|^2 with the reference's complex64 rounding (transform.py:212)
   const float *x0 = a.x + (size_t)s * a.M * a.Ns;
   const double *st = a.state + (size_t)s * so.total;
-  for (int n = lane; n < N; n += 32) {
-    const int g = (b - 1) * L + n;
-    const T v = (g >= 0) ? (T)x0[g] : (T)st[so.x0_prev + n];
-    fb[FIDX(n)] = v * win[n];
+  if (b >= 1) {
+    C2 v[F1::PER][F1::R];
+    const float2 *src = reinterpret_cast<const float2 *>(x0 + (size_t)(b - 1) * L);
+    const C2 *w2 = reinterpret_cast<const C2 *>(win);
+#pragma unroll
+    for (int i = 0; i < F1::PER; ++i)
+#pragma unroll
+      for (int r = 0; r < F1::R; ++r) {
+        const int e = lane + 32 * i + r * F1::NB;
+        const float2 xv = src[e];
+        const C2 wv = w2[e];
+        v[i][r] = mk2<T>(mul_rn((T)xv.x, wv.x), mul_rn((T)xv.y, wv.y));      // rounded on its own, like the staged path
+      }
+    F1::run(v, buf, tw_h, lane);
+  } else {
+    for (int n = lane; n < N; n += 32) {
+      const int g = (b - 1) * L + n;
+      const T xv = (g >= 0) ? (T)x0[g] : (T)st[so.x0_prev + n];
+      fb[FIDX(n)] = mul_rn(xv, win[n]);
+    }
+    __syncwarp();
+    warp_cfft<H, T>(buf, tw_h, lane);
   }
-  __syncwarp();
-  warp_rfft<N, T>(buf, tw_h, tw_n, lane);
   double *P0 = reinterpret_cast<double *>(a.ws + w.P0) + ((size_t)s * a.nblk + b) * K;
-  for (int k = lane; k < K; k += 32) {
-    const C2 v = buf[FPAD<T>(k)];
-    const double re = (double)(float)v.x, im = (double)(float)v.y;
-    P0[k] = re * re + im * im;
+  auto pw = [](C2 v) { const double re = (double)(float)v.x, im = (double)(float)v.y; return re * re + im * im; };
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int k = lane + 32 * i;
+    if (k <= H / 2) {
+      if (k == 0) {
+        const C2 z = buf[FPAD<T>(0)];
+        P0[0] = pw(mk2<T>(z.x + z.y, (T)0)); P0[H] = pw(mk2<T>(z.x - z.y, (T)0));
+      } else {
+        C2 x1, x2;
+        rfft_split_pair<T, C2>(buf[FPAD<T>(k)], buf[FPAD<T>(H - k)], tw_n[k], x1, x2);
+        P0[k] = pw(x1); P0[H - k] = pw(x2);
+      }
+    }
   }
 #undef FIDX
 }
@@ -346,15 +392,34 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
       if (lane * 128 < (int)(K * sizeof(T))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + lane * 128));
       if (lane * 128 < (int)(L * sizeof(T))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + lane * 128));
     }
+    // The real-FFT split / merge passes are fused with the elementwise work around them (same operations and rounding as
+    // warp_rfft / warp_irfft_unscaled, 15 instead of 22 shared-memory round trips per block): each lane owns the bin
+    // pairs (k, H - k), k = lane + 32 i.
+    const C2 *Xb = Xf + (size_t)b * K;
+    const T *Pb = Pf + (size_t)b * K;
+    // (1) y = irfft(X_f W): products of a pair, merged, straight into the transform buffer
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) buf[FPAD<T>(k)] = cmul(Xf[(size_t)b * K + k], W[k]); }
+    for (int i = 0; i < 5; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= H / 2) {
+        if (k == 0) {
+          const T p0 = cmul(Xb[0], W[0]).x, ph = cmul(Xb[H], W[H]).x;
+          buf[FPAD<T>(0)] = mk2<T>(p0 + ph, -(p0 - ph));
+        } else {
+          C2 z1, z2;
+          irfft_merge_pair<T, C2>(cmul(Xb[k], W[k]), cmul(Xb[H - k], W[H - k]), tw_n[k], z1, z2);
+          buf[FPAD<T>(k)] = z1; buf[FPAD<T>(H - k)] = z2;
+        }
+      }
+    }
     __syncwarp();
-    warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
+    warp_cfft<H, T>(buf, tw_h, lane);                                       // x[2n] = r.x, x[2n+1] = -r.y (sign folded below)
+    const T sgn = (lane & 1) ? (T)-1 : (T)1;
     T e[L / 32];
 #pragma unroll
     for (int j = 0; j < L / 32; ++j) {
       const int n = lane + 32 * j;
-      e[j] = xad[(size_t)b * L + n] - fb[FIDX(L + n)] * invN;               // e = d - y, last hop_len samples (:161, :174)
+      e[j] = xad[(size_t)b * L + n] - (sgn * fb[FIDX(L + n)]) * invN;       // e = d - y, last hop_len samples (:161, :174)
       bm[(size_t)b * L + n] = e[j];
       if (bmo) bmo[(size_t)b * L + n] = (float)e[j];
     }
@@ -362,24 +427,38 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
 #pragma unroll
     for (int j = 0; j < L / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = (T)0; fb[FIDX(L + n)] = e[j]; }     // e_pad (:185)
     __syncwarp();
-    warp_rfft<N, T>(buf, tw_h, tw_n, lane);
+    warp_cfft<H, T>(buf, tw_h, lane);
+    // (2) E = split, W' = W + mu conj(X_f) E / P_f, merged for the constraint's inverse transform -- all per pair in registers
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {                                            // X_f / P_f again from L2: cheaper than 27 live registers
+    for (int i = 0; i < 5; ++i) {
       const int k = lane + 32 * i;
-      if (k < K) {
-        const C2 g = cmulc(buf[FPAD<T>(k)], Xf[(size_t)b * K + k]);         // conj(X) * E
-        const T ip = (T)1 / Pf[(size_t)b * K + k];
-        C2 wv = W[k];
-        wv.x += step_bm * (g.x * ip); wv.y += step_bm * (g.y * ip);
-        buf[FPAD<T>(k)] = wv;
+      if (k <= H / 2) {
+        if (k == 0) {
+          const C2 z = buf[FPAD<T>(0)];
+          const C2 E0 = mk2<T>(z.x + z.y, (T)0), Eh = mk2<T>(z.x - z.y, (T)0);
+          const C2 g0 = cmulc(E0, Xb[0]), gh = cmulc(Eh, Xb[H]);
+          const T w0 = W[0].x + step_bm * (g0.x * ((T)1 / Pb[0])), wh = W[H].x + step_bm * (gh.x * ((T)1 / Pb[H]));
+          buf[FPAD<T>(0)] = mk2<T>(w0 + wh, -(w0 - wh));
+        } else {
+          C2 E1, E2, z1, z2;
+          rfft_split_pair<T, C2>(buf[FPAD<T>(k)], buf[FPAD<T>(H - k)], tw_n[k], E1, E2);
+          const C2 g1 = cmulc(E1, Xb[k]), g2 = cmulc(E2, Xb[H - k]);        // conj(X) * E
+          const T ip1 = (T)1 / Pb[k], ip2 = (T)1 / Pb[H - k];
+          C2 w1 = W[k], w2 = W[H - k];
+          w1.x += step_bm * (g1.x * ip1); w1.y += step_bm * (g1.y * ip1);
+          w2.x += step_bm * (g2.x * ip2); w2.y += step_bm * (g2.y * ip2);
+          irfft_merge_pair<T, C2>(w1, w2, tw_n[k], z1, z2);
+          buf[FPAD<T>(k)] = z1; buf[FPAD<T>(H - k)] = z2;
+        }
       }
     }
     __syncwarp();
-    warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
+    warp_cfft<H, T>(buf, tw_h, lane);
+    // (3) constraint in the time domain (sign of the inverse folded in): zero tail, tap bounds
 #pragma unroll
     for (int j = 0; j < N / 32; ++j) {
       const int n = lane + 32 * j;
-      T v = fb[FIDX(n)] * invN;
+      T v = (sgn * fb[FIDX(n)]) * invN;
       if (n >= L) {
         v = (T)0;                                                           // w[-hop_len:] = 0 (:94)
       } else {
@@ -391,9 +470,22 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
       fb[FIDX(n)] = v;
     }
     __syncwarp();
-    warp_rfft<N, T>(buf, tw_h, tw_n, lane);
+    warp_cfft<H, T>(buf, tw_h, lane);
+    // (4) W = split, straight into the weight array
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) W[k] = buf[FPAD<T>(k)]; }
+    for (int i = 0; i < 5; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= H / 2) {
+        if (k == 0) {
+          const C2 z = buf[FPAD<T>(0)];
+          W[0] = mk2<T>(z.x + z.y, (T)0); W[H] = mk2<T>(z.x - z.y, (T)0);
+        } else {
+          C2 x1, x2;
+          rfft_split_pair<T, C2>(buf[FPAD<T>(k)], buf[FPAD<T>(H - k)], tw_n[k], x1, x2);
+          W[k] = x1; W[H - k] = x2;
+        }
+      }
+    }
     __syncwarp();
   }
 #undef FIDX
@@ -436,14 +528,31 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
 #define FIDX(n) (2 * FPAD<T>((n) >> 1) + ((n) & 1))
   // X_a = rfft([bm_prev | bm]) of channel m for block b into plane `pl`
   auto spectrum = [&](int m, int b, int pl) {
-    const T *src = Bs + (size_t)m * (L + a.Ns) + (size_t)b * L;
+    const C2 *src = reinterpret_cast<const C2 *>(Bs + (size_t)m * (L + a.Ns) + (size_t)b * L);
+    {
+      typedef FftFirst<H, T> F1;                       // first radix-8 pass fed from registers (coalesced 8-byte global loads)
+      C2 v[F1::PER][F1::R];
 #pragma unroll
-    for (int j = 0; j < N / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = src[n]; }
-    __syncwarp();
-    warp_rfft<N, T>(buf, tw_h, tw_n, lane);
-    C2 *dst = XaBuf + ((size_t)pl * M + m) * K;
+      for (int i = 0; i < F1::PER; ++i)
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) dst[k] = buf[FPAD<T>(k)]; }
+        for (int r = 0; r < F1::R; ++r) v[i][r] = src[lane + 32 * i + r * F1::NB];
+      F1::run(v, buf, tw_h, lane);
+    }
+    C2 *dst = XaBuf + ((size_t)pl * M + m) * K;                             // real-FFT split straight into the plane
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= H / 2) {
+        if (k == 0) {
+          const C2 z = buf[FPAD<T>(0)];
+          dst[0] = mk2<T>(z.x + z.y, (T)0); dst[H] = mk2<T>(z.x - z.y, (T)0);
+        } else {
+          C2 x1, x2;
+          rfft_split_pair<T, C2>(buf[FPAD<T>(k)], buf[FPAD<T>(H - k)], tw_n[k], x1, x2);
+          dst[k] = x1; dst[H - k] = x2;
+        }
+      }
+    }
     __syncwarp();
   };
   spectrum(warp, 0, 0);
@@ -467,25 +576,50 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
     }
     __syncthreads();
     if (warp == 0) {
-      // (c) output block and error spectrum
+      // (c) output block and error spectrum (merge / split fused with the copies in and out, sign of the inverse folded in)
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) buf[FPAD<T>(k)] = Ef[k]; }
+      for (int i = 0; i < 5; ++i) {
+        const int k = lane + 32 * i;
+        if (k <= H / 2) {
+          if (k == 0) {
+            const T p0 = Ef[0].x, ph = Ef[H].x;
+            buf[FPAD<T>(0)] = mk2<T>(p0 + ph, -(p0 - ph));
+          } else {
+            C2 z1, z2;
+            irfft_merge_pair<T, C2>(Ef[k], Ef[H - k], tw_n[k], z1, z2);
+            buf[FPAD<T>(k)] = z1; buf[FPAD<T>(H - k)] = z2;
+          }
+        }
+      }
       __syncwarp();
-      warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
+      warp_cfft<H, T>(buf, tw_h, lane);
+      const T sgn = (lane & 1) ? (T)-1 : (T)1;
       T ev[L / 32];
 #pragma unroll
       for (int i = 0; i < L / 32; ++i) {
         const int n = lane + 32 * i;
-        ev[i] = Fd[(size_t)b * L + n] - fb[FIDX(L + n)] * invN;             // e = d - y
+        ev[i] = Fd[(size_t)b * L + n] - (sgn * fb[FIDX(L + n)]) * invN;     // e = d - y
         a.y[(size_t)s * a.Ns + (size_t)b * L + n] = (float)ev[i];
       }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < L / 32; ++i) { const int n = lane + 32 * i; fb[FIDX(n)] = (T)0; fb[FIDX(L + n)] = ev[i]; }
       __syncwarp();
-      warp_rfft<N, T>(buf, tw_h, tw_n, lane);
+      warp_cfft<H, T>(buf, tw_h, lane);
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) Ef[k] = buf[FPAD<T>(k)]; }
+      for (int i = 0; i < 5; ++i) {
+        const int k = lane + 32 * i;
+        if (k <= H / 2) {
+          if (k == 0) {
+            const C2 z = buf[FPAD<T>(0)];
+            Ef[0] = mk2<T>(z.x + z.y, (T)0); Ef[H] = mk2<T>(z.x - z.y, (T)0);
+          } else {
+            C2 x1, x2;
+            rfft_split_pair<T, C2>(buf[FPAD<T>(k)], buf[FPAD<T>(H - k)], tw_n[k], x1, x2);
+            Ef[k] = x1; Ef[H - k] = x2;
+          }
+        }
+      }
     } else if (b + 1 < a.nblk) {
       // meanwhile: reference spectra of the next block (warp 1 also takes channel 0)
       spectrum(warp, b + 1, cur ^ 1);
@@ -515,15 +649,42 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
     // (e) constraint per channel: irfft, scale, zero the second half, rfft (:92-97)
     C2 *Wm = Waic + (size_t)warp * K;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) buf[FPAD<T>(k)] = Wm[k]; }
+    for (int i = 0; i < 5; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= H / 2) {
+        if (k == 0) {
+          const T p0 = Wm[0].x, ph = Wm[H].x;
+          buf[FPAD<T>(0)] = mk2<T>(p0 + ph, -(p0 - ph));
+        } else {
+          C2 z1, z2;
+          irfft_merge_pair<T, C2>(Wm[k], Wm[H - k], tw_n[k], z1, z2);
+          buf[FPAD<T>(k)] = z1; buf[FPAD<T>(H - k)] = z2;
+        }
+      }
+    }
     __syncwarp();
-    warp_irfft_unscaled<N, T>(buf, tw_h, tw_n, lane);
+    warp_cfft<H, T>(buf, tw_h, lane);
+    {
+      const T sgn = (lane & 1) ? (T)-1 : (T)1;
 #pragma unroll
-    for (int j = 0; j < N / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = (n >= L) ? (T)0 : fb[FIDX(n)] * invN * sc; }
+      for (int j = 0; j < N / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = (n >= L) ? (T)0 : (sgn * fb[FIDX(n)]) * invN * sc; }
+    }
     __syncwarp();
-    warp_rfft<N, T>(buf, tw_h, tw_n, lane);
+    warp_cfft<H, T>(buf, tw_h, lane);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < K) Wm[k] = buf[FPAD<T>(k)]; }
+    for (int i = 0; i < 5; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= H / 2) {
+        if (k == 0) {
+          const C2 z = buf[FPAD<T>(0)];
+          Wm[0] = mk2<T>(z.x + z.y, (T)0); Wm[H] = mk2<T>(z.x - z.y, (T)0);
+        } else {
+          C2 x1, x2;
+          rfft_split_pair<T, C2>(buf[FPAD<T>(k)], buf[FPAD<T>(H - k)], tw_n[k], x1, x2);
+          Wm[k] = x1; Wm[H - k] = x2;
+        }
+      }
+    }
     __syncthreads();
   }
 #undef FIDX

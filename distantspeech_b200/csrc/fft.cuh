@@ -178,6 +178,28 @@ __device__ __forceinline__ void warp_rfft_split_store(const typename V2<T>::type
   }
 }
 
+// The real-FFT split and the inverse's merge for one bin pair (k, H - k), 1 <= k <= H/2, w = exp(-2 pi i k / N) -- the
+// bodies of warp_rfft / warp_irfft_unscaled below, for kernels that fuse them with their own elementwise work instead of
+// paying a shared-memory round trip for each (fdgsc2.cu).  Same operations, same rounding.
+//   split: a = Z[k], b = Z[H-k] of the H-point transform  ->  X1 = X[k], X2 = X[H-k]
+template <typename T, typename C> __device__ __forceinline__ void rfft_split_pair(C a, C b, C w, C &X1, C &X2) {
+  const T sx = (T)0.5 * (a.x + b.x), sy = (T)0.5 * (a.y - b.y);
+  const T dx = (T)0.5 * (a.x - b.x), dy = (T)0.5 * (a.y + b.y);
+  const T px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;
+  const T ex = -py, ey = px;
+  X1 = mk2<T>(sx - ex, sy - ey);
+  X2 = mk2<T>(sx + ex, -(sy + ey));
+}
+//   merge: a = Y[k], b = Y[H-k]  ->  Z1 = conj(Z[k]), Z2 = conj(Z[H-k]) (input of the forward transform that inverts)
+template <typename T, typename C> __device__ __forceinline__ void irfft_merge_pair(C a, C b, C w, C &Z1, C &Z2) {
+  const T sx = a.x + b.x, sy = a.y - b.y;
+  const T dx = a.x - b.x, dy = a.y + b.y;
+  const T px = w.x * dx + w.y * dy, py = w.x * dy - w.y * dx;
+  const T fx = -py, fy = px;
+  Z1 = mk2<T>(sx + fx, -(sy + fy));
+  Z2 = mk2<T>(sx - fx, (sy - fy));
+}
+
 // in-place forward complex FFT of H points held in buf[FPAD<T>(i)], one warp
 template <int H, typename T>
 __device__ __forceinline__ void warp_cfft(typename V2<T>::type *buf, const typename V2<T>::type *__restrict__ tw_h, int lane) {
