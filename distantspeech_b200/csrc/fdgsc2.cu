@@ -414,20 +414,31 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
     }
     __syncwarp();
     warp_cfft<H, T>(buf, tw_h, lane);                                       // x[2n] = r.x, x[2n+1] = -r.y (sign folded below)
-    const T sgn = (lane & 1) ? (T)-1 : (T)1;
-    T e[L / 32];
+    {
+      // e = d - y on the last hop_len samples (:161, :174), computed by the lane that owns those samples in the next
+      // transform's first radix-8 pass (complex element c = samples 2c, 2c + 1; the upper half of the frame), so the
+      // zero-padded error [0 | e] (:185) goes into that transform from registers
+      typedef FftFirst<H, T> F1;
+      C2 v[F1::PER][F1::R];
+      const C2 *xd2 = reinterpret_cast<const C2 *>(xad + (size_t)b * L);
+      C2 *bm2 = reinterpret_cast<C2 *>(bm + (size_t)b * L);
 #pragma unroll
-    for (int j = 0; j < L / 32; ++j) {
-      const int n = lane + 32 * j;
-      e[j] = xad[(size_t)b * L + n] - (sgn * fb[FIDX(L + n)]) * invN;       // e = d - y, last hop_len samples (:161, :174)
-      bm[(size_t)b * L + n] = e[j];
-      if (bmo) bmo[(size_t)b * L + n] = (float)e[j];
+      for (int i = 0; i < F1::PER; ++i)
+#pragma unroll
+        for (int r = 0; r < F1::R; ++r) {
+          const int c = lane + 32 * i + r * F1::NB;
+          C2 z = mk2<T>((T)0, (T)0);
+          if (2 * c >= L) {
+            const C2 q = buf[FPAD<T>(c)], d = xd2[c - L / 2];
+            z = mk2<T>(d.x - q.x * invN, d.y - (-q.y) * invN);
+            bm2[c - L / 2] = z;
+            if (bmo) *reinterpret_cast<float2 *>(bmo + (size_t)b * L + 2 * c - L) = make_float2((float)z.x, (float)z.y);
+          }
+          v[i][r] = z;
+        }
+      __syncwarp();
+      F1::run(v, buf, tw_h, lane);
     }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < L / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = (T)0; fb[FIDX(L + n)] = e[j]; }     // e_pad (:185)
-    __syncwarp();
-    warp_cfft<H, T>(buf, tw_h, lane);
     // (2) E = split, W' = W + mu conj(X_f) E / P_f, merged for the constraint's inverse transform -- all per pair in registers
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -454,23 +465,31 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
     }
     __syncwarp();
     warp_cfft<H, T>(buf, tw_h, lane);
-    // (3) constraint in the time domain (sign of the inverse folded in): zero tail, tap bounds
+    // (3) constraint in the time domain (sign of the inverse folded in): zero tail, tap bounds -- read in the order of the
+    //     next transform's first radix-8 pass, which is then fed from registers
+    {
+      typedef FftFirst<H, T> F1;
+      C2 v[F1::PER][F1::R];
 #pragma unroll
-    for (int j = 0; j < N / 32; ++j) {
-      const int n = lane + 32 * j;
-      T v = (sgn * fb[FIDX(n)]) * invN;
-      if (n >= L) {
-        v = (T)0;                                                           // w[-hop_len:] = 0 (:94)
-      } else {
-        T ub = (T)a.delta;
-        const int d = n - N / 4;
-        if (d == 0) ub = (T)0.9; else if (d == 1 || d == -1) ub = (T)0.3; else if (d == 2 || d == -2) ub = (T)0.05;
-        v = fmin(fmax(v, -(T)a.delta), ub);                                 // tap bounds (:48-59, :96-108)
-      }
-      fb[FIDX(n)] = v;
+      for (int i = 0; i < F1::PER; ++i)
+#pragma unroll
+        for (int r = 0; r < F1::R; ++r) {
+          const int c = lane + 32 * i + r * F1::NB;                         // complex element = samples 2c, 2c + 1
+          C2 z = mk2<T>((T)0, (T)0);
+          if (2 * c < L) {                                                  // w[-hop_len:] = 0 (:94)
+            const C2 q = buf[FPAD<T>(c)];
+            T t0 = q.x * invN, t1 = (-q.y) * invN;
+            const int d0 = 2 * c - N / 4, d1 = d0 + 1;
+            T ub0 = (T)a.delta, ub1 = (T)a.delta;
+            if (d0 == 0) ub0 = (T)0.9; else if (d0 == 1 || d0 == -1) ub0 = (T)0.3; else if (d0 == 2 || d0 == -2) ub0 = (T)0.05;
+            if (d1 == 0) ub1 = (T)0.9; else if (d1 == 1 || d1 == -1) ub1 = (T)0.3; else if (d1 == 2 || d1 == -2) ub1 = (T)0.05;
+            z = mk2<T>(fmin(fmax(t0, -(T)a.delta), ub0), fmin(fmax(t1, -(T)a.delta), ub1));      // tap bounds (:48-59, :96-108)
+          }
+          v[i][r] = z;
+        }
+      __syncwarp();                                                         // every lane has read before any lane overwrites
+      F1::run(v, buf, tw_h, lane);
     }
-    __syncwarp();
-    warp_cfft<H, T>(buf, tw_h, lane);
     // (4) W = split, straight into the weight array
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -593,19 +612,27 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
       }
       __syncwarp();
       warp_cfft<H, T>(buf, tw_h, lane);
-      const T sgn = (lane & 1) ? (T)-1 : (T)1;
-      T ev[L / 32];
+      {
+        typedef FftFirst<H, T> F1;                     // e = d - y and [0 | e] straight into the next transform's first pass
+        C2 v[F1::PER][F1::R];
+        const C2 *fd2 = reinterpret_cast<const C2 *>(Fd + (size_t)b * L);
+        float2 *y2 = reinterpret_cast<float2 *>(a.y + (size_t)s * a.Ns + (size_t)b * L);
 #pragma unroll
-      for (int i = 0; i < L / 32; ++i) {
-        const int n = lane + 32 * i;
-        ev[i] = Fd[(size_t)b * L + n] - (sgn * fb[FIDX(L + n)]) * invN;     // e = d - y
-        a.y[(size_t)s * a.Ns + (size_t)b * L + n] = (float)ev[i];
+        for (int i = 0; i < F1::PER; ++i)
+#pragma unroll
+          for (int r = 0; r < F1::R; ++r) {
+            const int c = lane + 32 * i + r * F1::NB;
+            C2 z = mk2<T>((T)0, (T)0);
+            if (2 * c >= L) {
+              const C2 q = buf[FPAD<T>(c)], d = fd2[c - L / 2];
+              z = mk2<T>(d.x - q.x * invN, d.y - (-q.y) * invN);            // e = d - y
+              y2[c - L / 2] = make_float2((float)z.x, (float)z.y);
+            }
+            v[i][r] = z;
+          }
+        __syncwarp();
+        F1::run(v, buf, tw_h, lane);
       }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < L / 32; ++i) { const int n = lane + 32 * i; fb[FIDX(n)] = (T)0; fb[FIDX(L + n)] = ev[i]; }
-      __syncwarp();
-      warp_cfft<H, T>(buf, tw_h, lane);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int k = lane + 32 * i;
@@ -665,12 +692,20 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
     __syncwarp();
     warp_cfft<H, T>(buf, tw_h, lane);
     {
-      const T sgn = (lane & 1) ? (T)-1 : (T)1;
+      typedef FftFirst<H, T> F1;                       // scale / zero-tail pass feeds the next transform's first pass from registers
+      C2 v[F1::PER][F1::R];
 #pragma unroll
-      for (int j = 0; j < N / 32; ++j) { const int n = lane + 32 * j; fb[FIDX(n)] = (n >= L) ? (T)0 : (sgn * fb[FIDX(n)]) * invN * sc; }
+      for (int i = 0; i < F1::PER; ++i)
+#pragma unroll
+        for (int r = 0; r < F1::R; ++r) {
+          const int c = lane + 32 * i + r * F1::NB;
+          C2 z = mk2<T>((T)0, (T)0);
+          if (2 * c < L) { const C2 q = buf[FPAD<T>(c)]; z = mk2<T>(q.x * invN * sc, (-q.y) * invN * sc); }
+          v[i][r] = z;
+        }
+      __syncwarp();
+      F1::run(v, buf, tw_h, lane);
     }
-    __syncwarp();
-    warp_cfft<H, T>(buf, tw_h, lane);
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       const int k = lane + 32 * i;
