@@ -32,7 +32,7 @@ constexpr int F2_L = 256, F2_N = 512, F2_K = 257, F2_H = 256, F2_FLMAX = 128;
 #define FD_BM_MINB 3
 #endif
 #ifndef FD_AIC_MINB
-#define FD_AIC_MINB 3
+#define FD_AIC_MINB 4
 #endif
 
 struct Fd2Args {
@@ -511,6 +511,11 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
   for (int k = lane; k < K; k += 32) { st[2 * k] = (double)W[k].x; st[2 * k + 1] = (double)W[k].y; }
 }
 
+// transform buffer elements the canceller really needs: the XOR swizzle of 8-byte elements stays inside 16-element groups
+// (272 for H + 1 = 257), the padded layout of 16-byte elements needs fft_buf_elems -- the difference lets four canceller
+// CTAs of six warps share an SM
+template <typename T> __host__ __device__ constexpr int aic_buf_elems() { return sizeof(T) == 4 ? ((F2_K + 15) / 16) * 16 : fft_buf_elems(F2_N); }
+
 // interference canceller: CTA per stream, warp per channel.  The reference spectra X_a of block b + 1 depend only on the
 // blocking outputs, so they are computed by the otherwise idle warps WHILE warp 0 runs the serial output / error-spectrum
 // step of block b (ncu on the unpipelined version: 3.8 barrier stalls per issue): 4 transform times per block on the
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(256, FD_AIC_MINB) fd_aic_kernel(Fd2Args a, con
                                                      const typename V2<T>::type *__restrict__ tw_n_g) {
   typedef typename V2<T>::type C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int N = F2_N, H = F2_H, K = F2_K, L = F2_L, BE = fft_buf_elems(F2_N);
+  constexpr int N = F2_N, H = F2_H, K = F2_K, L = F2_L, BE = aic_buf_elems<T>();
   const Fd2State so(a.M);
   const Fd2Ws<T> w(a.S, a.M, a.Ns);
   const int M = a.M, NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, s = blockIdx.x;
@@ -796,7 +801,7 @@ static int launch_fdgsc2(const Fd2Args &a, const TwiddleSet &tw, cudaStream_t st
     DS_LAUNCH_CHECK();
   }
   {
-    const size_t smem = tw_bytes + ((size_t)M * BE + (size_t)3 * M * F2_K + F2_K + 1) * sizeof(C2) + (size_t)F2_K * sizeof(T) + 16 + 8 * sizeof(double);
+    const size_t smem = tw_bytes + ((size_t)M * aic_buf_elems<T>() + (size_t)3 * M * F2_K + F2_K + 1) * sizeof(C2) + (size_t)F2_K * sizeof(T) + 16 + 8 * sizeof(double);
     auto k = fd_aic_kernel<T>;
     DS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<a.S, 32 * M, smem, st>>>(a, TwSel<T>::h(tw), TwSel<T>::n(tw));
