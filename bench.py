@@ -514,7 +514,9 @@ def run_headline(args, env):
                                 "what": "same pinned buffers, staging buffers, time slices and streams, cudaMemcpy2DAsync only "
                                         "(H2D and D2H in flight together), wall clock, max over ranks"},
                "frac_of_copy_ceiling": v_pcm / v_copy,
-               "limiter": "host->device copy over PCIe (kernels hidden behind the copies)" if v_pcm / v_copy > 0.9
+               "limiter": ("host->device copies: the call runs at the pace of the bare copies of the same buffers (kernels hidden); "
+                           "at N > 1 the per-GPU copy rate (copy_ceiling.h2d_GBps_per_gpu) drops below one link's ~54 GB/s because all "
+                           "ranks share the host's memory and PCIe root") if v_pcm / v_copy > 0.9
                else "see frac_of_copy_ceiling: below the bare-copy ceiling",
                "host_placement": place}
         del x_pcm, y_pcm
