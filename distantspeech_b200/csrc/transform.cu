@@ -7,6 +7,7 @@
 //   FixedBeamformer beamformer/fixedbeamformer.py:147-207 (Y = sum_m conj(W) X, :163)
 #include "common.cuh"
 #include "fft.cuh"
+#include "fft16.cuh"
 
 namespace ds {
 
@@ -141,6 +142,253 @@ __global__ void stft_history_kernel(const float *x, const short *x16, float *his
   }
 }
 
+// ---------------------------------------------------------------------------
+// n_fft = 512 with the fp32 transform (the headline shape): a HALF-warp per frame, "square" 16 x 16 FFT (fft16.cuh).
+// Lane j of a half-warp owns z[j + 16 r] (r = 0..15) in the first radix-16 pass -- loaded straight from global memory,
+// 128 contiguous bytes per half-warp and r -- and Z[j + 16 q] after the second one; the 16 x 16 transpose in between is the
+// only shared-memory round trip (STS.64 columns, LDS.128 rows, both conflict free at a row stride of 18 elements).  The
+// real-FFT split pairs Z[k] with Z[256 - k], which the mirror lane (16 - j) & 15 holds in register 15 - q: two shuffles
+// per pair instead of a trip through shared memory.  Window, second-pass twiddles and split twiddles are lane-invariant
+// and stay in registers for the life of the (persistent) warp; the two half-warps take consecutive frames of one row, so
+// the 50 % overlap of their input is served by L1.  Non-interior frames (history, reflect padding, odd alignment) fill
+// the same registers through the scalar loader, so a frame has the same bits whichever way its samples arrived --
+// chunked streaming stays bit-identical to one call.
+// ---------------------------------------------------------------------------
+constexpr int SQ_WARPS = 4;
+constexpr int SQ_RS = 18;
+
+// real-FFT split of the pairs (k, 256 - k), k = j + 16 q < 128, written straight to the spectrum
+template <typename OutC>
+__device__ __forceinline__ void sq_split_store(const float2 (&u)[16], const float2 (&tws)[8], OutC *__restrict__ out, int j, int mirror,
+                                               bool valid) {
+  constexpr int H = 256;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float2 za = u[P16(q)];
+    float2 zb;
+    zb.x = __shfl_sync(0xffffffffu, u[P16(15 - q)].x, mirror);
+    zb.y = __shfl_sync(0xffffffffu, u[P16(15 - q)].y, mirror);
+    const float2 own = u[P16((16 - q) & 15)];                // lane 0 pairs with itself: Z[16 q] <-> Z[16 (16 - q)]
+    zb.x = (j == 0) ? own.x : zb.x;
+    zb.y = (j == 0) ? own.y : zb.y;
+    float2 X1, X2;
+    rfft_split_pair<float>(za, zb, tws[q], X1, X2);
+    OutC o1, o2;
+    o1.x = X1.x; o1.y = X1.y; o2.x = X2.x; o2.y = X2.y;
+    if (valid) { out[j + 16 * q] = o1; out[H - j - 16 * q] = o2; }
+  }
+  if (j == 0 && valid) {                                    // k = 128 pairs with itself
+    const float2 za = u[P16(8)];
+    float2 X1, X2;
+    rfft_split_pair<float>(za, za, make_float2(0.f, -1.f), X1, X2);
+    OutC o1;
+    o1.x = X1.x; o1.y = X1.y;
+    out[H / 2] = o1;
+  }
+}
+
+#ifndef SQ_MINB
+#define SQ_MINB 3          // CTAs (of SQ_WARPS warps) per SM the register budget is set for
+#endif
+// Measured on the B200 (config 4, 1024 streams x 10 s x 8 mics, analysis pass of ds_chain_run_profiled; Stockham kernel 4.15 ms;
+// profiles/ab_runs_r02.txt): constants in registers, 12 warps/SM 3.74 ms; window + split twiddles in shared memory, 16 warps
+// 3.35 ms; all constants in shared memory, 20 warps 3.15 ms (24 warps 3.36 ms); register prefetch of the next pair, 8 warps
+// 3.53 ms; prefetch + window / split twiddles in shared memory, 12 warps **3.00 ms** (default); prefetch + everything in shared
+// memory, 12 warps 3.04 ms, 16 warps 3.23 ms; prefetch.global.L2 instead of the register prefetch 3.4 - 3.7 ms.  15.7 GB in
+// 3.00 ms = 5.2 TB/s = 80 % of the measured copy peak: what is left is the HBM system, not the transform.
+#ifndef SQ_CONST_SMEM
+#define SQ_CONST_SMEM 1    // 1: window and split twiddles from shared memory; 2: second-pass twiddles too; 0: all in registers
+#endif
+#ifndef SQ_REGPF
+#define SQ_REGPF 1         // 1: the next frame pair's samples are loaded (into registers) before the current pair is transformed
+#endif
+#ifndef SQ_L2PF
+#define SQ_L2PF 0          // 1: prefetch.global.L2 of the next frame pair's samples
+#endif
+
+// samples of frame pair p for this lane: raw[r] = (x[2 e], x[2 e + 1]), e = j + 16 r, before the window; interior frames of
+// aligned rows by coalesced 8-byte (4-byte for int16 PCM) loads, everything else through the scalar loader
+template <bool PCM>
+__device__ __forceinline__ void sq_load(const StftArgs &a, unsigned p, unsigned Tp, int half, int j, float2 (&raw)[16], bool &valid,
+                                        size_t &o) {
+  constexpr int N = 512, K = 257;
+  const int ov = N - a.hop;
+  const unsigned sc = p / Tp;
+  const int t = 2 * (int)(p - sc * Tp) + half;
+  valid = t < a.T;
+  const float *xs = PCM ? nullptr : a.x + (size_t)sc * a.Ns;
+  const short *xs16 = PCM ? a.x16 + (size_t)sc * a.Ns : nullptr;
+  int g0;
+  if (a.mode == DS_STFT_STREAMING) g0 = t * a.hop - ov;
+  else if (a.mode == DS_STFT_CENTER) g0 = t * a.hop - N / 2;
+  else g0 = t * a.hop;
+  const unsigned s = sc / (unsigned)a.C;
+  const unsigned c = sc - s * (unsigned)a.C;
+  o = (((size_t)s * a.T + (valid ? t : 0)) * a.C + c) * K;
+  const bool interior = valid && (g0 >= 0) && (g0 + N <= a.Ns) &&
+                        (PCM ? ((reinterpret_cast<size_t>(xs16 + g0) & 3) == 0) : ((reinterpret_cast<size_t>(xs + g0) & 7) == 0));
+  if (interior) {
+    const float2 *src = reinterpret_cast<const float2 *>(xs + g0) + j;
+    const short2 *src16 = reinterpret_cast<const short2 *>(xs16 + g0) + j;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if constexpr (PCM) { const short2 pv = __ldg(src16 + 16 * r); raw[r] = make_float2(pcm16_scale(pv.x), pcm16_scale(pv.y)); }
+      else raw[r] = __ldg(src + 16 * r);
+    }
+  } else if (valid) {
+    const float *hs = a.history ? a.history + (size_t)sc * ov : nullptr;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float sv[2];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        int g = g0 + 2 * (j + 16 * r) + cc;
+        if (a.mode == DS_STFT_STREAMING) {
+          sv[cc] = (g < 0) ? hs[ov + g] : load_sample<PCM>(xs, xs16, g);
+        } else {
+          if (g < 0) g = -g;                              // np.pad(mode="reflect")
+          if (g >= a.Ns) g = 2 * (a.Ns - 1) - g;
+          sv[cc] = load_sample<PCM>(xs, xs16, g);
+        }
+      }
+      raw[r] = make_float2(sv[0], sv[1]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) raw[r] = make_float2(0.f, 0.f);
+  }
+}
+
+template <bool PCM>
+__global__ void __launch_bounds__(SQ_WARPS * 32, SQ_MINB) stft_sq_kernel(StftArgs a, const float2 *__restrict__ tw_h_g,
+                                                                        const float2 *__restrict__ tw_n_g) {
+  constexpr int H = 256;
+  __shared__ __align__(16) float2 xbuf[SQ_WARPS][2 * 16 * SQ_RS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
+  float2 *xb = xbuf[warp] + half * 16 * SQ_RS;
+  // lane-invariant constants: registers (default) or shared memory (more resident warps)
+#if SQ_CONST_SMEM >= 1
+  __shared__ float2 s_win[H], s_tws[H / 2];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) s_win[i] = make_float2((float)a.window[2 * i], (float)a.window[2 * i + 1]);
+  for (int i = threadIdx.x; i < H / 2; i += blockDim.x) s_tws[i] = tw_n_g[i];
+#else
+  float2 win[16], tws[8];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) win[r] = make_float2((float)a.window[2 * (j + 16 * r)], (float)a.window[2 * (j + 16 * r) + 1]);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) tws[q] = tw_n_g[j + 16 * q];
+#endif
+#if SQ_CONST_SMEM >= 2
+  __shared__ float2 s_tw2[H];                               // [r][j] = W256^(r j)
+  for (int i = threadIdx.x; i < H; i += blockDim.x) s_tw2[i] = tw_h_g[((i >> 4) * (i & 15)) & (H - 1)];
+#else
+  float2 tw2[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) tw2[r] = tw_h_g[(r * j) & (H - 1)];
+#endif
+#if SQ_CONST_SMEM >= 1
+  __syncthreads();
+#endif
+  const unsigned Tp = ((unsigned)a.T + 1u) >> 1;
+  const unsigned total = (unsigned)a.S * a.C * Tp;       // host guarantees S * C * T < 2^31
+  const int mirror = (lane & 16) | ((16 - j) & 15);
+  const unsigned stride = gridDim.x * SQ_WARPS;
+  unsigned p = blockIdx.x * SQ_WARPS + warp;
+  float2 raw[16];
+  bool valid = false;
+  size_t o = 0;
+#if SQ_REGPF
+  if (p < total) sq_load<PCM>(a, p, Tp, half, j, raw, valid, o);
+#endif
+  for (; p < total; p += stride) {
+#if !SQ_REGPF
+    sq_load<PCM>(a, p, Tp, half, j, raw, valid, o);
+#endif
+#if SQ_L2PF
+    if (p + stride < total) {
+      // the next pair's samples (3 KB for float32 at hop 256) towards L2: one 128-byte line per lane of the first 24
+      const unsigned pn = p + stride, scn = pn / Tp;
+      const int tn = 2 * (int)(pn - scn * Tp);
+      const long long gn = (long long)scn * a.Ns + (long long)tn * a.hop + (long long)lane * (PCM ? 64 : 32);
+      if (lane < 24 && gn + 32 < (long long)a.S * a.C * a.Ns) {
+        if constexpr (PCM) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x16 + gn));
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + gn));
+      }
+    }
+#endif
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+#if SQ_CONST_SMEM >= 1
+      const float2 wv = s_win[j + 16 * r];
+#else
+      const float2 wv = win[r];
+#endif
+      v[r] = make_float2(mul_rn(raw[r].x, wv.x), mul_rn(raw[r].y, wv.y));
+    }
+    const bool cur_valid = valid;
+    const size_t cur_o = o;
+#if SQ_REGPF
+    if (p + stride < total) sq_load<PCM>(a, p + stride, Tp, half, j, raw, valid, o);
+#endif
+    // pass 1: V_j[q] = sum_r z[j + 16 r] W16^(r q), stored transposed at [q][j]
+    dft16(v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) xb[q * SQ_RS + j] = v[P16(q)];
+    __syncwarp();
+    // pass 2: lane j reads row j (V_r[j], r = 0..15), applies W256^(r j) and transforms over r: Z[j + 16 q]
+    float2 u[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 w4 = *reinterpret_cast<const float4 *>(xb + j * SQ_RS + 2 * i);
+      u[2 * i] = make_float2(w4.x, w4.y); u[2 * i + 1] = make_float2(w4.z, w4.w);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 1; r < 16; ++r) {
+#if SQ_CONST_SMEM >= 2
+      u[r] = cmul(u[r], s_tw2[r * 16 + j]);
+#else
+      u[r] = cmul(u[r], tw2[r]);
+#endif
+    }
+    dft16(u);
+#if SQ_CONST_SMEM >= 1
+    float2 tws[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tws[q] = s_tws[j + 16 * q];
+#endif
+    if (a.out_c128) sq_split_store(u, tws, reinterpret_cast<double2 *>(a.X) + cur_o, j, mirror, cur_valid);
+    else sq_split_store(u, tws, reinterpret_cast<float2 *>(a.X) + cur_o, j, mirror, cur_valid);
+  }
+}
+
+template <typename T> struct SqStft {
+  static bool applies(int, const StftArgs &) { return false; }
+  static int launch(const StftArgs &, const TwiddleSet &, cudaStream_t) { return DS_EUNSUPPORTED; }
+};
+template <> struct SqStft<float> {
+  static bool applies(int n_fft, const StftArgs &) {
+#ifdef DS_STFT_NO_SQ
+    return false;
+#else
+    return n_fft == 512;
+#endif
+  }
+  static int launch(const StftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+    const long long total = (long long)a.S * a.C * a.T;
+    if (total >= (1LL << 31)) { set_error("stft: more than 2^31 frames in one call"); return DS_EUNSUPPORTED; }
+    const long long pairs = (long long)a.S * a.C * ((a.T + 1) / 2);
+    long long blocks = (pairs + SQ_WARPS - 1) / SQ_WARPS;
+    if (blocks > 148LL * SQ_MINB) blocks = 148LL * SQ_MINB;
+    if (blocks < 1) blocks = 1;
+    if (a.x16) stft_sq_kernel<true><<<(unsigned)blocks, SQ_WARPS * 32, 0, st>>>(a, tw.h32, tw.n32);
+    else stft_sq_kernel<false><<<(unsigned)blocks, SQ_WARPS * 32, 0, st>>>(a, tw.h32, tw.n32);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+  }
+};
+
 template <int N, typename T>
 static int launch_stft(const StftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
   typedef typename V2<T>::type C2;
@@ -160,6 +408,7 @@ static int launch_stft(const StftArgs &a, const TwiddleSet &tw, cudaStream_t st)
 
 template <typename T>
 static int dispatch_stft(int n_fft, const StftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+  if (SqStft<T>::applies(n_fft, a)) return SqStft<T>::launch(a, tw, st);
   switch (n_fft) {
     case 128: return launch_stft<128, T>(a, tw, st);
     case 256: return launch_stft<256, T>(a, tw, st);

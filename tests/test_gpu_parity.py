@@ -28,6 +28,21 @@ def test_stft_vs_oracle(cuda, n_fft, hop, center, precision):
     assert np.max(np.abs(out - ref)) <= tol * scale
 
 
+@pytest.mark.parametrize("hop,center,n", [(77, True, 9000), (256, False, 256 * 40 + 512), (256, True, 256 * 41), (129, False, 7001)])
+def test_stft_512_half_warp_paths(cuda, hop, center, n):
+    # n_fft = 512 / fp32 runs the half-warp-per-frame kernel (stft_sq_kernel): odd frame counts (one idle half-warp),
+    # rows whose frames are not 8-byte aligned (scalar loader), reflect padding, several channels, complex128 output
+    from distantspeech_b200.transform.transform import stft
+    rng = np.random.default_rng(hop + n)
+    x = (rng.standard_normal((3, n)) * 0.2).astype(np.float32)
+    win = O.sqrt_hann(512)
+    for c in range(3):
+        ref = O.stft(x[c].astype(np.float64), n_fft=512, hop_length=hop, window=win, center=center)
+        out = stft(x[c], n_fft=512, hop_length=hop, window=win, center=center, precision="fp32")
+        assert out.shape == ref.shape
+        assert np.max(np.abs(out - ref)) <= 3e-6 * np.max(np.abs(ref))
+
+
 def test_stft_golden_and_errors(cuda):
     from distantspeech_b200.transform.transform import stft, istft
     g = golden("stft_istft.npz")
