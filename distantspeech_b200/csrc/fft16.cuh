@@ -41,4 +41,27 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
   dft4(v[12], v[13], v[14], v[15]);
 }
 
+// row stride (complex elements) of a half-warp's 16 x 16 transpose buffer: 16-byte aligned rows, conflict-free STS.64
+// columns and LDS.128 rows
+constexpr int SQ_RS = 18;
+
+// 256-point complex forward transform by one half-warp: on entry v[r] = z[j + 16 r] (lane j of the half-warp), on exit
+// u[P16(q)] = Z[j + 16 q].  xb: the half-warp's 16 x SQ_RS buffer; tw2[r] = exp(-2 pi i r j / 256).  Every lane of the
+// warp must call it (two __syncwarp).
+__device__ __forceinline__ void sq_cfft256(float2 (&v)[16], float2 (&u)[16], float2 *xb, const float2 (&tw2)[16], int j) {
+  dft16(v);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) xb[q * SQ_RS + j] = v[P16(q)];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 w4 = *reinterpret_cast<const float4 *>(xb + j * SQ_RS + 2 * i);
+    u[2 * i] = make_float2(w4.x, w4.y); u[2 * i + 1] = make_float2(w4.z, w4.w);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 1; r < 16; ++r) u[r] = cmul(u[r], tw2[r]);
+  dft16(u);
+}
+
 }  // namespace ds

@@ -155,7 +155,6 @@ __global__ void stft_history_kernel(const float *x, const short *x16, float *his
 // chunked streaming stays bit-identical to one call.
 // ---------------------------------------------------------------------------
 constexpr int SQ_WARPS = 4;
-constexpr int SQ_RS = 18;
 
 // real-FFT split of the pairs (k, 256 - k), k = j + 16 q < 128, written straight to the spectrum
 template <typename OutC>
@@ -1012,6 +1011,207 @@ static int launch_fixedbf_seq(const FixedBfArgs &a, const TwiddleSet &tw, cudaSt
   return DS_OK;
 }
 
+// n_fft = 512, hop = 256, up to 3 beams: the fused fixed beamformer on the half-warp "square" transform (fft16.cuh).  A warp
+// owns a run of consecutive frames of one stream and takes them two at a time (one per half-warp): per microphone one
+// 256-point transform whose real-FFT split (partner bins from the mirror lane by shuffles) feeds the weight sums
+// sum_m conj(W) X held in registers (lane j owns the bin pairs (k, 256 - k), k = j + 16 q < 128); per beam the inverse
+// transform (merge, mirror shuffles, the same forward transform on conj(Z)), the synthesis window and the overlap-add:
+// the first frame's second half reaches the second frame's half-warp by shuffles, the second frame's second half is
+// carried in registers to the next pair.  One shared-memory round trip per transform, nothing else leaves the registers.
+constexpr int FSQ_WARPS = 4;
+
+template <int NB>
+__global__ void __launch_bounds__(FSQ_WARPS * 32, NB == 1 ? 3 : 2) fixedbf_sq_kernel(FixedBfArgs a, const float2 *__restrict__ tw_h_g,
+                                                                                    const float2 *__restrict__ tw_n_g, int G, int nseg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int N = 512, H = 256, K = H + 1, HOP = 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x, half = lane >> 4, j = lane & 15;
+  float2 *s_win = reinterpret_cast<float2 *>(smem_raw);              // [H]  (w[2e], w[2e+1])
+  float2 *s_tws = s_win + H;                                        // [H/2]
+  float2 *xbuf = s_tws + H / 2;                                     // [FSQ_WARPS][2][16 * SQ_RS]
+  float2 *Ws = xbuf + FSQ_WARPS * 2 * 16 * SQ_RS;                   // [NB][M][K]: weights, bin index innermost
+  for (int i = tid; i < H; i += blockDim.x) s_win[i] = make_float2((float)a.window[2 * i], (float)a.window[2 * i + 1]);
+  for (int i = tid; i < H / 2; i += blockDim.x) s_tws[i] = tw_n_g[i];
+  for (int i = tid; i < NB * K * a.M; i += blockDim.x) {              // a.W is [NB][K][M]
+    const int m = i % a.M, k = (i / a.M) % K, b = i / (a.M * K);
+    Ws[((size_t)b * a.M + m) * K + k] = a.W[i];
+  }
+  float2 tw2[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) tw2[r] = tw_h_g[(r * j) & (H - 1)];
+  __syncthreads();
+  const long long w = (long long)blockIdx.x * FSQ_WARPS + warp;
+  if (w >= (long long)a.S * nseg) return;                             // no CTA-wide synchronisation below
+  float2 *xb = xbuf + (warp * 2 + half) * 16 * SQ_RS;
+  const int s = (int)(w / nseg), seg = (int)(w % nseg);
+  const int t0 = seg * G, t1 = min(a.T, t0 + G);
+  const int parity = *reinterpret_cast<const int *>(a.state);
+  const size_t halfb = fbf_half_bytes(a.S, a.M, a.B, HOP);
+  const float *hist_in = reinterpret_cast<const float *>(a.state + 16 + (size_t)parity * halfb);
+  const float *tail_in = hist_in + (size_t)a.S * a.M * HOP;
+  float *hist_out = reinterpret_cast<float *>(a.state + 16 + (size_t)(1 - parity) * halfb);
+  float *tail_out = hist_out + (size_t)a.S * a.M * HOP;
+  const float inv_n = 1.0f / (float)N;
+  const int mirror = (lane & 16) | ((16 - j) & 15);
+
+  // pv: second half of the frame before the pair (samples 2 (j + 16 q), +1 of the block), needed by the first half-warp
+  float2 pv[NB][8];
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      pv[b][q] = (t0 == 0) ? *reinterpret_cast<const float2 *>(tail_in + ((long long)s * NB + b) * HOP + 2 * (j + 16 * q))   // x[:overlap] += previous_output
+                           : make_float2(0.f, 0.f);
+
+  for (int tt = (t0 > 0 ? t0 - 1 : 0); tt < t1; tt += 2) {
+    const int t = tt + half;
+    const bool valid = t < t1;
+    float2 y1[NB][8], y2[NB][8], yq[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      yq[b] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { y1[b][q] = make_float2(0.f, 0.f); y2[b][q] = make_float2(0.f, 0.f); }
+    }
+    const int g0 = t * HOP - HOP;
+    for (int m = 0; m < a.M; ++m) {
+      const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
+      float2 v[16], u[16];
+      if (valid && g0 >= 0 && ((reinterpret_cast<size_t>(xs + g0) & 7) == 0)) {
+        const float2 *src = reinterpret_cast<const float2 *>(xs + g0) + j;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float2 xv = __ldg(src + 16 * r);
+          const float2 wv = s_win[j + 16 * r];
+          v[r] = make_float2(mul_rn(xv.x, wv.x), mul_rn(xv.y, wv.y));
+        }
+      } else if (valid) {
+        const float *hs = hist_in + ((long long)s * a.M + m) * HOP;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int g = g0 + 2 * (j + 16 * r);
+          const float x0 = (g < 0) ? hs[HOP + g] : xs[g];
+          const float x1 = (g + 1 < 0) ? hs[HOP + g + 1] : xs[g + 1];
+          const float2 wv = s_win[j + 16 * r];
+          v[r] = make_float2(mul_rn(x0, wv.x), mul_rn(x1, wv.y));
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+      }
+      sq_cfft256(v, u, xb, tw2, j);
+      // real-FFT split fused with the weight sums: Y_b[k] += conj(W[b,k,m]) X_m[k]
+      const float2 *wm = Ws + (size_t)m * K;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 za = u[P16(q)];
+        float2 zb;
+        zb.x = __shfl_sync(0xffffffffu, u[P16(15 - q)].x, mirror);
+        zb.y = __shfl_sync(0xffffffffu, u[P16(15 - q)].y, mirror);
+        const float2 own = u[P16((16 - q) & 15)];
+        zb.x = (j == 0) ? own.x : zb.x;
+        zb.y = (j == 0) ? own.y : zb.y;
+        float2 X1, X2;
+        rfft_split_pair<float>(za, zb, s_tws[j + 16 * q], X1, X2);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float2 wa = wm[(size_t)b * a.M * K + j + 16 * q];
+          const float2 wb = wm[(size_t)b * a.M * K + H - j - 16 * q];
+          y1[b][q].x += wa.x * X1.x + wa.y * X1.y; y1[b][q].y += wa.x * X1.y - wa.y * X1.x;
+          y2[b][q].x += wb.x * X2.x + wb.y * X2.y; y2[b][q].y += wb.x * X2.y - wb.y * X2.x;
+        }
+      }
+      {                                                               // k = 128 pairs with itself (lane 0's register 8): X = conj(Z)
+        const float2 za = u[P16(8)];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float2 wq = wm[(size_t)b * a.M * K + H / 2];
+          yq[b].x += wq.x * za.x - wq.y * za.y; yq[b].y += -wq.x * za.y - wq.y * za.x;
+        }
+      }
+    }
+    // synthesis of every beam, overlap-add
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float2 z[16], Z2[8], r2[16];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) irfft_merge_pair<float>(y1[b][q], y2[b][q], s_tws[j + 16 * q], z[q], Z2[q]);
+      float2 zq, zq2;
+      irfft_merge_pair<float>(yq[b], yq[b], make_float2(0.f, -1.f), zq, zq2);
+#pragma unroll
+      for (int r = 8; r < 16; ++r) {
+        float2 rc;
+        rc.x = __shfl_sync(0xffffffffu, Z2[15 - r].x, mirror);
+        rc.y = __shfl_sync(0xffffffffu, Z2[15 - r].y, mirror);
+        const float2 own = (r == 8) ? zq : Z2[(16 - r) & 7];
+        z[r].x = (j == 0) ? own.x : rc.x;
+        z[r].y = (j == 0) ? own.y : rc.y;
+      }
+      if (j == 0) {                                                   // bins 0 and 256 (imaginary parts ignored like numpy.fft.irfft)
+        const float a0 = y1[b][0].x, b0 = y2[b][0].x;
+        z[0] = make_float2(a0 + b0, -(a0 - b0));
+      }
+      sq_cfft256(z, r2, xb, tw2, j);
+      // r2[P16(q)] = conj(x[2n] + i x[2n+1]) * N, n = j + 16 q
+      float2 c[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 wv = s_win[j + 16 * q];
+        c[q] = make_float2(r2[P16(q)].x * inv_n * wv.x, -r2[P16(q)].y * inv_n * wv.y);
+      }
+      float *ys = a.y + ((long long)s * NB + b) * a.Ns + (long long)t * HOP;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float2 s0, nx;
+        s0.x = __shfl_sync(0xffffffffu, c[q + 8].x, j);               // second half of the first frame of the pair
+        s0.y = __shfl_sync(0xffffffffu, c[q + 8].y, j);
+        nx.x = __shfl_sync(0xffffffffu, c[q + 8].x, j | 16);          // second half of the second frame
+        nx.y = __shfl_sync(0xffffffffu, c[q + 8].y, j | 16);
+        const float2 ad = half ? s0 : pv[b][q];
+        const float vx = ad.x + c[q].x, vy = ad.y + c[q].y;           // (0 + f[t-1]) + f[t];  t = 0: previous_output + f[0]
+        if (valid && t >= t0)
+          *reinterpret_cast<float2 *>(ys + 2 * (j + 16 * q)) = make_float2((float)((double)vx * a.scale), (float)((double)vy * a.scale));
+        pv[b][q] = (tt + 1 < t1) ? nx : s0;
+      }
+    }
+  }
+  // ---- new state (last run of each stream) ----------------------------------------
+  if (t1 == a.T) {
+    if (half == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float2 *>(tail_out + ((long long)s * NB + b) * HOP + 2 * (j + 16 * q)) = pv[b][q];
+    }
+    for (int i = lane; i < a.M * HOP; i += 32) {
+      const int m = i / HOP, jj = i - m * HOP;
+      const int g = a.Ns + jj;  // index into concat(history, x)
+      const float *hs = hist_in + ((long long)s * a.M + m) * HOP;
+      const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
+      hist_out[((long long)s * a.M + m) * HOP + jj] = (g < HOP) ? hs[g] : xs[g - HOP];
+    }
+  }
+}
+
+template <int NB>
+static int launch_fixedbf_sq(const FixedBfArgs &a, const TwiddleSet &tw, cudaStream_t st) {
+  long long nseg = (2LL * 148 * 24 + a.S - 1) / a.S;
+  const long long max_seg = a.T / 16 > 0 ? a.T / 16 : 1;
+  if (nseg > max_seg) nseg = max_seg;
+  if (nseg < 1) nseg = 1;
+  const int G = (int)((a.T + nseg - 1) / nseg);
+  nseg = (a.T + G - 1) / G;
+  const size_t smem = (size_t)(256 + 128 + FSQ_WARPS * 2 * 16 * SQ_RS) * sizeof(float2) + (size_t)NB * a.M * 257 * sizeof(float2);
+  if (smem > 75 * 1024) return DS_EUNSUPPORTED;     // three (two) CTAs per SM
+  auto kern = fixedbf_sq_kernel<NB>;
+  DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long warps = (long long)a.S * nseg;
+  kern<<<(unsigned)((warps + FSQ_WARPS - 1) / FSQ_WARPS), FSQ_WARPS * 32, smem, st>>>(a, tw.h32, tw.n32, G, (int)nseg);
+  DS_LAUNCH_CHECK();
+  return DS_OK;
+}
+
 __global__ void flip_parity_kernel(unsigned char *state) {
   int *p = reinterpret_cast<int *>(state);
   *p = 1 - *p;
@@ -1022,7 +1222,11 @@ static int launch_fixedbf(const FixedBfArgs &a0, const TwiddleSet &tw, cudaStrea
   FixedBfArgs a = a0;
   if constexpr (N <= 512) {
     if (a.hop * 2 == N && a.B <= 3) {
-      int rc = a.B == 1 ? launch_fixedbf_seq<N, 1>(a, tw, st) : a.B == 2 ? launch_fixedbf_seq<N, 2>(a, tw, st) : launch_fixedbf_seq<N, 3>(a, tw, st);
+      int rc = DS_EUNSUPPORTED;
+#ifndef DS_FIXEDBF_NO_SQ
+      if constexpr (N == 512) rc = a.B == 1 ? launch_fixedbf_sq<1>(a, tw, st) : a.B == 2 ? launch_fixedbf_sq<2>(a, tw, st) : launch_fixedbf_sq<3>(a, tw, st);
+#endif
+      if (rc == DS_EUNSUPPORTED) rc = a.B == 1 ? launch_fixedbf_seq<N, 1>(a, tw, st) : a.B == 2 ? launch_fixedbf_seq<N, 2>(a, tw, st) : launch_fixedbf_seq<N, 3>(a, tw, st);
       if (rc == DS_OK) {
         flip_parity_kernel<<<1, 1, 0, st>>>(a.state);
         DS_LAUNCH_CHECK();
