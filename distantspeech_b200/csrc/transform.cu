@@ -1020,8 +1020,12 @@ static int launch_fixedbf_seq(const FixedBfArgs &a, const TwiddleSet &tw, cudaSt
 // carried in registers to the next pair.  One shared-memory round trip per transform, nothing else leaves the registers.
 constexpr int FSQ_WARPS = 4;
 
+#ifndef FSQ_MINB1
+#define FSQ_MINB1 2         // with the prefetch: 254 registers, 8 warps per SM (A/B on the B200, config 2: no prefetch / 12 warps 3.41 ms,
+                            // prefetch / 12 warps (spills) 3.53 ms, prefetch / 8 warps 2.86 ms; Stockham warp kernel 5.19 ms)
+#endif
 template <int NB>
-__global__ void __launch_bounds__(FSQ_WARPS * 32, NB == 1 ? 3 : 2) fixedbf_sq_kernel(FixedBfArgs a, const float2 *__restrict__ tw_h_g,
+__global__ void __launch_bounds__(FSQ_WARPS * 32, NB == 1 ? FSQ_MINB1 : 2) fixedbf_sq_kernel(FixedBfArgs a, const float2 *__restrict__ tw_h_g,
                                                                                     const float2 *__restrict__ tw_n_g, int G, int nseg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int N = 512, H = 256, K = H + 1, HOP = 256;
@@ -1074,31 +1078,45 @@ __global__ void __launch_bounds__(FSQ_WARPS * 32, NB == 1 ? 3 : 2) fixedbf_sq_ke
       for (int q = 0; q < 8; ++q) { y1[b][q] = make_float2(0.f, 0.f); y2[b][q] = make_float2(0.f, 0.f); }
     }
     const int g0 = t * HOP - HOP;
-    for (int m = 0; m < a.M; ++m) {
+#ifndef FSQ_PF
+#define FSQ_PF 1          // the next microphone's samples are loaded before the current one is transformed
+#endif
+    // samples of microphone m for this lane (before the window): raw[r] = (x[2 e], x[2 e + 1]), e = j + 16 r
+    auto load_mic = [&](int m, float2 (&raw)[16]) {
       const float *xs = a.x + ((long long)s * a.M + m) * a.Ns;
-      float2 v[16], u[16];
       if (valid && g0 >= 0 && ((reinterpret_cast<size_t>(xs + g0) & 7) == 0)) {
         const float2 *src = reinterpret_cast<const float2 *>(xs + g0) + j;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const float2 xv = __ldg(src + 16 * r);
-          const float2 wv = s_win[j + 16 * r];
-          v[r] = make_float2(mul_rn(xv.x, wv.x), mul_rn(xv.y, wv.y));
-        }
+        for (int r = 0; r < 16; ++r) raw[r] = __ldg(src + 16 * r);
       } else if (valid) {
         const float *hs = hist_in + ((long long)s * a.M + m) * HOP;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const int g = g0 + 2 * (j + 16 * r);
-          const float x0 = (g < 0) ? hs[HOP + g] : xs[g];
-          const float x1 = (g + 1 < 0) ? hs[HOP + g + 1] : xs[g + 1];
-          const float2 wv = s_win[j + 16 * r];
-          v[r] = make_float2(mul_rn(x0, wv.x), mul_rn(x1, wv.y));
+          raw[r] = make_float2((g < 0) ? hs[HOP + g] : xs[g], (g + 1 < 0) ? hs[HOP + g + 1] : xs[g + 1]);
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+        for (int r = 0; r < 16; ++r) raw[r] = make_float2(0.f, 0.f);
       }
+    };
+    float2 raw[16];
+#if FSQ_PF
+    load_mic(0, raw);
+#endif
+    for (int m = 0; m < a.M; ++m) {
+      float2 v[16], u[16];
+#if !FSQ_PF
+      load_mic(m, raw);
+#endif
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 wv = s_win[j + 16 * r];
+        v[r] = make_float2(mul_rn(raw[r].x, wv.x), mul_rn(raw[r].y, wv.y));
+      }
+#if FSQ_PF
+      if (m + 1 < a.M) load_mic(m + 1, raw);
+#endif
       sq_cfft256(v, u, xb, tw2, j);
       // real-FFT split fused with the weight sums: Y_b[k] += conj(W[b,k,m]) X_m[k]
       const float2 *wm = Ws + (size_t)m * K;
