@@ -3,42 +3,65 @@
 //   P[d, t] = sum_k | sum_m conj(a[d,k,m]) yhat[k,t,m] |          (doa/srp.py:45-51)
 //
 // Per frequency bin the inner sum is a real GEMM with a contraction depth of only 2M:
-//   [Re Z | Im Z] (128 directions x 2*64 frames) = A' (128 x 2M) . B'^T (2M x 128)
+//   [Re Z | Im Z] (128 directions x 2*128 frames) = A' (128 x 2M) . B'^T (2M x 256)
 //   A'[d]      = [ cos(w tau_dm) ... | -sin(w tau_dm) ... ]                 (a = cos - j sin)
 //   B'[t]      = [ yr_m ... |  yi_m ... ]   -> Re Z = sum ar yr + ai yi
-//   B'[64 + t] = [ yi_m ... | -yr_m ... ]   -> Im Z = sum ar yi - ai yr
+//   B'[128 + t] = [ yi_m ... | -yr_m ... ]  -> Im Z = sum ar yi - ai yr
 // so the kernel is bound by what surrounds the MMA: generating the steering tile on
 // chip (it is never stored: D x K x M complex would be 4 GB) and the |.| + sum_k
-// epilogue out of tensor memory.  One CTA = 128 directions x 64 frames, looping over
-// all bins:
-//   warps 0-7   epilogue: tcgen05.ld the 128 x 128 fp32 accumulator, |z|, accumulate over bins
-//               (warp w reads TMEM lanes 32 (w % 4) .. +31 and the frame half w / 4; the epilogue is
-//               bound by the special-function unit -- one sqrt per (direction, frame, bin) -- so it
-//               gets two warps per scheduler to keep that unit fed across TMEM-load latency)
-//   warps 8-11  producers: steering tile generated on chip (phasor recurrence) into shared memory
-//               in the canonical no-swizzle K-major core-matrix layout, 3 stages
-//   warp  12    one elected thread issues tcgen05.mma (kind::tf32, M128 N128 K8, 2M/8 per bin)
-//   warp  13    one elected thread streams the spectrum tile of each bin into shared memory with
+// epilogue out of tensor memory.  One CTA (one per SM) = 128 directions x 128 frames, looping over
+// all bins -- the steering tile costs as many issue slots per bin as half the epilogue, so it is
+// shared by as many frames as tensor memory holds (two 256-column accumulators = all 512 columns):
+//   warps 0-15  epilogue: tcgen05.ld the 128 x 256 fp32 accumulator, |z|, accumulate over bins
+//               (warp w reads TMEM lanes 32 (w % 4) .. +31 and the frame quarter w / 4; packed fp32
+//               (f32x2) squares and sums, one special-function sqrt per (direction, frame, bin): 16 results
+//               per clock and SM, 1 024 cycles per bin and tile against 785 for the four MMAs)
+//   warps 16-23 producers (two threads per direction, half the microphones each): steering tile generated
+//               on chip (phasor recurrence on (cos, -sin)) into shared memory in the canonical no-swizzle
+//               K-major core-matrix layout, 4 stages;
+//               rounding to tf32 is one integer add per value (+ half an ulp; the tensor core
+//               truncates the rest -- the same result as cvt.rna, which costs four instructions)
+//   warp  24    one elected thread issues tcgen05.mma (kind::tf32, M128 N256 K8, 2M/8 per bin)
+//   warp  25    one elected thread streams the spectrum tile of each bin into shared memory with
 //               cp.async.bulk (the tile was laid out and rounded to tf32 once by srp_pack_kernel)
-//   warps 14-15 idle (they complete the fourth warpgroup: setmaxnreg is a warpgroup-wide instruction)
-// Registers are rebalanced with setmaxnreg (launch 64: epilogue 72, producers 88, last warpgroup 24).
-// TMEM: 2 accumulator stages x 128 columns.  Synchronisation: mbarriers
+//   warps 26-27 idle (they complete the seventh warpgroup: setmaxnreg is a warpgroup-wide instruction)
+// Registers are rebalanced with setmaxnreg (launch 72: epilogue 80, producers 64, last warpgroup 24).
+// TMEM: 2 accumulator stages x 256 columns.  Synchronisation: mbarriers
 // (producer -> MMA -> producer, MMA -> epilogue -> MMA) with tcgen05.commit.
+// Round 1's shape (128 x 64 tiles, two CTAs per SM, cvt.rna, scalar epilogue) needed 2 980 issue slots per
+// 8 192 accumulator elements (epilogue 1 200, producers 1 040, waits) and ran at 6.76 ms for config 5; this shape needs
+// 1 520 and runs at 5.5 ms.  Where the time goes (cycles per bin and tile = 16 384 accumulator elements, role variants
+// behind the SRP_DBG_* macros, profiles/ab_runs_r02.txt): the four MMAs free-running 785 (the K = 8 operand fetch from
+// shared memory, not the 512-cycle math), + the two-stage accumulator hand-off 850, + producers and bulk copies 1 022,
+// + epilogue 1 518; the sqrt unit alone would allow 1 024.  The costs add instead of overlapping: with all 512
+// tensor-memory columns in two stages the MMA of bin k + 2 cannot start before the epilogue of bin k has drained.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace ds {
 
 namespace tc {
 
-constexpr int TILE_D = 128, TILE_T = 64, UMMA_N = 2 * TILE_T;
-constexpr int STAGES = 3, ACC_STAGES = 2;
-constexpr int EPI_WARPS = 8, PROD_WARPS = 4;
+constexpr int TILE_D = 128, TILE_T = 128, UMMA_N = 2 * TILE_T;
+// The accumulator of a bin can be produced and handed over in NGRP frame groups ([Re | Im] of GRP_T frames each, one
+// M128 N(2 GRP_T) MMA chain and one barrier pair per group), so that the epilogue warps of one group work while the tensor
+// core still computes the next one.  MEASURED (config 5): NGRP = 2 5.95 ms against 5.56 ms for NGRP = 1 -- the N = 128
+// MMAs cost more than the de-phasing of the epilogue warps gains; a software-pipelined tensor-memory load (next 8 columns
+// in flight during the square roots of the current 8) was 5.87 ms.  Default: one group, plain load / wait / compute.
+#ifndef SRP_NGRP
+#define SRP_NGRP 1
+#endif
+constexpr int NGRP = SRP_NGRP, GRP_T = TILE_T / NGRP, GRP_N = 2 * GRP_T;
+#ifndef SRP_STAGES
+#define SRP_STAGES 4
+#endif
+constexpr int STAGES = SRP_STAGES, ACC_STAGES = 2;
+constexpr int EPI_WARPS = 16, PROD_WARPS = 8;
 constexpr int EPI_COLS = TILE_T / (EPI_WARPS / 4);      // frames per epilogue thread
 constexpr int RESYNC = 32;            // bins between exact re-evaluations of the steering phasors
 constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS, COPY_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = (EPI_WARPS + PROD_WARPS + 4) * 32;
-constexpr int PROD_THREADS = PROD_WARPS * 32;
 
 // Spectrum tiles for the B operand, built once per call: for bin k and frame tile j the 128 x 2M tile
 //   row r < 64 : [ yr_m ... |  yi_m ... ] of frame 64 j + r          (-> Re Z)
@@ -56,8 +79,9 @@ __global__ void srp_pack_kernel(const float2 *__restrict__ Yhat, unsigned char *
   const long long kt = g / ((long long)CHUNKS * UMMA_N);        // k * n_tiles + tile
   const int tile = (int)(kt % n_tiles);
   const int k = (int)(kt / n_tiles);
-  const bool im_row = r >= TILE_T;
-  const int t = tile * TILE_T + (im_row ? r - TILE_T : r);
+  const int grp = r / GRP_N, rr = r % GRP_N;                    // rows: [Re grp 0 | Im grp 0 | Re grp 1 | Im grp 1]
+  const bool im_row = rr >= GRP_T;
+  const int t = tile * TILE_T + grp * GRP_T + (im_row ? rr - GRP_T : rr);
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   if (t < T) {
     const float2 *src = Yhat + ((size_t)k * T + t) * MM;
@@ -73,18 +97,22 @@ __global__ void srp_pack_kernel(const float2 *__restrict__ Yhat, unsigned char *
 }
 
 template <int MM>   // microphones
-__global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__restrict__ tau, const unsigned char *__restrict__ Bp,
+__global__ void __launch_bounds__(NTHREADS, 1) srp_tc_kernel(const float *__restrict__ tau, const unsigned char *__restrict__ Bp,
                                                              float *__restrict__ P, int D, int T, int K, float two_f0, int n_tiles) {
   constexpr int KD = 2 * MM;                      // contraction depth (fp32 / tf32 elements)
   constexpr int A_BYTES = TILE_D * KD * 4, B_BYTES = UMMA_N * KD * 4;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // a steering row (one direction) is produced by PSPLIT threads, MH microphones each: one producer warp per scheduler
+  // took ~1 000 cycles per bin (128 dependent-ish instructions, shared-memory stores, proxy fence) and was the critical
+  // path of the whole pipeline (MMA + producers alone: 1 022 cycles per bin against 843 for the MMAs)
+  constexpr int PSPLIT = MM >= 8 ? 2 : 1, MH = MM / PSPLIT, PROD_ACTIVE = TILE_D * PSPLIT;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *tiles = smem;                                            // [STAGES][A | B]
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *acc_full = empty_bar + STAGES;
-  uint64_t *acc_empty = acc_full + ACC_STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES);
+  uint64_t *acc_empty = acc_full + ACC_STAGES * NGRP;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES * NGRP);
   float *tau_s = reinterpret_cast<float *>(tmem_slot + 4);                 // [TILE_D][MM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,8 +123,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
     tau_s[i] = (d < D) ? tau[(size_t)d * MM + (i % MM)] : 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PROD_THREADS + 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS * 32); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PROD_ACTIVE + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ACC_STAGES * NGRP; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS * 32 / NGRP); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {      // the MMA warp owns the TMEM allocation
@@ -110,41 +138,65 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
 
   if (warp < EPI_WARPS) {
     // ===================== epilogue: |z| and sum over bins ==========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     float acc[EPI_COLS];
 #pragma unroll
     for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
     const int quad = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    for (int k = 0; k < K; ++k) {
-      const int as = k % ACC_STAGES;
-      mbar_wait(&acc_full[as], (k / ACC_STAGES) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tcol = tmem_base + lane_addr + as * UMMA_N + half * EPI_COLS;
+    const int grp = half / (EPI_WARPS / 4 / NGRP), hh = half % (EPI_WARPS / 4 / NGRP);
+    const int tb0 = t0 + grp * GRP_T + hh * EPI_COLS;
+    const uint32_t tcol0 = tmem_base + lane_addr + grp * GRP_N + hh * EPI_COLS;
+    // |z| of eight (direction, frame) pairs, two per instruction (packed fp32), into the running sums of column group h
+    auto mag8 = [&](const uint32_t (&re)[8], const uint32_t (&im)[8], auto hc) {
+      constexpr int h = decltype(hc)::value;
+      if (tb0 + h * 8 < T) {                                  // warp-uniform: frame groups past the end stay zero
 #pragma unroll
-      for (int h = 0; h < EPI_COLS / 16; ++h) {
-        uint32_t re[16], im[16];
-        tmem_ld16(tcol + h * 16, re);
-        tmem_ld16(tcol + TILE_T + h * 16, im);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float zr = __uint_as_float(re[j]), zi = __uint_as_float(im[j]);
+        for (int j = 0; j < 8; j += 2) {
 #ifdef SRP_DBG_EPI_LIGHT
-          acc[h * 16 + j] += zr + zi;
+          acc[h * 8 + j] += __uint_as_float(re[j]) + __uint_as_float(im[j]);
+          acc[h * 8 + j + 1] += __uint_as_float(re[j + 1]) + __uint_as_float(im[j + 1]);
 #else
-          float mag;
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(zr, zr, zi * zi)));
-          acc[h * 16 + j] += mag;
+          unsigned long long zr2, zi2, s2, a2, m2;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(zr2) : "r"(re[j]), "r"(re[j + 1]));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(zi2) : "r"(im[j]), "r"(im[j + 1]));
+          asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(s2) : "l"(zi2));
+          asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(s2) : "l"(zr2), "l"(s2));
+          float s_lo, s_hi, m_lo, m_hi;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(s_lo), "=f"(s_hi) : "l"(s2));
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m_lo) : "f"(s_lo));
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m_hi) : "f"(s_hi));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(m2) : "f"(m_lo), "f"(m_hi));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(acc[h * 8 + j]), "f"(acc[h * 8 + j + 1]));
+          asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a2) : "l"(a2), "l"(m2));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[h * 8 + j]), "=f"(acc[h * 8 + j + 1]) : "l"(a2));
 #endif
         }
       }
+    };
+    for (int k = 0; k < K; ++k) {
+      const int as = k % ACC_STAGES;
+      mbar_wait(&acc_full[as * NGRP + grp], (k / ACC_STAGES) & 1);     // (one polling / arriving lane per warp: measured slower)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tcol = tcol0 + as * UMMA_N;
+#ifdef SRP_DBG_EPI_NONE
+      if (k >= 0) { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); mbar_arrive(&acc_empty[as * NGRP + grp]); continue; }
+#endif
+      uint32_t re0[8], im0[8], re1[8], im1[8];
+      tmem_ld8(tcol, re0); tmem_ld8(tcol + 8, re1); tmem_ld8(tcol + GRP_T, im0); tmem_ld8(tcol + GRP_T + 8, im1);
+      tmem_wait_ld(re0, im0); tmem_wait_ld(re1, im1);
+      mag8(re0, im0, std::integral_constant<int, 0>{});
+      mag8(re1, im1, std::integral_constant<int, 1>{});
+      tmem_ld8(tcol + 16, re0); tmem_ld8(tcol + 24, re1); tmem_ld8(tcol + GRP_T + 16, im0); tmem_ld8(tcol + GRP_T + 24, im1);
+      tmem_wait_ld(re0, im0); tmem_wait_ld(re1, im1);
+      mag8(re0, im0, std::integral_constant<int, 2>{});
+      mag8(re1, im1, std::integral_constant<int, 3>{});
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&acc_empty[as]);
+      mbar_arrive(&acc_empty[as * NGRP + grp]);
     }
     const int d = d0 + quad * 32 + lane;
     if (d < D) {
-      const int tb = t0 + half * EPI_COLS;
+      const int tb = tb0;
       float *out = P + (size_t)d * T + tb;
       const bool vec = (tb + EPI_COLS <= T) && ((reinterpret_cast<size_t>(out) & 15) == 0);
       if (vec) {
@@ -161,26 +213,36 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
     if (warp == MMA_WARP) {
     // ===================== MMA issuer ==================================================
     // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UMMA_N >> 3) << 17) | ((uint32_t)(TILE_D >> 4) << 24);
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GRP_N >> 3) << 17) | ((uint32_t)(TILE_D >> 4) << 24);
     for (int k = 0; k < K; ++k) {
       const int s = k % STAGES, as = k % ACC_STAGES;
-      if (k >= ACC_STAGES) mbar_wait(&acc_empty[as], ((k / ACC_STAGES) - 1) & 1);
       mbar_wait(&full_bar[s], (k / STAGES) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < KD / 8; ++kk) {
-          // one K = 8 step = two 16-byte chunks of the canonical layout
-          const uint64_t ad = make_desc(a_addr + kk * 2 * (TILE_D * 16), TILE_D * 16, 128);
-          const uint64_t bd = make_desc(b_addr + kk * 2 * (UMMA_N * 16), UMMA_N * 16, 128);
-          umma_tf32(tmem_base + as * UMMA_N, ad, bd, IDESC, kk > 0 ? 1u : 0u);
+      for (int g = 0; g < NGRP; ++g) {
+#ifndef SRP_DBG_NO_ACC_WAIT
+        if (k >= ACC_STAGES) mbar_wait(&acc_empty[as * NGRP + g], ((k / ACC_STAGES) - 1) & 1);
+#endif
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES + g * (GRP_N / 8) * 128;     // rows GRP_N g .. of the 256-row tile
+#pragma unroll
+          for (int kk = 0; kk < KD / 8; ++kk) {
+            // one K = 8 step = two 16-byte chunks of the canonical layout
+            const uint64_t ad = make_desc(a_addr + kk * 2 * (TILE_D * 16), TILE_D * 16, 128);
+            const uint64_t bd = make_desc(b_addr + kk * 2 * (UMMA_N * 16), UMMA_N * 16, 128);
+#ifdef SRP_DBG_F16HACK
+            // timing experiment only (wrong results): half as many MMAs of twice the depth on the same bytes
+            if (kk < KD / 16) umma_f16(tmem_base + as * UMMA_N + g * GRP_N, ad, bd, IDESC & ~((7u << 7) | (7u << 10)), kk > 0 ? 1u : 0u);
+#else
+            umma_tf32(tmem_base + as * UMMA_N + g * GRP_N, ad, bd, IDESC, kk > 0 ? 1u : 0u);
+#endif
+          }
+          if (g == NGRP - 1) umma_commit(&empty_bar[s]);     // smem stage may be refilled once these MMAs retire
+          umma_commit(&acc_full[as * NGRP + g]);             // this group's accumulator is ready for its epilogue warps
         }
-        umma_commit(&empty_bar[s]);     // smem stage may be refilled once these MMAs retire
-        umma_commit(&acc_full[as]);     // accumulator ready for the epilogue
+        __syncwarp();
       }
-      __syncwarp();
     }
     } else if (warp == COPY_WARP && lane == 0) {
     // ===================== spectrum tiles: one bulk copy per bin ==============================
@@ -189,6 +251,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
         const int s = k % STAGES;
         if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1);
         const uint32_t bar = smem_u32(&full_bar[s]);
+#ifdef SRP_DBG_NO_COPY
+        mbar_arrive(&full_bar[s]); continue;
+#endif
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)B_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(tiles + s * STAGE_BYTES + A_BYTES)),
@@ -201,40 +266,48 @@ __global__ void __launch_bounds__(NTHREADS, 2) srp_tc_kernel(const float *__rest
     // Thread pt owns steering row pt (one direction, all MM mics): its phasors advance from bin to
     // bin by one complex rotation exp(-j 2 pi df tau) and are re-evaluated exactly every RESYNC bins.
     // All shared-memory traffic is 16-byte vectors.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-    const int pt = threadIdx.x - PROD_WARP0 * 32;          // 0 .. 127
-    float cs[MM], sn[MM], rc[MM], rs[MM];
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    const int pt = threadIdx.x - PROD_WARP0 * 32;          // 0 .. 255
+    if (pt < PROD_ACTIVE) {
+    const int row = pt % TILE_D, m0 = (pt / TILE_D) * MH;   // this thread's direction and first microphone
+    // the phasor is carried as (cos, -sin) = the two steering coefficients themselves (a = cos - j sin)
+    float cs[MH], ns[MH], rc[MH], rs[MH];
 #pragma unroll
-    for (int m = 0; m < MM; ++m) sincospif(two_f0 * tau_s[pt * MM + m], &rs[m], &rc[m]);   // rotation per bin
-    const int a_row = (pt >> 3) * 128 + (pt & 7) * 16;
+    for (int m = 0; m < MH; ++m) sincospif(two_f0 * tau_s[row * MM + m0 + m], &rs[m], &rc[m]);   // rotation per bin
+    const int a_row = (row >> 3) * 128 + (row & 7) * 16;
     for (int k = 0; k < K; ++k) {
       const int s = k % STAGES;
       if ((k % RESYNC) == 0) {
         const float fk2 = two_f0 * (float)k;
 #pragma unroll
-        for (int m = 0; m < MM; ++m) sincospif(fk2 * tau_s[pt * MM + m], &sn[m], &cs[m]);
+        for (int m = 0; m < MH; ++m) { float sv; sincospif(fk2 * tau_s[row * MM + m0 + m], &sv, &cs[m]); ns[m] = -sv; }
       }
       if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1);
       unsigned char *At = tiles + s * STAGE_BYTES;
-      // steering row: [cos_0 .. cos_{M-1} | -sin_0 .. -sin_{M-1}]   (a = cos - j sin)
+#ifdef SRP_DBG_PROD_NONE
+      if (k >= 0) { mbar_arrive(&full_bar[s]); continue; }
+#endif
+      // steering row: [cos_0 .. cos_{M-1} | -sin_0 .. -sin_{M-1}], rounded to tf32 by adding half an ulp of the
+      // 10-bit mantissa to the bit pattern (|x| <= 1: no overflow) -- the MMA drops the low 13 bits
+#define RB(x) (__float_as_uint(x) + 0x1000u)
 #pragma unroll
-      for (int q = 0; q < MM / 4; ++q) {
-        *reinterpret_cast<float4 *>(At + q * (TILE_D * 16) + a_row) =
-            make_float4(to_tf32(cs[4 * q]), to_tf32(cs[4 * q + 1]), to_tf32(cs[4 * q + 2]), to_tf32(cs[4 * q + 3]));
-        *reinterpret_cast<float4 *>(At + (MM / 4 + q) * (TILE_D * 16) + a_row) =
-            make_float4(-to_tf32(sn[4 * q]), -to_tf32(sn[4 * q + 1]), -to_tf32(sn[4 * q + 2]), -to_tf32(sn[4 * q + 3]));
+      for (int q = 0; q < MH / 4; ++q) {
+        *reinterpret_cast<uint4 *>(At + (m0 / 4 + q) * (TILE_D * 16) + a_row) = make_uint4(RB(cs[4 * q]), RB(cs[4 * q + 1]), RB(cs[4 * q + 2]), RB(cs[4 * q + 3]));
+        *reinterpret_cast<uint4 *>(At + (MM / 4 + m0 / 4 + q) * (TILE_D * 16) + a_row) = make_uint4(RB(ns[4 * q]), RB(ns[4 * q + 1]), RB(ns[4 * q + 2]), RB(ns[4 * q + 3]));
       }
+#undef RB
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (tensor core)
       mbar_arrive(&full_bar[s]);
-      // advance the phasors to the next bin
+      // advance the phasors to the next bin: (c, n) <- (c rc + n rs, n rc - c rs)
 #ifndef SRP_DBG_PROD_LIGHT
 #pragma unroll
-      for (int m = 0; m < MM; ++m) {
-        const float c = cs[m], sv = sn[m];
-        cs[m] = fmaf(c, rc[m], -sv * rs[m]);
-        sn[m] = fmaf(sv, rc[m], c * rs[m]);
+      for (int m = 0; m < MH; ++m) {
+        const float c = cs[m], nv = ns[m];
+        cs[m] = fmaf(c, rc[m], nv * rs[m]);
+        ns[m] = fmaf(nv, rc[m], -c * rs[m]);
       }
 #endif
+    }
     }
   }
 
@@ -252,7 +325,7 @@ template <int MM> static int launch(const float *tau, const float2 *Yhat, unsign
   const long long chunks = (long long)K * n_tiles * UMMA_N * (KD / 4);
   srp_pack_kernel<MM><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(Yhat, Bp, T, K, n_tiles);
   DS_LAUNCH_CHECK();
-  const size_t smem = (size_t)STAGES * (TILE_D + UMMA_N) * KD * 4 + (2 * STAGES + 2 * ACC_STAGES) * 8 + 16 + (size_t)TILE_D * MM * 4 + 128;
+  const size_t smem = (size_t)STAGES * (TILE_D + UMMA_N) * KD * 4 + (2 * STAGES + 2 * ACC_STAGES * NGRP) * 8 + 16 + (size_t)TILE_D * MM * 4 + 128;
   auto kern = srp_tc_kernel<MM>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((D + TILE_D - 1) / TILE_D, n_tiles);
