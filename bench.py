@@ -371,15 +371,18 @@ def parity_streams(cfg, xs, ys, what):
             "ok": bool(worst_err <= 1e-4 and worst_snr >= 60)}
 
 
+# translation unit of the dominant kernel (mcspp_fast.cu and every header it includes)
+DOMINANT_KERNEL_SOURCES = ("mcspp_fast.cu", "chain_step.cuh", "mcspp_args.cuh", "perbin.cuh", "common.cuh")
+
+
 def kernel_sources_sha():
-    """sha1 over the CUDA sources: ncu-derived figures in profiles/traffic.json are only quoted for the build they were
-    captured from."""
+    """sha1 over the sources of the dominant kernel's translation unit: the ncu-derived figures in profiles/traffic.json
+    are only quoted for the kernel build they were captured from."""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(ROOT, "distantspeech_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(d, f), "rb").read())
+    for f in DOMINANT_KERNEL_SOURCES:
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:12]
 
 
