@@ -604,6 +604,121 @@ __global__ void __launch_bounds__(ISEQ_WARPS * 32) istft_seq_kernel(IstftArgs a,
   }
 }
 
+// n_fft = 512, hop = 256, fp32 transform: the inverse STFT on the half-warp "square" transform (fft16.cuh).  A warp owns a run
+// of consecutive hop-blocks of one (stream, channel) and takes the frames two at a time (one per half-warp): merge of the bin
+// pairs (k, 256 - k) (the partner half of Z from the mirror lane by shuffles), the forward transform of conj(Z), the
+// synthesis window in double like the reference's float64 product (transform.py:368), and the overlap-add in registers --
+// the first frame's second half reaches the second half-warp by shuffles, the second frame's is carried to the next pair.
+// tail_only: a second launch (one warp per sequence) recomputes the last frame and stores its second half as the new
+// streaming tail -- the same arithmetic as the main pass, so chunked streaming stays bit-identical to one call.
+constexpr int ISQ_WARPS = 4;
+
+__global__ void __launch_bounds__(ISQ_WARPS * 32, 3) istft_sq_kernel(IstftArgs a, const float2 *__restrict__ tw_h_g,
+                                                                    const float2 *__restrict__ tw_n_g, int G, int nseg, int tail_only) {
+  constexpr int N = 512, H = 256, HOP = 256;
+  __shared__ __align__(16) float2 xbuf[ISQ_WARPS][2 * 16 * SQ_RS];
+  __shared__ double2 s_win[H];                                          // (w[2e], w[2e+1])
+  __shared__ float2 s_tws[H / 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) s_win[i] = make_double2(a.window[2 * i], a.window[2 * i + 1]);
+  for (int i = threadIdx.x; i < H / 2; i += blockDim.x) s_tws[i] = tw_n_g[i];
+  float2 tw2[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) tw2[r] = tw_h_g[(r * j) & (H - 1)];
+  __syncthreads();
+  const long long w = (long long)blockIdx.x * ISQ_WARPS + warp;
+  if (w >= (long long)a.S * a.C * nseg) return;                          // no CTA-wide synchronisation below
+  float2 *xb = xbuf[warp] + half * 16 * SQ_RS;
+  const int sc = (int)(w / nseg), seg = (int)(w % nseg);
+  const int s = sc / a.C, c = sc % a.C;
+  const int nblk = (a.n_out + HOP - 1) / HOP;
+  const int b0 = tail_only ? a.T : seg * G, b1 = tail_only ? a.T : min(b0 + G, nblk);
+  const float inv_n = 1.0f / (float)N;
+  float *ys = a.y16 ? nullptr : a.y + (long long)sc * a.n_out;
+  short *ys16 = a.y16 ? a.y16 + (long long)sc * a.n_out : nullptr;
+  const bool streaming = a.mode == DS_STFT_STREAMING;
+  const int mirror = (lane & 16) | ((16 - j) & 15);
+  // pv: second half of the frame before the pair, as this lane's samples 2 (j + 16 q), +1 of the block
+  float2 pv[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    pv[q] = (b0 == 0 && streaming) ? *reinterpret_cast<const float2 *>(a.tail + (long long)sc * HOP + 2 * (j + 16 * q))   // x[:overlap] += previous_output (:476)
+                                   : make_float2(0.f, 0.f);
+  const int f_end = tail_only ? a.T : min(b1, a.T + 1);                   // blocks / frames f < f_end are visited
+  for (int tt = (b0 >= 1 ? b0 - 1 : 0); tt < f_end; tt += 2) {
+    const int f = tt + half;
+    const bool fvalid = f < a.T && f < f_end;                             // frame f exists (block T of the plain mode has only a carry)
+    float2 z[16], Z2[8], r2[16];
+    float2 ya[8], yb[8], yq = make_float2(0.f, 0.f);
+    if (fvalid) {
+      const long long ibase = (long long)s * a.sS + (long long)f * a.sT + (long long)c * a.sC;
+      if (a.in_c128) {
+        const double2 *in = reinterpret_cast<const double2 *>(a.Y) + ibase;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double2 v1 = in[(long long)(j + 16 * q) * a.sK], v2 = in[(long long)(H - j - 16 * q) * a.sK];
+          ya[q] = make_float2((float)v1.x, (float)v1.y); yb[q] = make_float2((float)v2.x, (float)v2.y);
+        }
+        if (j == 0) { const double2 v = in[(long long)(H / 2) * a.sK]; yq = make_float2((float)v.x, (float)v.y); }
+      } else {
+        const float2 *in = reinterpret_cast<const float2 *>(a.Y) + ibase;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { ya[q] = in[(long long)(j + 16 * q) * a.sK]; yb[q] = in[(long long)(H - j - 16 * q) * a.sK]; }
+        if (j == 0) yq = in[(long long)(H / 2) * a.sK];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { ya[q] = make_float2(0.f, 0.f); yb[q] = make_float2(0.f, 0.f); }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) irfft_merge_pair<float>(ya[q], yb[q], s_tws[j + 16 * q], z[q], Z2[q]);
+    float2 zq, zq2;
+    irfft_merge_pair<float>(yq, yq, make_float2(0.f, -1.f), zq, zq2);
+#pragma unroll
+    for (int r = 8; r < 16; ++r) {
+      float2 rc;
+      rc.x = __shfl_sync(0xffffffffu, Z2[15 - r].x, mirror);
+      rc.y = __shfl_sync(0xffffffffu, Z2[15 - r].y, mirror);
+      const float2 own = (r == 8) ? zq : Z2[(16 - r) & 7];
+      z[r].x = (j == 0) ? own.x : rc.x;
+      z[r].y = (j == 0) ? own.y : rc.y;
+    }
+    if (j == 0) {                                                       // bins 0 and 256 (imaginary parts ignored like numpy.fft.irfft)
+      const float a0 = ya[0].x, b0v = yb[0].x;
+      z[0] = make_float2(a0 + b0v, -(a0 - b0v));
+    }
+    sq_cfft256(z, r2, xb, tw2, j);
+    // r2[P16(q)] = conj(x[2n] + i x[2n+1]) * N, n = j + 16 q; windowed sample (:368)
+    float2 cw[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const double2 wv = s_win[j + 16 * q];
+      cw[q] = make_float2((float)((double)(r2[P16(q)].x * inv_n) * wv.x), (float)((double)(-r2[P16(q)].y * inv_n) * wv.y));
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float2 s0, nx;
+      s0.x = __shfl_sync(0xffffffffu, cw[q + 8].x, j);                   // second half of the first frame of the pair
+      s0.y = __shfl_sync(0xffffffffu, cw[q + 8].y, j);
+      nx.x = __shfl_sync(0xffffffffu, cw[q + 8].x, j | 16);              // second half of the second frame
+      nx.y = __shfl_sync(0xffffffffu, cw[q + 8].y, j | 16);
+      const float2 ad = half ? s0 : pv[q];
+      float vx = ad.x + cw[q].x, vy = ad.y + cw[q].y;                    // (0 + f[b-1]) + f[b]
+      const int g = f * HOP + 2 * (j + 16 * q);
+      if (f >= b0 && f < b1 && g < a.n_out) {                            // n_out is a multiple of the hop: both samples or none
+        if (streaming) { vx = (float)((double)vx * a.scale); vy = (float)((double)vy * a.scale); }   // :479
+        if (ys16) *reinterpret_cast<short2 *>(ys16 + g) = make_short2(pcm16_from_sample(vx), pcm16_from_sample(vy));
+        else *reinterpret_cast<float2 *>(ys + g) = make_float2(vx, vy);
+      }
+      pv[q] = (tt + 1 < f_end) ? nx : s0;
+    }
+  }
+  if (tail_only && half == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<float2 *>(a.tail + (long long)sc * HOP + 2 * (j + 16 * q)) = pv[q];
+  }
+}
+
 template <int N, typename T>
 static int launch_istft(const IstftArgs &a, const TwiddleSet &tw, cudaStream_t st) {
   const int R = (N + a.hop - 1) / a.hop;
@@ -613,6 +728,27 @@ static int launch_istft(const IstftArgs &a, const TwiddleSet &tw, cudaStream_t s
   auto kern = istft_kernel<N, T>;
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = (a.n_out + a.hop - 1) / a.hop;
+#ifndef DS_ISTFT_NO_SQ
+  if constexpr (N == 512 && sizeof(T) == 4) {
+    if (a.hop * 2 == N && (a.mode != DS_STFT_STREAMING || a.tail)) {
+      const long long seqs = (long long)a.S * a.C;
+      long long nseg = (2LL * 148 * 16 + seqs - 1) / seqs;
+      const long long max_seg = (nblk + 15) / 16;
+      if (nseg > max_seg) nseg = max_seg;
+      if (nseg < 1) nseg = 1;
+      const int G = (int)((nblk + nseg - 1) / nseg);
+      nseg = (nblk + G - 1) / G;
+      const long long warps = seqs * nseg;
+      istft_sq_kernel<<<(unsigned)((warps + ISQ_WARPS - 1) / ISQ_WARPS), ISQ_WARPS * 32, 0, st>>>(a, tw.h32, tw.n32, G, (int)nseg, 0);
+      DS_LAUNCH_CHECK();
+      if (a.mode == DS_STFT_STREAMING && a.tail) {
+        istft_sq_kernel<<<(unsigned)((seqs + ISQ_WARPS - 1) / ISQ_WARPS), ISQ_WARPS * 32, 0, st>>>(a, tw.h32, tw.n32, 0, 1, 1);
+        DS_LAUNCH_CHECK();
+      }
+      return DS_OK;
+    }
+  }
+#endif
   if (a.hop * 2 == N && (a.mode != DS_STFT_STREAMING || a.tail)) {
     // one warp per run of G hop-blocks; enough runs to fill the machine twice over
     typedef typename V2<T>::type C2;
