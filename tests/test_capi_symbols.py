@@ -95,7 +95,7 @@ def test_argument_validation_precedes_any_device_work():
     np_ = _lib.SubbandNlmsParams(257, 1, 1, 4, 5, 4, 0, 0, 0.1, 0.9, 1e-4)   # 4 taps x 5 channels: not compiled
     assert lib.ds_subband_nlms_run(ctypes.byref(np_), one, one, one, null, one, null) == EUNSUP
     assert lib.ds_srp_run(10, 4, 5, 513, 48000.0, 1024, one, one, null, one, 1, null) == EUNSUP   # tensor path: 4, 8, 16 mics
-    assert lib.ds_srp_workspace_bytes(937, 16, 513, 1) == 513 * 15 * 128 * 32 * 4 and lib.ds_srp_workspace_bytes(937, 16, 513, 0) == 0
+    assert lib.ds_srp_workspace_bytes(937, 16, 513, 1) == 513 * 8 * 256 * 32 * 4 and lib.ds_srp_workspace_bytes(937, 16, 513, 0) == 0
     # 8f.3 / 8f.4 entry points
     assert lib.ds_steering_run(4, 6, null, one, null) == EINVAL and b"null" in lib.ds_last_error()
     assert lib.ds_steering_run(4, 9, one, one, null) == EUNSUP and b"n_mics" in lib.ds_last_error()    # > 8 sensors
