@@ -345,4 +345,171 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
     return yout;
 }
 
+// ---- version 2 of the frame step: the same quantities, restructured for register pressure -------------------------------
+// Phi_yy' = alpha Phi_yy + (1 - alpha) Re(y y^H) enters xi and gamma linearly, so both forms are evaluated against the OLD
+// Phi_yy (read from shared memory) and the rank-two part in closed form:
+//   tr(A Phi_yy')              = alpha tr(A Phi_yy) + (1 - alpha) Re(y^H A y)                       (Re(y^H A y) = s_yu, already there)
+//   sum_ij Phi_yy'_ij z_ij     = alpha sum_ij Phi_yy_ij z_ij + (1 - alpha) (d1^2 + d2^2 + d3^2 + d4^2),  z_ij = Re(conj(u_i) u_j),
+//                                d1 = yr.ur, d2 = yi.ui, d3 = yr.ui, d4 = yi.ur
+// One pass over the matrix (4 fp64 operations per element) then needs A and u but NOT y, A dies right after it, and the
+// Phi_yy recursion itself becomes a streaming pass (load, 3 operations, store) that depends on nothing adaptive -- the
+// scheduler can sink it under the serial speech-presence chain.  u = A y is formed in two halves (real, imaginary part) so
+// that y is held in double precision for one half at a time.  +24 fp64 instructions per bin and frame against version 1,
+// in exchange for ~40 fewer live registers in the passes that used to hold A, y and u together.
+template <int M, int NT, bool USE_C>
+__device__ __forceinline__ float2 chain_bin_step_v2(const float2 (&yf)[M], float2 ynb0, float2 ynb1, int k, int K, int frm,
+                                                    bool reset, McraRegs &mc, double *smy, double *smv, const double *smc,
+                                                    const double *a0, const McsppArgs &a, double &p_post) {
+  constexpr int NP = M * (M + 1) / 2;
+    // ---- A = inv(Re Phi_vv + eps I)                                         mcspp_base.py:278
+    double A[NP];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = i; j < M; ++j) A[pidx<M>(i, j)] = smv[pidx<M>(i, j) * NT] + ((i == j) ? a.eps : 0.0);
+    spd_inverse_packed<M>(A);
+
+    // ---- prior from MCRA on channel 0                                       :98-122
+    double q;
+    {
+      const double Ym1 = (k > 0) ? power_c((double)ynb0.x, (double)ynb0.y) : 0.0;
+      const double Yp1 = (k < K - 1) ? power_c((double)ynb1.x, (double)ynb1.y) : 0.0;
+      const double Y0 = power_c((double)yf[0].x, (double)yf[0].y);
+      mcra_step_sel(mc, Ym1, Y0, Yp1, k, K, frm, reset, a.mc);
+      const double omp = fmax(1.0 - mc.p, 1e-300);                           // p <= p_max < 1: never taken
+      const double rs = rsqrt_pos(omp);
+      double sq = omp * rs;
+      sq = fma(fma(-sq, sq, omp), 0.5 * rs, sq);
+      q = fmin(fmax(sq, a.q_min), a.q_max);
+    }
+#define AS(i, j) (((i) <= (j)) ? A[pidx<M>(i, j)] : A[pidx<M>(j, i)])
+    // ---- MVDR denominator den = a^H A a = sum_{i<=j} A_ij C_ij                beamformer.py:152-153
+    double den4[4] = {0.0, 0.0, 0.0, 0.0};
+    if constexpr (USE_C) {
+#pragma unroll
+      for (int e = 0; e < NP; ++e) den4[e & 3] = fma(A[e], smc[e * NT], den4[e & 3]);
+    } else {
+      double ar[M], ai[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) { const double2 av = ld_f64x2_once(a0 + 2 * m * K); ar[m] = av.x; ai[m] = av.y; }
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = i; j < M; ++j) {
+          const int e = pidx<M>(i, j);
+          const double c = fma(ai[i], ai[j], ar[i] * ar[j]);
+          den4[(i == j) ? (i & 1) : 2 + (e & 1)] = fma(A[e], c, den4[(i == j) ? (i & 1) : 2 + (e & 1)]);
+        }
+      den4[2] *= 2.0; den4[3] *= 2.0;
+    }
+    const double den = (den4[0] + den4[1]) + (den4[2] + den4[3]);
+    double trA = 0.0, trA2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) { if (i & 1) trA2 += A[pidx<M>(i, i)]; else trA += A[pidx<M>(i, i)]; }
+    trA += trA2;
+
+    // ---- u = A y in two halves; numerator a^H u, s_yu = Re(y^H u), |u|^2, the four dot products      :282-284, beamformer.py:152
+    double ur[M], ui[M];
+    double Yr = 0.0, Yi = 0.0, Yr2 = 0.0, Yi2 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0, uu = 0.0, uu2 = 0.0;
+    {
+      double yr[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) yr[m] = (double)yf[m].x;
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        double sr = 0.0, sr2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) { if (j & 1) sr2 = fma(AS(i, j), yr[j], sr2); else sr = fma(AS(i, j), yr[j], sr); }
+        ur[i] = sr + sr2;
+      }
+      double yi[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) yi[m] = (double)yf[m].y;
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        double si = 0.0, si2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) { if (j & 1) si2 = fma(AS(i, j), yi[j], si2); else si = fma(AS(i, j), yi[j], si); }
+        ui[i] = si + si2;
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const double2 av = ld_f64x2_once(a0 + 2 * m * K);
+        Yr = fma(av.x, ur[m], Yr);   Yi = fma(-av.y, ur[m], Yi);
+        Yr2 = fma(av.y, ui[m], Yr2); Yi2 = fma(av.x, ui[m], Yi2);
+        d1 = fma(yr[m], ur[m], d1);  d2 = fma(yi[m], ui[m], d2);
+        d3 = fma(yr[m], ui[m], d3);  d4 = fma(yi[m], ur[m], d4);
+        uu = fma(ur[m], ur[m], uu);  uu2 = fma(ui[m], ui[m], uu2);
+      }
+    }
+    const double syu = d1 + d2;
+
+    // ---- one pass over the OLD Phi_yy: tr(A Phi_yy) and sum_ij Phi_yy_ij Re(conj(u_i) u_j); A is dead afterwards   :280-284
+    double trd[2] = {0.0, 0.0}, tro[4] = {0.0, 0.0, 0.0, 0.0}, gmd[2] = {0.0, 0.0}, gmo[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = i; j < M; ++j) {
+        const int e = pidx<M>(i, j);
+        const double ph = smy[e * NT];
+        const double z = fma(ui[i], ui[j], ur[i] * ur[j]);
+        if (i == j) { trd[i & 1] = fma(A[e], ph, trd[i & 1]); gmd[i & 1] = fma(ph, z, gmd[i & 1]); }
+        else { tro[e & 3] = fma(A[e], ph, tro[e & 3]); gmo[e & 3] = fma(ph, z, gmo[e & 3]); }
+      }
+#undef AS
+    const double alpha = a.alpha, one_m_alpha = 1.0 - a.alpha;
+    double xi = fma(2.0, (tro[0] + tro[1]) + (tro[2] + tro[3]), trd[0] + trd[1]);           // tr(A Phi_yy_old)
+    xi = fma(alpha, xi, one_m_alpha * syu);                                                 // tr(A Phi_yy')
+    xi = fma(a.eps, trA, xi - (double)M);
+    double gam = fma(2.0, (gmo[0] + gmo[1]) + (gmo[2] + gmo[3]), gmd[0] + gmd[1]);
+    gam = fma(alpha, gam, one_m_alpha * (fma(d1, d1, d2 * d2) + fma(d3, d3, d4 * d4)));
+    gam = fma(a.eps, uu + uu2, gam - syu);
+    xi = fmin(fmax(xi, a.snr_min), a.snr_max);                               // :286-287
+    gam = fmin(fmax(gam, a.snr_min), a.snr_max);
+
+    // ---- posterior SPP                                                       :124-138
+    const double xi1 = 1.0 + xi;
+    const double rxi1 = rcp_pos(xi1);
+    double p = rcp_pos(1.0 + q * rcp_pos(1.0 - q) * xi1 * exp_nonpos(-1.0 * (gam * rxi1)));
+    p = fmin(fmax(p, a.p_min), a.p_max);
+    p_post = p;
+
+    // ---- OMLSA gain and output  Y = (w^H y) G,  w = A a / den                :140-155
+    double scale = rcp_pos(den);
+    if (a.apply_gain) {
+      const float pf = (float)p;
+      double G = (double)expf(pf * logf((float)(xi * rxi1)) + (1.0f - pf) * (float)a.logGmin);
+      G = fmax(fmin(G, 1.0), a.Gmin);
+      if (k < 2) G = 0.0;
+      scale *= G;
+    }
+    const float2 yout = make_float2((float)((Yr + Yr2) * scale), (float)((Yi + Yi2) * scale));
+
+    // ---- both covariance recursions as streaming passes (Phi_yy' depends on nothing adaptive)     :84-90, :299-319
+    const double at = a.alpha_d + (1.0 - a.alpha_d) * p;
+    const double one_m_at = 1.0 * (1.0 - at);
+    double yr[M], yi[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { yr[m] = (double)yf[m].x; yi[m] = (double)yf[m].y; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const double tr_i = one_m_alpha * yr[i], ti_i = one_m_alpha * yi[i];
+#pragma unroll
+      for (int j = i; j < M; ++j) {
+        const int e = pidx<M>(i, j);
+        smy[e * NT] = fma(tr_i, yr[j], fma(ti_i, yi[j], alpha * smy[e * NT]));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const double tr_i = one_m_at * yr[i], ti_i = one_m_at * yi[i];
+#pragma unroll
+      for (int j = i; j < M; ++j) {
+        const int e = pidx<M>(i, j);
+        smv[e * NT] = fma(tr_i, yr[j], fma(ti_i, yi[j], at * smv[e * NT]));
+      }
+    }
+    return yout;
+}
+
 }  // namespace ds

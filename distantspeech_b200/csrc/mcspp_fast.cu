@@ -13,11 +13,21 @@
 
 namespace ds {
 
+#ifdef DS_FAST_TRACE
+// timing experiment only: start clock of frames 100..163 of every warp, plus the SM and hardware warp slot it ran on
+__device__ long long g_trace[8192 * 66];
+#endif
+
 #ifndef DS_FAST_SKEW
 #define DS_FAST_SKEW 8000       // cycles, about one frame of the M = 8 kernel; 0 disables
 #endif
+#ifndef DS_CHAIN_V2
+#define DS_CHAIN_V2 0
+#endif
 #ifndef DS_FAST_MINB
 #define DS_FAST_MINB 4
+#endif
+#ifndef DS_FAST_USE_C
 #define DS_FAST_USE_C 1
 #endif
 
@@ -85,6 +95,15 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
   for (int t = 0; t < a.T; ++t) {
     // issue the loads of this frame's spectrum first: they are consumed only after the matrix
     // inverse, so the HBM latency hides behind the Gauss-Jordan sweeps
+#ifdef DS_FAST_TRACE
+    if ((tid & 31) == 0 && t >= 100 && t < 164) {
+      const unsigned gw = blockIdx.x * (NT / 32) + (tid >> 5);
+      if (gw < 8192) {
+        g_trace[gw * 66 + (t - 100)] = clock64();
+        if (t == 100) { unsigned smid, wid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); asm("mov.u32 %0, %%warpid;" : "=r"(wid)); g_trace[gw * 66 + 64] = smid; g_trace[gw * 66 + 65] = wid; }
+      }
+    }
+#endif
     float2 yf[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) yf[m] = ld_f2_once(Xp + m * K);
@@ -103,7 +122,11 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
     }
     const bool reset = (frm > 0) && (ell_mod == 0);
     double p_post;
+#if DS_CHAIN_V2
+    *Yp = chain_bin_step_v2<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
+#else
     *Yp = chain_bin_step<M, NT, USE_C, MIXED>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
+#endif
     if constexpr (TAP_P) a.tp[((long long)s * a.T + t) * K + k] = p_post;     // the only tap this kernel serves
     if (reset) ell = 0;
     ++ell; ++frm;
@@ -127,7 +150,10 @@ static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
   constexpr int NT = DS_FAST_NT;
   constexpr int NP = M * (M + 1) / 2;
   constexpr int MINB = DS_FAST_MINB; // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
-  const size_t smem = (size_t)(DS_FAST_USE_C ? 3 : 2) * NP * NT * sizeof(double);
+#ifndef DS_FAST_SMEM_PAD_KB
+#define DS_FAST_SMEM_PAD_KB 0     // occupancy experiments only: extra dynamic shared memory per CTA
+#endif
+  const size_t smem = (size_t)(DS_FAST_USE_C ? 3 : 2) * NP * NT * sizeof(double) + (size_t)DS_FAST_SMEM_PAD_KB * 1024;
 #ifdef DS_CHAIN_MIXED      // A/B build only (tools/build_variant.sh x mcspp_fast.cu -DDS_CHAIN_MIXED): see chain_step.cuh
   auto kern = a.tp ? mcspp_fast_kernel<M, NT, MINB, true> : mcspp_fast_kernel<M, NT, MINB, false, true>;
 #else
@@ -155,3 +181,7 @@ int launch_mcspp_fast(int M, const McsppArgs &a, cudaStream_t st) {
 }
 
 }  // namespace ds
+
+#ifdef DS_FAST_TRACE
+extern "C" int ds_debug_trace_read(long long *host, size_t bytes) { return (int)cudaMemcpyFromSymbol(host, ds::g_trace, bytes); }
+#endif
