@@ -113,7 +113,11 @@ __global__ void fd_prologue_kernel(Fd2Args a) {
 // microphone.  Taps run in groups of four over a register window of the input: per group one 16-byte shared-memory load
 // of samples (conflict-free) and one broadcast load of taps feed 16 multiply-adds; every output still sums its taps in
 // ascending order like the sequential FIR.
-constexpr int FIR_TS = 1024, FIR_NT = 256;
+#ifndef FIR_NPT
+#define FIR_NPT 4          // consecutive outputs per thread (A/B, FDGSC pipeline ms: 4 -> 129.1, 8 -> 135.8 (the 32-byte lane stride
+                           // makes the 16-byte sample loads two-way bank conflicted), 16 -> 157.0)
+#endif
+constexpr int FIR_TS = 1024, FIR_NT = FIR_TS / FIR_NPT;
 template <typename T> __device__ __forceinline__ void load4(const T *p, T (&v)[4]) {
   if constexpr (sizeof(T) == 4) {
     const float4 q = *reinterpret_cast<const float4 *>(p);
@@ -149,35 +153,43 @@ __global__ void __launch_bounds__(FIR_NT) fd_fir_kernel(Fd2Args a) {
     }
   }
   __syncthreads();
-  const int n0 = threadIdx.x * 4;
-  if (n0 >= nt) return;                            // nt is a multiple of 256 (Ns is): whole groups of four
-  T mean[4] = {(T)0, (T)0, (T)0, (T)0};
+  const int n0 = threadIdx.x * FIR_NPT;
+  if (n0 >= nt) return;                            // nt is a multiple of 256 (Ns is): whole groups of FIR_NPT
+  T mean[FIR_NPT];
+#pragma unroll
+  for (int j = 0; j < FIR_NPT; ++j) mean[j] = (T)0;
   T *A = reinterpret_cast<T *>(a.ws + w.A);
   const int nq = (FL + 3) / 4;
   for (int m = 0; m < M; ++m) {
     const T *row = xs + (size_t)m * XS + F2_FLMAX + n0;
     const T *hm = hs + m * F2_FLMAX;
-    T acc[4] = {(T)0, (T)0, (T)0, (T)0};
-    T hi[4], lo[4], h4[4];
-    load4<T>(row, hi);                             // x[n0 .. n0+3]
-    for (int q = 0; q < nq; ++q) {
-      load4<T>(row - 4 * q - 4, lo);               // x[n0-4q-4 .. n0-4q-1]
-      load4<T>(hm + 4 * q, h4);
-      // y[n0+j] += h[k] x[n0 + j - k],  k = 4q .. 4q+3
-      acc[0] += h4[0] * hi[0]; acc[1] += h4[0] * hi[1]; acc[2] += h4[0] * hi[2]; acc[3] += h4[0] * hi[3];
-      acc[0] += h4[1] * lo[3]; acc[1] += h4[1] * hi[0]; acc[2] += h4[1] * hi[1]; acc[3] += h4[1] * hi[2];
-      acc[0] += h4[2] * lo[2]; acc[1] += h4[2] * lo[3]; acc[2] += h4[2] * hi[0]; acc[3] += h4[2] * hi[1];
-      acc[0] += h4[3] * lo[1]; acc[1] += h4[3] * lo[2]; acc[2] += h4[3] * lo[3]; acc[3] += h4[3] * hi[0];
+    T acc[FIR_NPT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) hi[j] = lo[j];
+    for (int j = 0; j < FIR_NPT; ++j) acc[j] = (T)0;
+    // sliding register window X[i] = x[n0 - 4q - 4 + i], i = 0 .. FIR_NPT + 3: per group of four taps one 16-byte load of
+    // samples and one broadcast load of taps feed 4 FIR_NPT multiply-adds
+    T X[FIR_NPT + 4], h4[4];
+#pragma unroll
+    for (int g = 0; g < FIR_NPT / 4; ++g) { T v[4]; load4<T>(row + 4 * g, v); X[4 + 4 * g] = v[0]; X[5 + 4 * g] = v[1]; X[6 + 4 * g] = v[2]; X[7 + 4 * g] = v[3]; }
+#pragma unroll 3
+    for (int q = 0; q < nq; ++q) {
+      { T v[4]; load4<T>(row - 4 * q - 4, v); X[0] = v[0]; X[1] = v[1]; X[2] = v[2]; X[3] = v[3]; }   // x[n0-4q-4 .. n0-4q-1]
+      load4<T>(hm + 4 * q, h4);
+      // y[n0+j] += h[k] x[n0 + j - k],  k = 4q + t  ->  X[4 + j - t]; taps in ascending order for every output
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int j = 0; j < FIR_NPT; ++j) acc[j] += h4[t] * X[4 + j - t];
+#pragma unroll
+      for (int i = FIR_NPT + 3; i >= 4; --i) X[i] = X[i - 4];
     }
     T *dst = A + ((size_t)s * M + m) * (F2_L / 2 + a.Ns) + F2_L / 2 + tile0 + n0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { dst[j] = acc[j]; mean[j] += acc[j]; }
+    for (int j = 0; j < FIR_NPT; ++j) { dst[j] = acc[j]; mean[j] += acc[j]; }
   }
   T *F = reinterpret_cast<T *>(a.ws + w.F) + (size_t)s * (F2_L + a.Ns) + F2_L + tile0 + n0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < FIR_NPT; ++j) {
     const T v = mean[j] / (T)M;                    // np.mean(x, axis=1)  (FDGSC.py:138)
     F[j] = v;
     if (a.fix_out) a.fix_out[(size_t)s * a.Ns + tile0 + n0 + j] = (float)v;
