@@ -429,7 +429,7 @@ def run_headline(args, env):
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     algo_bytes = ALGO_BYTES_PER_AUDIO_S * S * (N / FS)
     dom = int(np.argmax(phase))
-    names = ["stft_kernel", "mcspp_fast_kernel" if not args.full_state else "mcspp_kernel", "istft_seq_kernel"]
+    names = ["stft_sq_kernel", "mcspp_fast_kernel" if not args.full_state else "mcspp_kernel", "istft_sq_kernel"]
     traffic, traffic_note = None, "no ncu capture of this build (profiles/traffic.json is keyed by the CUDA sources' sha)"
     flop_bf, pipe_pct = 1928.0, None
     try:
@@ -503,8 +503,10 @@ def run_headline(args, env):
         x_pcm = t.empty((S, M, N), dtype=t.int16, pin_memory=True)
         x_pcm.copy_((x * 32767.0).round_().clamp_(-32768, 32767))   # x is scratch from here on
         y_pcm = t.empty((S, N), dtype=t.int16, pin_memory=True)
+        chain.process_host(x_pcm, y_pcm, slice_frames=cs)         # allocates the staging pipeline copy_only reuses
+        ms_c0 = copy_only(env, chain, x_pcm, y_pcm, cs, args.steps)
         ms_p, wall_p = e2e_run(x_pcm, y_pcm)
-        ms_c = copy_only(env, chain, x_pcm, y_pcm, cs, args.steps)
+        ms_c = min(ms_c0, copy_only(env, chain, x_pcm, y_pcm, cs, args.steps))    # a ceiling: the faster of the passes before / after
         h2d, d2h = int(S * M * N * 2), int(S * N * 2)
         v_pcm, v_copy = audio_step * args.steps / (ms_p / 1e3), audio_step * args.steps / (ms_c / 1e3)
         e2e = {"value": v_pcm, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -515,7 +517,8 @@ def run_headline(args, env):
                "copy_ceiling": {"value": v_copy, "unit": "audio-s/s", "ms_per_step": ms_c / args.steps,
                                 "h2d_GBps_per_gpu": h2d / (ms_c / args.steps / 1e3) / 1e9,
                                 "what": "same pinned buffers, staging buffers, time slices and streams, cudaMemcpy2DAsync only "
-                                        "(H2D and D2H in flight together), wall clock, max over ranks"},
+                                        "(H2D and D2H in flight together), wall clock, max over ranks; the faster of one pass before and "
+                                        "one after the timed call (the host's copy rate varies by ~10 % from pass to pass)"},
                "frac_of_copy_ceiling": v_pcm / v_copy,
                "limiter": ("host->device copies: the call runs at the pace of the bare copies of the same buffers (kernels hidden); "
                            "at N > 1 the per-GPU copy rate (copy_ceiling.h2d_GBps_per_gpu) drops below one link's ~54 GB/s because all "

@@ -17,14 +17,14 @@ tj = json.load(open(path))
 for r in rows[2:]:
     rec = dict(zip(hdr, r))
     kn = rec["Kernel Name"]
-    key = next((k for k in ("mcspp_fast_kernel", "stft_sq_kernel", "stft_kernel", "istft_seq_kernel") if k in kn), None)
+    key = next((k for k in ("mcspp_fast_kernel", "stft_sq_kernel", "istft_sq_kernel", "stft_kernel", "istft_seq_kernel") if k in kn), None)
     if key is None:
         continue
     units = dict(zip(hdr, rows[1]))
     def gb(metric):
         v = float(rec[metric]); u = units[metric]
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-    d = tj.setdefault("stft_kernel" if key == "stft_sq_kernel" else key, {})
+    d = tj.setdefault(key, {})
     d["dram_bytes_per_stream_10s"] = (gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")) / S
     d["capture"] = "%s (S=%d)" % (name, S)
     if key == "mcspp_fast_kernel":
