@@ -25,10 +25,18 @@ template <int M> __host__ __device__ constexpr int psym(int i, int j) { return i
 // negated on the way out.  Compared with Cholesky (U, U^-1, U^-1 U^-T) the dependent
 // chain per pivot is one reciprocal + two FMA levels, and the 28 rank-1 updates of a
 // pivot are independent -- this is what the fp64 pipe needs at 2-3 warps per scheduler.
+#ifndef DS_CHAIN_RCP1
+#define DS_CHAIN_RCP1 0
+#endif
+#if DS_CHAIN_RCP1
+#define CHAIN_RCP rcp_pos_1ulp
+#else
+#define CHAIN_RCP rcp_pos
+#endif
 template <int M> __device__ __forceinline__ void spd_inverse_packed(double (&a)[M * (M + 1) / 2]) {
   sfor<0, M>([&](auto kc) {
     constexpr int k = SIDX(kc);
-    const double r = rcp_pos(a[pidx<M>(k, k)]);
+    const double r = CHAIN_RCP(a[pidx<M>(k, k)]);
     double t[M];
     sfor<0, M>([&](auto ic) { constexpr int i = SIDX(ic); if constexpr (i != k) t[i] = a[psym<M>(i, k)] * r; });
     sfor<0, M>([&](auto ic) {
@@ -310,15 +318,15 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
 
     // ---- P6: posterior SPP                                                   :124-138
     const double xi1 = 1.0 + xi;
-    const double rxi1 = rcp_pos(xi1);
-    double p = rcp_pos(1.0 + q * rcp_pos(1.0 - q) * xi1 * exp_nonpos(-1.0 * (gam * rxi1)));
+    const double rxi1 = CHAIN_RCP(xi1);
+    double p = CHAIN_RCP(1.0 + q * CHAIN_RCP(1.0 - q) * xi1 * exp_nonpos(-1.0 * (gam * rxi1)));
     p = fmin(fmax(p, a.p_min), a.p_max);
     p_post = p;
 
     // ---- OMLSA gain and output  Y = (w^H y) G,  w = A a / den                :140-155
     // (ahead of the noise-PSD update in program order: its serial fp32 log/exp chain then overlaps the update's
     //  shared-memory traffic instead of trailing it)
-    double scale = rcp_pos(den);
+    double scale = CHAIN_RCP(den);
     if (a.apply_gain) {
       // the gain only scales the output (no feedback into the recursions): fp32 exp/log are enough
       const float pf = (float)p;
@@ -469,13 +477,13 @@ __device__ __forceinline__ float2 chain_bin_step_v2(const float2 (&yf)[M], float
 
     // ---- posterior SPP                                                       :124-138
     const double xi1 = 1.0 + xi;
-    const double rxi1 = rcp_pos(xi1);
-    double p = rcp_pos(1.0 + q * rcp_pos(1.0 - q) * xi1 * exp_nonpos(-1.0 * (gam * rxi1)));
+    const double rxi1 = CHAIN_RCP(xi1);
+    double p = CHAIN_RCP(1.0 + q * CHAIN_RCP(1.0 - q) * xi1 * exp_nonpos(-1.0 * (gam * rxi1)));
     p = fmin(fmax(p, a.p_min), a.p_max);
     p_post = p;
 
     // ---- OMLSA gain and output  Y = (w^H y) G,  w = A a / den                :140-155
-    double scale = rcp_pos(den);
+    double scale = CHAIN_RCP(den);
     if (a.apply_gain) {
       const float pf = (float)p;
       double G = (double)expf(pf * logf((float)(xi * rxi1)) + (1.0f - pf) * (float)a.logGmin);
