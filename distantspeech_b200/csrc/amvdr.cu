@@ -35,8 +35,14 @@ struct AmvdrArgs {
 // strictly upper entries in qidx order.
 template <int M> __host__ __device__ constexpr int amvdr_state_elems() { return 3 * M * M + 5; }
 
+// resident CTAs per SM the register allocation aims for (the state lives in shared memory: 3 M^2 doubles per thread)
+#ifndef AMVDR_MINB4
+#define AMVDR_MINB4 3          // A/B on the B200 (config 1, ms per step): 2 -> 37.5 (255 registers), 3 -> 33.8 (168), 4 -> 35.5 (128, spills)
+#endif
+template <int M> __host__ __device__ constexpr int amvdr_minb() { return M <= 4 ? AMVDR_MINB4 : (M <= 6 ? 3 : 2); }
+
 template <int M, int NT>
-__global__ void __launch_bounds__(NT) amvdr_kernel(AmvdrArgs a) {
+__global__ void __launch_bounds__(NT, amvdr_minb<M>()) amvdr_kernel(AmvdrArgs a) {
   constexpr int NQ = M * (M - 1) / 2, MM = M * M;
   constexpr int NE = amvdr_state_elems<M>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -62,14 +68,31 @@ __global__ void __launch_bounds__(NT) amvdr_kernel(AmvdrArgs a) {
   const double ay = a.alpha_y, one_m_ay = 1.0 - a.alpha_y, av = a.alpha_v, one_m_av = 1.0 - a.alpha_v;
 
   startup_dephase(8000);
+  // the spectrum of frame t + 1 is loaded while frame t is processed, frames further ahead are pulled into L2
+  // (ncu before: 1.6 long-scoreboard stalls per issue on these loads)
+  const float2 *Xp = a.X + (long long)s * a.T * M * K + k;
+  float2 zn[M], znb0 = make_float2(0.f, 0.f), znb1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < M; ++m) zn[m] = Xp[(long long)m * K];
+  if (k > 0) znb0 = Xp[-1];
+  if (k < K - 1) znb1 = Xp[1];
   for (int t = 0; t < a.T; ++t) {
-    const float2 *Xp = a.X + ((long long)s * a.T + t) * M * K + k;
     double zr[M], zi[M];
 #pragma unroll
-    for (int m = 0; m < M; ++m) { const float2 v = Xp[(long long)m * K]; zr[m] = (double)v.x; zi[m] = (double)v.y; }
-    double Ym1 = 0.0, Yp1 = 0.0;
-    if (k > 0) { const float2 v = Xp[-1]; Ym1 = power_c((double)v.x, (double)v.y); }
-    if (k < K - 1) { const float2 v = Xp[1]; Yp1 = power_c((double)v.x, (double)v.y); }
+    for (int m = 0; m < M; ++m) { zr[m] = (double)zn[m].x; zi[m] = (double)zn[m].y; }
+    const double Ym1 = (k > 0) ? power_c((double)znb0.x, (double)znb0.y) : 0.0;
+    const double Yp1 = (k < K - 1) ? power_c((double)znb1.x, (double)znb1.y) : 0.0;
+    Xp += (long long)M * K;
+    if (t + 1 < a.T) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) zn[m] = Xp[(long long)m * K];
+      if (k > 0) znb0 = Xp[-1];
+      if (k < K - 1) znb1 = Xp[1];
+      if (t + 5 < a.T) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) asm volatile("prefetch.global.L2 [%0];" ::"l"(Xp + (long long)4 * M * K + (long long)m * K));
+      }
+    }
     const double Y0 = power_c(zr[0], zi[0]);
     const bool reset = (frm > 0) && (ell == 0);
     mcra_step(mS, mSmin, mStmp, mp, mlam, Ym1, Y0, Yp1, k, K, frm, reset, a.mc);
