@@ -16,8 +16,32 @@ from .beamformer import beamformer
 from .MicArray import MicArray
 
 
+class _Lazy(object):
+    """A host array that is fetched from the device the first time it is read (a device -> host copy into pageable memory
+    costs more than the whole kernel chain of a batched call, and most callers never look at these attributes)."""
+
+    def __init__(self, fetch):
+        self._fetch, self._value = fetch, None
+
+    def get(self):
+        if self._fetch is not None:
+            self._value, self._fetch = self._fetch(), None
+        return self._value
+
+
+def _lazy_attr(name):
+    def get(self):
+        v = self.__dict__.get(name)
+        return v.get() if isinstance(v, _Lazy) else v
+
+    def set_(self, value):
+        self.__dict__[name] = value
+    return property(get, set_)
+
+
 class _McraView(object):
-    """The ``self.mcra`` attribute of the reference: counters on the host, p on the device."""
+    """The ``self.mcra`` attribute of the reference: counters on the host, p on the device (read back on first access)."""
+    p = _lazy_attr("_p")
 
     def __init__(self):
         self.L = 15
@@ -28,6 +52,8 @@ class _McraView(object):
 
 
 class adaptivebeamfomer(beamformer):
+    H = _lazy_attr("_H")          # weights of the last frame, [M, K] (or [S, M, K]); read back from the device on first access
+
     def __init__(self, mic: MicArray, frameLen=256, hop=None, nfft=None, c=343, r=0.032, fs=16000):
         beamformer.__init__(self, mic=mic, frame_len=frameLen, hop=hop, nfft=nfft, c=c, fs=fs)
         self.M = mic.M
@@ -122,19 +148,25 @@ class adaptivebeamfomer(beamformer):
         T = X.shape[1]
         Y = t.empty((S, T, 1, self.half_bin), dtype=t.complex64, device="cuda")
         Hl = t.empty((S, self.half_bin, M), dtype=t.complex128, device="cuda")
-        pl = t.empty((S, T, self.half_bin), dtype=t.float64, device="cuda")
         prm = self._params(S, T, method)
+        # no per-frame p tap: the reference only keeps the last frame's mcra.p, which is part of the state blob
         L.check(L.lib().ds_amvdr_run(C.byref(prm), L.ptr(self._state), L.ptr(a_dev), L.ptr(X), L.ptr(Y), L.ptr(Hl),
-                                     L.ptr(pl), L.stream_ptr()), "ds_amvdr_run")
+                                     None, L.stream_ptr()), "ds_amvdr_run")
         f, e = C.c_int32(self.mcra.frm_cnt), C.c_int32(self.mcra.ell)
         L.lib().ds_mcra_advance(int(self.mcra.L), T, C.byref(f), C.byref(e))
         self.mcra.frm_cnt, self.mcra.ell = f.value, e.value
         y = istft_device(Y, self.nfft, self.hop, win, L.DS_STFT_STREAMING, tail=self._tail,
                          scale=self.hop / self.transformer.W0)[:, 0, :]
-        Hn = Hl.cpu().numpy()
-        self.H = Hn[0].T if S == 1 else Hn.transpose(0, 2, 1)                     # [M, K]
-        pn = pl[:, -1, :].cpu().numpy()
-        self.mcra.p = pn[0] if S == 1 else pn
+
+        def fetch_H(Hl=Hl, S=S):
+            Hn = Hl.cpu().numpy()
+            return Hn[0].T if S == 1 else Hn.transpose(0, 2, 1)                   # [M, K]
+
+        def fetch_p(st=self._state, S=S, idx=3 * M * M + 3):
+            pn = st.view(t.float64).view(S, -1, self.half_bin)[:, idx, :].cpu().numpy()           # state order: Rvv, Rinv, Ryy, mcra[S, Smin, Stmp, p, lambda]
+            return pn[0] if S == 1 else pn
+        self.H = _Lazy(fetch_H)
+        self.mcra.p = _Lazy(fetch_p)
         beampattern = None
         if retH:
             beampattern = self.beampattern(self.omega, self.H if S == 1 else self.H[0])

@@ -730,7 +730,10 @@ static int launch_istft(const IstftArgs &a, const TwiddleSet &tw, cudaStream_t s
   const int nblk = (a.n_out + a.hop - 1) / a.hop;
 #ifndef DS_ISTFT_NO_SQ
   if constexpr (N == 512 && sizeof(T) == 4) {
-    if (a.hop * 2 == N && (a.mode != DS_STFT_STREAMING || a.tail)) {
+    // the square kernel stores sample pairs: 8-byte aligned float32 (4-byte aligned int16) output and tail rows
+    const bool aligned = (a.y16 ? (reinterpret_cast<size_t>(a.y16) & 3) == 0 : (reinterpret_cast<size_t>(a.y) & 7) == 0) &&
+                         (reinterpret_cast<size_t>(a.tail) & 7) == 0;
+    if (aligned && a.hop * 2 == N && (a.mode != DS_STFT_STREAMING || a.tail)) {
       const long long seqs = (long long)a.S * a.C;
       long long nseg = (2LL * 148 * 16 + seqs - 1) / seqs;
       const long long max_seg = (nblk + 15) / 16;
@@ -1378,7 +1381,7 @@ static int launch_fixedbf(const FixedBfArgs &a0, const TwiddleSet &tw, cudaStrea
     if (a.hop * 2 == N && a.B <= 3) {
       int rc = DS_EUNSUPPORTED;
 #ifndef DS_FIXEDBF_NO_SQ
-      if constexpr (N == 512) rc = a.B == 1 ? launch_fixedbf_sq<1>(a, tw, st) : a.B == 2 ? launch_fixedbf_sq<2>(a, tw, st) : launch_fixedbf_sq<3>(a, tw, st);
+      if constexpr (N == 512) if ((reinterpret_cast<size_t>(a.y) & 7) == 0) rc = a.B == 1 ? launch_fixedbf_sq<1>(a, tw, st) : a.B == 2 ? launch_fixedbf_sq<2>(a, tw, st) : launch_fixedbf_sq<3>(a, tw, st);
 #endif
       if (rc == DS_EUNSUPPORTED) rc = a.B == 1 ? launch_fixedbf_seq<N, 1>(a, tw, st) : a.B == 2 ? launch_fixedbf_seq<N, 2>(a, tw, st) : launch_fixedbf_seq<N, 3>(a, tw, st);
       if (rc == DS_OK) {
