@@ -31,6 +31,9 @@ constexpr int F2_L = 256, F2_N = 512, F2_K = 257, F2_H = 256, F2_FLMAX = 128;
 #ifndef FD_BM_MINB
 #define FD_BM_MINB 3
 #endif
+#ifndef FD_BM_PF
+#define FD_BM_PF "prefetch.global.L2"
+#endif
 #ifndef FD_AIC_MINB
 #define FD_AIC_MINB 4
 #endif
@@ -400,9 +403,9 @@ __global__ void __launch_bounds__(BM_WARPS * 32, FD_BM_MINB) fd_bm_kernel(Fd2Arg
       // next block's operands towards L2 now (ncu: 3.4 long-scoreboard stalls per issue without it): 128-byte lines
       const char *px = reinterpret_cast<const char *>(Xf + (size_t)(b + 1) * K), *pp = reinterpret_cast<const char *>(Pf + (size_t)(b + 1) * K);
       const char *pd = reinterpret_cast<const char *>(xad + (size_t)(b + 1) * L);
-      if (lane * 128 < (int)(K * sizeof(C2))) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + lane * 128));
-      if (lane * 128 < (int)(K * sizeof(T))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + lane * 128));
-      if (lane * 128 < (int)(L * sizeof(T))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + lane * 128));
+      if (lane * 128 < (int)(K * sizeof(C2))) asm volatile(FD_BM_PF " [%0];" ::"l"(px + lane * 128));
+      if (lane * 128 < (int)(K * sizeof(T))) asm volatile(FD_BM_PF " [%0];" ::"l"(pp + lane * 128));
+      if (lane * 128 < (int)(L * sizeof(T))) asm volatile(FD_BM_PF " [%0];" ::"l"(pd + lane * 128));
     }
     // The real-FFT split / merge passes are fused with the elementwise work around them (same operations and rounding as
     // warp_rfft / warp_irfft_unscaled, 15 instead of 22 shared-memory round trips per block): each lane owns the bin
