@@ -5,6 +5,11 @@
 //   istft           transform.py:237-404 + __overlap_add :224-234 (float32 OLA, no window-sum norm)
 //   Transform       transform.py:407-496 (streaming history/tail, hop/W0 scaling :479)
 //   FixedBeamformer beamformer/fixedbeamformer.py:147-207 (Y = sum_m conj(W) X, :163)
+//
+// Two families of kernels: the half-warp "square" transform for n_fft = 512 with the fp32 FFT (stft_sq_kernel,
+// istft_sq_kernel, fixedbf_sq_kernel; fft16.cuh) -- the shape of every BASELINE configuration on this path -- and the
+// Stockham warp transform for every other size and for the fp64 FFT (stft_kernel, istft_seq_kernel / istft_kernel,
+// fixedbf_seq_kernel / fixedbf_kernel; fft.cuh).
 #include "common.cuh"
 #include "fft.cuh"
 #include "fft16.cuh"
