@@ -69,7 +69,11 @@ __device__ __forceinline__ float2 ld_f2_once(const float2 *p) {
 // one 16-byte load for a (re, im) pair: half the L2 sectors of two strided 8-byte loads
 __device__ __forceinline__ double2 ld_f64x2_once(const double *p) {
   double2 v;
+#ifdef DS_A0_EVICT_LAST
+  asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#else
   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#endif
   return v;
 }
 __device__ __forceinline__ double ld_f64_once(const double *p) {
