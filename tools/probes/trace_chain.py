@@ -46,3 +46,23 @@ for s_ in np.unique(sm)[:40]:
 st = np.array(stats)
 print("pairs", len(st), " mean |drift| over the window (frames): %.3f" % np.mean(np.abs(((st[:, 1] - st[:, 0] + 0.5) % 1) - 0.5)))
 print("histogram of offsets at the end of the window:", np.histogram(st[:, 1] % 1, bins=10, range=(0, 1))[0])
+
+# frame time of a warp as a function of the phase offset of the warp that shares its scheduler (only frames during which
+# exactly that one partner was resident on the scheduler for the whole frame)
+bins = [[] for _ in range(10)]
+for s_ in np.unique(sm):
+    idx = np.where(sm == s_)[0]
+    for sched in range(4):
+        grp = idx[(wid[idx] % 4) == sched]
+        for a in grp:
+            A = tr[a, :64]
+            for b in grp:
+                if a == b: continue
+                B = tr[b, :64]
+                for i in range(63):
+                    t0, t1 = A[i], A[i + 1]
+                    jdx = np.searchsorted(B, t0, side="right") - 1
+                    if jdx < 0 or jdx + 2 >= 64: continue
+                    off = (t0 - B[jdx]) / (B[jdx + 1] - B[jdx])      # how far the partner is into its frame when A starts one
+                    bins[min(9, int(off * 10))].append(t1 - t0)
+print("partner's phase at my frame start -> my frame time (cycles): " + "  ".join("%.1f:%.0f(n=%d)" % (i / 10, np.median(b) if b else 0, len(b)) for i, b in enumerate(bins)))
