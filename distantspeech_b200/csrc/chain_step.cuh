@@ -84,6 +84,11 @@ __device__ __forceinline__ double ld_f64_once(const double *p) {
 
 struct McraRegs { double S, Smin, Stmp, p, lam; };
 
+// rendezvous of the two warps that share a scheduler (mcspp_fast.cu): predicated, so the frame body stays one basic block
+__device__ __forceinline__ void pair_sync(int id, bool on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p bar.sync %1, 64;\n\t}" ::"r"((unsigned)on), "r"(id));
+}
+
 // exp(x) for x <= 0 without the library's out-of-range branch: the argument is clamped at -700
 // (exp(-700) ~ 1e-304 is already far below anything that can move the SPP), so 2^n stays a normal
 // number and the scaling is a plain exponent-field add.  Cody-Waite reduction + degree-13 Taylor
@@ -159,10 +164,10 @@ __device__ __forceinline__ void mcra_step_sel(McraRegs &m, double Ym1, double Y0
 // it needs cost more than the 288 DFMA it saves -- and less accurate: 100 dB instead of 108 dB on the synthetic streams,
 // 46 dB (below the 60 dB contract) when Phi_vv is close to singular, because xi and gamma are differences of nearly equal
 // sums (tools/mixed_precision_study.py).  Kept only so the measurement can be repeated.
-template <int M, int NT, bool USE_C, bool MIXED = false>
+template <int M, int NT, bool USE_C, bool MIXED = false, bool PAIRED = false>
 __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 ynb0, float2 ynb1, int k, int K, int frm,
                                                  bool reset, McraRegs &mc, double *smy, double *smv, const double *smc,
-                                                 const double *a0, const McsppArgs &a, double &p_post) {
+                                                 const double *a0, const McsppArgs &a, double &p_post, int mid_bar = 0) {
   constexpr int NP = M * (M + 1) / 2;
     // ---- P1: A = inv(Re Phi_vv + eps I)                                     mcspp_base.py:278
     double A[NP];
@@ -216,6 +221,10 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
 #pragma unroll
     for (int i = 0; i < M; ++i) { if (i & 1) trA2 += A[pidx<M>(i, i)]; else trA += A[pidx<M>(i, i)]; }
     trA += trA2;
+    // rendezvous point of the second warp of a scheduler pair (mcspp_fast.cu; mid_bar = 0: none).  Measured positions
+    // (per-bin ms, default 16.87): after the sweep 16.87, here 16.49, after u = A y 16.49, after pass Z 17.50, after the SPP
+    // chain 17.99, before the noise update 17.67
+    if constexpr (PAIRED) pair_sync(mid_bar, mid_bar != 0);
 
     // ---- u = A y, numerator a^H u, s_yu = Re(y^H u) = y^H A y, uu = |u|^2     :282-284, beamformer.py:152
     double ur[M], ui[M];

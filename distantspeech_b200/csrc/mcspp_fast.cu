@@ -39,7 +39,11 @@ __device__ long long g_trace[8192 * 66];
 
 // TAP_P: also write the posterior p per frame (the mask of the mask-based beamformers); a separate instantiation,
 // because even a predicated-off store costs the headline kernel 2 % (registers: 16.84 -> 17.17 ms measured)
-template <int M, int NT, int MINB, bool TAP_P, bool MIXED = false>
+// PAIRED: 256-thread CTAs (one per SM); warps w and w + 4 share a scheduler and meet once per frame at a named barrier, one
+// at its frame start, the other after the MVDR denominator -- which pins their phase offset at a favourable value (the
+// frame time of a warp depends on where its scheduler partner is: profiles/ab_runs_r02.txt) instead of letting it wander:
+// 16.87 -> 16.49 ms.  No thread may leave early then: threads past the end redo the last item.
+template <int M, int NT, int MINB, bool TAP_P, bool MIXED = false, bool PAIRED = false>
 __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
   constexpr bool USE_C = DS_FAST_USE_C != 0;
   constexpr int NP = M * (M + 1) / 2;
@@ -50,8 +54,12 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
   const int tid = threadIdx.x;
   const int K = a.K;
   const int Kp = K - a.k_first;
-  const long long g = (long long)blockIdx.x * NT + tid;
-  if (g >= (long long)a.S * Kp) return;          // threads are independent: no block-wide sync below
+  long long g = (long long)blockIdx.x * NT + tid;
+  if (g >= (long long)a.S * Kp) {
+    // PAIRED: nobody may leave before the last rendezvous -- threads past the end redo the last item (same inputs, same
+    // results, the same values stored twice); otherwise threads are independent and simply leave
+    if constexpr (PAIRED) g = (long long)a.S * Kp - 1; else return;
+  }
   const int s = (int)(g / Kp), k = a.k_first + (int)(g % Kp);
   double *blob = a.state + (long long)s * NE * K + k;
   double *smy = sm + tid;                 // Phi_yy (real part), element e at smy[e * NT]
@@ -80,7 +88,7 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
 
   McraRegs mc = {mS, mSmin, mStmp, mp, mlam};
 #if DS_FAST_SKEW > 0
-  {
+  if constexpr (!PAIRED) {
     // De-phase the CTAs once at start-up: every warp runs the same ~1800-instruction frame body, and warps that
     // start together stay in lock-step for a long time (same phase => they want the fp64 pipe, the LSU and the
     // MUFU at the same moments).  A pseudo-random delay of 0..7/8 of a frame time per warp costs < 4 us per CTA
@@ -91,8 +99,11 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
     while (clock64() - t0 < wait) { }
   }
 #endif
+  const int pair_bar = 1 + ((tid >> 5) & 3);     // PAIRED: warps w and w + 4 of the CTA
+  const bool role_b = (tid >> 5) >= 4;
 #pragma unroll 1
   for (int t = 0; t < a.T; ++t) {
+    if constexpr (PAIRED) pair_sync(pair_bar, !role_b);
     // issue the loads of this frame's spectrum first: they are consumed only after the matrix
     // inverse, so the HBM latency hides behind the Gauss-Jordan sweeps
 #ifdef DS_FAST_TRACE
@@ -123,15 +134,17 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
     const bool reset = (frm > 0) && (ell_mod == 0);
     double p_post;
 #if DS_CHAIN_V2
-    *Yp = chain_bin_step_v2<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
+    const float2 yo = chain_bin_step_v2<M, NT, USE_C>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
 #else
-    *Yp = chain_bin_step<M, NT, USE_C, MIXED>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post);
+    const float2 yo = chain_bin_step<M, NT, USE_C, MIXED, PAIRED>(yf, ynb0, ynb1, k, K, frm, reset, mc, smy, smv, smc, a0, a, p_post,
+                                                                  (PAIRED && role_b) ? pair_bar : 0);
 #endif
+    *Yp = yo;
     if constexpr (TAP_P) a.tp[((long long)s * a.T + t) * K + k] = p_post;     // the only tap this kernel serves
+    if (a.k_first == 2 && k == 2) { Yp[-1] = make_float2(0.f, 0.f); Yp[-2] = make_float2(0.f, 0.f); }
     if (reset) ell = 0;
     ++ell; ++frm;
     ell_mod = (ell_mod + 1 == a.mc.L) ? 0 : ell_mod + 1;
-    if (a.k_first == 2 && k == 2) { Yp[-1] = make_float2(0.f, 0.f); Yp[-2] = make_float2(0.f, 0.f); }
     Yp += K;
   }
   mS = mc.S; mSmin = mc.Smin; mStmp = mc.Stmp; mp = mc.p; mlam = mc.lam;
@@ -144,12 +157,18 @@ __global__ void DS_FAST_BOUNDS mcspp_fast_kernel(McsppArgs a) {
 
 template <int M>
 static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
+#if !defined(DS_FAST_NT) && !defined(DS_FAST_NOPAIR) && !defined(DS_CHAIN_MIXED) && !DS_CHAIN_V2
+  // 8 microphones (the headline): one 256-thread CTA per SM with paired warps -- see mcspp_fast_kernel
+  constexpr bool PAIRED = (M == 8) && (DS_FAST_USE_C != 0);
+#else
+  constexpr bool PAIRED = false;
+#endif
 #ifndef DS_FAST_NT
 #define DS_FAST_NT 64
 #endif
-  constexpr int NT = DS_FAST_NT;
+  constexpr int NT = PAIRED ? 256 : DS_FAST_NT;
   constexpr int NP = M * (M + 1) / 2;
-  constexpr int MINB = DS_FAST_MINB; // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
+  constexpr int MINB = PAIRED ? 1 : DS_FAST_MINB; // 4 x 64 threads at <= 255 registers: fewer spills beat more warps here (measured)
 #ifndef DS_FAST_SMEM_PAD_KB
 #define DS_FAST_SMEM_PAD_KB 0     // occupancy experiments only: extra dynamic shared memory per CTA
 #endif
@@ -157,7 +176,7 @@ static int launch_fast_m(const McsppArgs &a, cudaStream_t st) {
 #ifdef DS_CHAIN_MIXED      // A/B build only (tools/build_variant.sh x mcspp_fast.cu -DDS_CHAIN_MIXED): see chain_step.cuh
   auto kern = a.tp ? mcspp_fast_kernel<M, NT, MINB, true> : mcspp_fast_kernel<M, NT, MINB, false, true>;
 #else
-  auto kern = a.tp ? mcspp_fast_kernel<M, NT, MINB, true> : mcspp_fast_kernel<M, NT, MINB, false>;
+  auto kern = a.tp ? mcspp_fast_kernel<M, NT, MINB, true, false, PAIRED> : mcspp_fast_kernel<M, NT, MINB, false, false, PAIRED>;
 #endif
   DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)a.S * (a.K - a.k_first);
