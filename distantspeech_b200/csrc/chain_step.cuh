@@ -18,6 +18,11 @@ template <int B, int E, typename F> __device__ __forceinline__ void sfor(F &&f) 
 }
 #define SIDX(ic) (decltype(ic)::value)
 
+// rendezvous of the two warps that share a scheduler (mcspp_fast.cu): predicated, so the frame body stays one basic block
+__device__ __forceinline__ void pair_sync(int id, bool on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p bar.sync %1, 64;\n\t}" ::"r"((unsigned)on), "r"(id));
+}
+
 template <int M> __host__ __device__ constexpr int psym(int i, int j) { return i <= j ? pidx<M>(i, j) : pidx<M>(j, i); }
 
 // In-place inverse of an SPD matrix in packed upper storage by symmetric Gauss-Jordan
@@ -84,10 +89,7 @@ __device__ __forceinline__ double ld_f64_once(const double *p) {
 
 struct McraRegs { double S, Smin, Stmp, p, lam; };
 
-// rendezvous of the two warps that share a scheduler (mcspp_fast.cu): predicated, so the frame body stays one basic block
-__device__ __forceinline__ void pair_sync(int id, bool on) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p bar.sync %1, 64;\n\t}" ::"r"((unsigned)on), "r"(id));
-}
+
 
 // exp(x) for x <= 0 without the library's out-of-range branch: the argument is clamped at -700
 // (exp(-700) ~ 1e-304 is already far below anything that can move the SPP), so 2^n stays a normal
@@ -222,8 +224,8 @@ __device__ __forceinline__ float2 chain_bin_step(const float2 (&yf)[M], float2 y
     for (int i = 0; i < M; ++i) { if (i & 1) trA2 += A[pidx<M>(i, i)]; else trA += A[pidx<M>(i, i)]; }
     trA += trA2;
     // rendezvous point of the second warp of a scheduler pair (mcspp_fast.cu; mid_bar = 0: none).  Measured positions
-    // (per-bin ms, default 16.87): after the sweep 16.87, here 16.49, after u = A y 16.49, after pass Z 17.50, after the SPP
-    // chain 17.99, before the noise update 17.67
+    // (per-bin ms, unpaired 16.87): in the middle of the sweep 16.82, after the sweep 16.87, here 16.49 (16.43 in the final form),
+    // after u = A y 16.49, after pass X 17.46, after pass Z 17.50, after the SPP chain 17.99, before the noise update 17.67
     if constexpr (PAIRED) pair_sync(mid_bar, mid_bar != 0);
 
     // ---- u = A y, numerator a^H u, s_yu = Re(y^H u) = y^H A y, uu = |u|^2     :282-284, beamformer.py:152
