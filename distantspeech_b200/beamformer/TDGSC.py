@@ -4,7 +4,9 @@ Per block of ``frameLen`` samples: DC notch, time alignment, mean fixed beam, MC
 fixed beam, pairwise-difference blocking matrix, and the constrained FDAF canceller ``FastFreqLms.update`` (non-causal,
 taps truncated by 30, gated per bin by 1 - p).  The stages feed forward, so each runs over the whole call as one
 launch (FIR, channel mean, adjacent difference, STFT, MCRA, ``ds_fdaf_run``), all on the device.
-``postfilter=True`` (NsOmlsaMulti on the output, :159-170) is not built.  Compiled for frameLen = 256.
+``postfilter=True`` (:157-170) runs NsOmlsaMulti on the spectra of the output and of the blocking outputs and
+resynthesises the gained output through the streaming transform -- also feed-forward (the canceller never sees the
+post-filtered signal), so it is four more launches over the whole call.  Compiled for frameLen = 256.
 Extension: a leading stream axis ``x [S, N, M]``.
 """
 import ctypes as C
@@ -13,7 +15,8 @@ import numpy as np
 
 from .. import _lib as L
 from ..noise_estimation.mcra import NoiseEstimationMCRA
-from ..transform.transform import _sqrt_hann, stft_device
+from ..noise_estimation.omlsa_multi import NsOmlsaMulti
+from ..transform.transform import _sqrt_hann, stft_device, istft_device
 from .FDGSC import TimeAlignment
 from .MicArray import MicArray
 from .beamformer import beamformer
@@ -50,6 +53,7 @@ class TDGSC(beamformer):
         self.mcra = NoiseEstimationMCRA(nfft=frameLen * 2)
         self.mcra.L = 65
         self.spp = self.mcra
+        self.omlsa_multi = NsOmlsaMulti(nfft=frameLen * 2, cal_weights=True, M=self.M)
         self.mu, self.alpha, self.fir_truncate = 0.01, 0.9, 30
         self._gated, self._non_causal = True, True        # GSC.process1 runs the same chain ungated and causal
         self._st = None
@@ -60,6 +64,7 @@ class TDGSC(beamformer):
         self.mcra = NoiseEstimationMCRA(nfft=self.frameLen * 2)
         self.mcra.L = 65
         self.spp = self.mcra
+        self.omlsa_multi = NsOmlsaMulti(nfft=self.frameLen * 2, cal_weights=True, M=self.M)
 
     def _ensure(self, S):
         t = L.require_cuda()
@@ -70,6 +75,7 @@ class TDGSC(beamformer):
             self.reset()
             self._st = dict(S=S, notch=z(S, M, 2, dt=t.float64), fir=z(S, M, self.time_alignment.delay_filter_len - 1, dt=t.float64),
                             h_fbf=z(S, 1, Lf),
+                            h_pf_y=z(S, 1, Lf), h_pf_u=z(S, M - 1, Lf), t_pf=z(S, 1, Lf),      # postfilter transforms (:40-41)
                             fdaf=t.zeros(L.lib().ds_fdaf_state_bytes(S, M - 1), dtype=t.uint8, device="cuda"))
         return self._st
 
@@ -87,8 +93,6 @@ class TDGSC(beamformer):
     def process(self, x, postfilter=False):
         """x [samples, chs] (or [S, samples, chs]) -> (output, p [257, n_blocks], output_bm [samples, chs-1]);
         the caller's array ends up DC-notched (:130-131)."""
-        if postfilter:
-            raise NotImplementedError("TDGSC postfilter=True is not built")
         t = L.require_cuda()
         as_torch = isinstance(x, t.Tensor)
         xd = L.to_device(x, t.float32)
@@ -138,6 +142,19 @@ class TDGSC(beamformer):
                                float(self.mu), float(self.alpha))
             L.check(lib.ds_fdaf_run(C.byref(prm), L.ptr(st["fdaf"]), L.ptr(bm), L.ptr(fbf32.contiguous()), L.ptr(p), L.ptr(e), sp),
                     "ds_fdaf_run")
+            if postfilter:
+                # Y = transform_fbf.stft(output_n), U = transform_bm.stft(bm_output), NsOmlsaMulti on their powers,
+                # Y *= sqrt(G), output_n = transform_fbf.istft(Y)                                            (:157-170)
+                win = L.device_window(_sqrt_hann(2 * Lf), 2 * Lf)
+                Yd = stft_device(e[:, None, :].contiguous(), 2 * Lf, Lf, win, L.DS_STFT_STREAMING, history=st["h_pf_y"])   # [S, T, 1, K]
+                Ud = stft_device(bm.contiguous(), 2 * Lf, Lf, win, L.DS_STFT_STREAMING, history=st["h_pf_u"])              # [S, T, M-1, K]
+                G, lam, pp = self.omlsa_multi._run(L.spectral_power(Yd).view(S, T, K), L.spectral_power(Ud))
+                last = [v[0, -1] if S == 1 else v[:, -1] for v in (G, lam, pp)]
+                self.omlsa_multi.G, self.omlsa_multi.lambda_d, self.omlsa_multi.p = (v.cpu().numpy() for v in last)
+                Yg = t.empty((S, T, 1, K), dtype=t.complex128, device="cuda")
+                L.check(lib.ds_spectral_gain_run(S * T * K, L.ptr(Yd), 0, L.ptr(G), 1, L.ptr(Yg), sp), "ds_spectral_gain_run")
+                e = istft_device(Yg, 2 * Lf, Lf, win, L.DS_STFT_STREAMING, tail=st["t_pf"],
+                                 scale=Lf / float(np.sum(_sqrt_hann(2 * Lf) ** 2)))[:, 0, :]
             out[:, :Nb] = e.double()
             out_bm[:, :Nb] = bm.permute(0, 2, 1).double()
             if p is not None:

@@ -747,6 +747,24 @@ def test_subband_rls_golden(cuda):
         SubbandRLS(filter_len=5)
 
 
+def test_tdgsc_postfilter_golden(cuda):
+    # postfilter=True (TDGSC.py:157-170): NsOmlsaMulti gain on the output through the streaming transforms, state carried
+    # across two calls; batch == single
+    from distantspeech_b200.beamformer.MicArray import MicArray
+    from distantspeech_b200.beamformer.TDGSC import TDGSC
+    g = golden("tdgsc_postfilter.npz")
+    n1 = int(g["n_first"])
+    td = TDGSC(MicArray(arrayType="circular", r=0.032, M=4), frameLen=256, angle=[30, 0])
+    ra, rb = td.process(g["x"][:n1].copy(), postfilter=True), td.process(g["x"][n1:].copy(), postfilter=True)
+    err, snr = assert_wave_parity(g["y"], np.concatenate([ra[0], rb[0]]), "TDGSC postfilter")
+    print("TDGSC postfilter: max-abs %.2e SNR %.1f dB" % (err, snr))
+    assert np.max(np.abs(td.omlsa_multi.G - g["G_last"])) < 1e-3
+    xb = np.stack([g["x"], g["x"][::-1].copy()])
+    yb = TDGSC(MicArray(arrayType="circular", r=0.032, M=4), frameLen=256, angle=[30, 0]).process(xb.copy(), postfilter=True)[0]
+    y0 = TDGSC(MicArray(arrayType="circular", r=0.032, M=4), frameLen=256, angle=[30, 0]).process(g["x"].copy(), postfilter=True)[0]
+    assert np.max(np.abs(yb[0] - y0)) < 1e-6
+
+
 def test_tdgsc_golden(cuda):
     from distantspeech_b200.beamformer.MicArray import MicArray
     from distantspeech_b200.beamformer.TDGSC import TDGSC

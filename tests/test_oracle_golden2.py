@@ -100,6 +100,17 @@ def test_subband_rls_golden():
     assert np.array_equal(err, g["err"]) and np.array_equal(o.W, g["W_last"]) and np.array_equal(o.P, g["P_last"])
 
 
+def test_tdgsc_postfilter_golden():
+    # TDGSC.process(postfilter=True) (TDGSC.py:157-170): NsOmlsaMulti gain on the output, two calls on one object
+    g = golden("tdgsc_postfilter.npz")
+    o = O.TdgscOracle(O.MicGeometry("circular", r=0.032, M=4, n_fft=256), 256, np.array([30, 0]) / 180 * np.pi)
+    n1 = int(g["n_first"])
+    x = g["x"].astype(np.float64)
+    a, b = o.process(x[:n1], postfilter=True), o.process(x[n1:], postfilter=True)
+    assert np.max(np.abs(np.concatenate([a[0], b[0]]) - g["y"])) < 1e-12
+    assert np.allclose(o.omlsa_multi.G, g["G_last"], rtol=1e-9) and np.allclose(o.omlsa_multi.lambda_d, g["lambda_last"], rtol=1e-9)
+
+
 def test_tdgsc_golden():
     g = golden("tdgsc.npz")
     o = O.TdgscOracle(O.MicGeometry("circular", r=0.032, M=4, n_fft=256), 256, np.array([30, 0]) / 180 * np.pi)
